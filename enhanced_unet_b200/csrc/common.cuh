@@ -1,0 +1,89 @@
+// Shared device/host helpers for the Enhanced-UNet B200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace eunet {
+
+// ---- error reporting (C-ABI: 0 = ok, negative = error; message via eunet_last_error()) ----
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);   // cudaPeekAtLastError based; sets error text
+
+#define EUNET_REQUIRE(cond, ...)                      \
+  do {                                                \
+    if (!(cond)) {                                    \
+      ::eunet::set_error(__VA_ARGS__);                \
+      return -1;                                      \
+    }                                                 \
+  } while (0)
+
+constexpr int kNumSMs = 148;
+
+enum DType : int { kF32 = 0, kBF16 = 1 };
+
+// ---- element access: 8 consecutive channels as fp32, from fp32 or bf16 storage ----
+struct F8 {
+  float v[8];
+};
+
+__device__ __forceinline__ F8 load8(const float* p) {
+  F8 r;
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ F8 load8(const __nv_bfloat16* p) {
+  F8 r;
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    r.v[2 * i] = __uint_as_float(w[i] << 16);
+    r.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+  return r;
+}
+__device__ __forceinline__ void store8(float* p, const F8& r) {
+  *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits), .y = hi
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const F8& r) {
+  uint4 u;
+  u.x = pack_bf16x2(r.v[0], r.v[1]);
+  u.y = pack_bf16x2(r.v[2], r.v[3]);
+  u.z = pack_bf16x2(r.v[4], r.v[5]);
+  u.w = pack_bf16x2(r.v[6], r.v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ float to_f32(float x) { return x; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 x) { return __bfloat162float(x); }
+template <typename T> __device__ __forceinline__ T from_f32(float x);
+template <> __device__ __forceinline__ float from_f32<float>(float x) { return x; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+
+// value after a round trip through the storage type (so that statistics / masks computed from
+// fp32 accumulators agree with what later kernels read back)
+template <typename T> __device__ __forceinline__ float round_to(float x) { return to_f32(from_f32<T>(x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline int clamp_grid(long long want, int per_sm = 8) {
+  long long cap = (long long)kNumSMs * per_sm;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+}  // namespace eunet

@@ -1,0 +1,21 @@
+// Internal declarations shared by the convolution translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace eunet {
+
+// fp32 CUDA-core path (conv_direct.cu)
+int conv3x3_fwd_f32(const float* x, int ldx, const float* w, float* y, int ldy, int B, int H, int W, int Cin, int Cout,
+                    double* stats, const float* scale, const float* shift, int relu, cudaStream_t st);
+int conv3x3_wgrad_f32(const float* x, int ldx, const float* dy, int lddy, float* dw, int B, int H, int W, int Cin, int Cout,
+                      cudaStream_t st);
+
+// Power-of-two (bw, bh, bb) with bw*bh*bb == pixels minimising the number of tiles over a [B,H,W] image batch.
+struct PixelTile {
+  int bw, bh, bb;
+  int tiles_x, tiles_y, tiles_b;
+  long long tiles() const { return (long long)tiles_x * tiles_y * tiles_b; }
+};
+PixelTile choose_pixel_tile(int B, int H, int W, int pixels);
+
+}  // namespace eunet

@@ -1,0 +1,562 @@
+// Bandwidth-bound kernels of the hot path: BatchNorm (finalize / apply+ReLU(+pool) / backward),
+// 2x2 max-pool, bilinear x2 upsample (forward + adjoint), layout packing.  NHWC, 8 channels
+// (128 bit for bf16) per thread access, fp32 math, fp64 cross-CTA accumulation.
+#include "common.cuh"
+#include "../../include/eunet.h"
+
+namespace eunet {
+
+#define DISPATCH_DTYPE(dtype, ...)                          \
+  do {                                                      \
+    if ((dtype) == EUNET_BF16) {                            \
+      using T = __nv_bfloat16;                              \
+      __VA_ARGS__;                                          \
+    } else if ((dtype) == EUNET_F32) {                      \
+      using T = float;                                      \
+      __VA_ARGS__;                                          \
+    } else {                                                \
+      set_error("unknown dtype %d", (int)(dtype));          \
+      return -1;                                            \
+    }                                                       \
+  } while (0)
+
+static inline int ew_grid(long long items, int threads = 256) {
+  long long blocks = (items + threads - 1) / threads;
+  long long cap = (long long)kNumSMs * 16;
+  return (int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm finalize / eval fold
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, long long count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, const float* __restrict__ conv_bias,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   long long* __restrict__ nbt, float momentum, float eps, float* __restrict__ scale,
+                                   float* __restrict__ shift, float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                                   int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && nbt != nullptr) *nbt += 1;
+  if (c >= C) return;
+  const double n = (double)count;
+  const double mean = stats[c] / n;
+  double var = stats[C + c] / n - mean * mean;   // biased variance of the bias-free conv output
+  if (var < 0.0) var = 0.0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = gamma[c];
+  const float sc = g * invstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - (float)mean * sc;          // the conv bias cancels inside train-mode BN
+  mean_out[c] = (float)mean;
+  invstd_out[c] = invstd;
+  if (running_mean != nullptr) {
+    const double b = conv_bias ? (double)conv_bias[c] : 0.0;
+    const double unbiased = count > 1 ? var * n / (n - 1.0) : var;
+    running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * (mean + b));
+    running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unbiased);
+  }
+}
+
+__global__ void bn_fold_eval_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ conv_bias, const float* __restrict__ rm,
+                                    const float* __restrict__ rv, float eps, float* __restrict__ scale,
+                                    float* __restrict__ shift, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sc = gamma[c] / sqrtf(rv[c] + eps);
+  const float b = conv_bias ? conv_bias[c] : 0.f;
+  scale[c] = sc;
+  shift[c] = beta[c] + (b - rm[c]) * sc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BN apply + ReLU (+ fused 2x2 max-pool)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void bn_apply_relu_kernel(const T* __restrict__ y, int ldy, T* __restrict__ out, int ldo, long long M, int C,
+                                     const float* __restrict__ scale, const float* __restrict__ shift) {
+  const int G = C >> 3;
+  const long long items = M * G;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % G);
+    const long long p = i / G;
+    F8 v = load8(y + p * ldy + cg * 8);
+    const F8 sc = load8(scale + cg * 8), sh = load8(shift + cg * 8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v.v[k] = fmaxf(fmaf(v.v[k], sc.v[k], sh.v[k]), 0.f);
+    store8(out + p * ldo + cg * 8, v);
+  }
+}
+
+template <typename T>
+__global__ void bn_apply_relu_pool_kernel(const T* __restrict__ y, int ldy, T* __restrict__ out, int ldo,
+                                          T* __restrict__ pooled, int ldp, int B, int H, int W, int C,
+                                          const float* __restrict__ scale, const float* __restrict__ shift) {
+  const int G = C >> 3, Hp = H >> 1, Wp = W >> 1;
+  const long long items = (long long)B * Hp * Wp * G;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % G);
+    long long q = i / G;
+    const int px = (int)(q % Wp); q /= Wp;
+    const int py = (int)(q % Hp);
+    const int b = (int)(q / Hp);
+    const F8 sc = load8(scale + cg * 8), sh = load8(shift + cg * 8);
+    F8 m;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m.v[k] = 0.f;   // post-ReLU values are >= 0
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const long long p = ((long long)b * H + (2 * py + dy)) * W + (2 * px + dx);
+        F8 v = load8(y + p * ldy + cg * 8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          v.v[k] = fmaxf(fmaf(v.v[k], sc.v[k], sh.v[k]), 0.f);
+          // the pooled value must equal the max of the STORED (rounded) activations
+          m.v[k] = fmaxf(m.v[k], round_to<T>(v.v[k]));
+        }
+        store8(out + p * ldo + cg * 8, v);
+      }
+    const long long pp = ((long long)b * Hp + py) * Wp + px;
+    store8(pooled + pp * ldp + cg * 8, m);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// max-pool 2x2
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void maxpool2_fwd_kernel(const T* __restrict__ x, int ldx, T* __restrict__ out, int ldo, int B, int H, int W,
+                                    int C) {
+  const int G = C >> 3, Hp = H >> 1, Wp = W >> 1;
+  const long long items = (long long)B * Hp * Wp * G;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % G);
+    long long q = i / G;
+    const int px = (int)(q % Wp); q /= Wp;
+    const int py = (int)(q % Hp);
+    const int b = (int)(q / Hp);
+    F8 m;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const long long p = ((long long)b * H + (2 * py + dy)) * W + (2 * px + dx);
+        const F8 v = load8(x + p * ldx + cg * 8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m.v[k] = (dy == 0 && dx == 0) ? v.v[k] : ((v.v[k] > m.v[k]) ? v.v[k] : m.v[k]);
+      }
+    store8(out + (((long long)b * Hp + py) * Wp + px) * ldo + cg * 8, m);
+  }
+}
+
+template <typename T, bool ACC>
+__global__ void maxpool2_bwd_kernel(const T* __restrict__ dpool, int ldp, const T* __restrict__ x, int ldx, T* __restrict__ dx,
+                                    int lddx, int B, int H, int W, int C) {
+  const int G = C >> 3, Hp = H >> 1, Wp = W >> 1;
+  const long long items = (long long)B * Hp * Wp * G;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % G);
+    long long q = i / G;
+    const int px = (int)(q % Wp); q /= Wp;
+    const int py = (int)(q % Hp);
+    const int b = (int)(q / Hp);
+    const F8 g = load8(dpool + (((long long)b * Hp + py) * Wp + px) * ldp + cg * 8);
+    F8 v[4];
+    long long pos[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      pos[w] = ((long long)b * H + (2 * py + (w >> 1))) * W + (2 * px + (w & 1));
+      v[w] = load8(x + pos[w] * ldx + cg * 8);
+    }
+    int arg[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {   // first maximum in row-major window order (ATen: val > maxval)
+      float m = v[0].v[k];
+      int a = 0;
+#pragma unroll
+      for (int w = 1; w < 4; ++w)
+        if (v[w].v[k] > m) { m = v[w].v[k]; a = w; }
+      arg[k] = a;
+    }
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      F8 o;
+      if (ACC) o = load8(dx + pos[w] * lddx + cg * 8);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float add = (arg[k] == w) ? g.v[k] : 0.f;
+        o.v[k] = ACC ? o.v[k] + add : add;
+      }
+      store8(dx + pos[w] * lddx + cg * 8, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bilinear x2 upsample, align_corners=False.  Output rows 2k / 2k+1 of input row k:
+//   out[2k]   = .25*in[k-1] + .75*in[k]   (k = 0: in[0]);   out[2k+1] = .75*in[k] + .25*in[k+1]  (k = H-1: in[H-1])
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void upsample2_fwd_kernel(const T* __restrict__ x, int ldx, T* __restrict__ out, int ldo, int B, int H, int W,
+                                     int C) {
+  const int G = C >> 3;
+  const long long items = (long long)B * H * W * G;
+  const int Wo = 2 * W, Ho = 2 * H;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % G);
+    long long q = i / G;
+    const int j = (int)(q % W); q /= W;
+    const int k = (int)(q % H);
+    const int b = (int)(q / H);
+    const float wxp = j > 0 ? 0.25f : 0.f, wxc0 = j > 0 ? 0.75f : 1.f;
+    const float wxn = j < W - 1 ? 0.25f : 0.f, wxc1 = j < W - 1 ? 0.75f : 1.f;
+    const float wyp = k > 0 ? 0.25f : 0.f, wyc0 = k > 0 ? 0.75f : 1.f;
+    const float wyn = k < H - 1 ? 0.25f : 0.f, wyc1 = k < H - 1 ? 0.75f : 1.f;
+    const int jm = j > 0 ? j - 1 : 0, jp = j < W - 1 ? j + 1 : W - 1;
+    F8 h0[3], h1[3];   // horizontally interpolated rows k-1, k, k+1 for output columns 2j and 2j+1
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      int kk = k + r - 1;
+      kk = kk < 0 ? 0 : (kk > H - 1 ? H - 1 : kk);
+      const T* row = x + (((long long)b * H + kk) * W) * ldx + cg * 8;
+      const F8 a = load8(row + (long long)jm * ldx), c = load8(row + (long long)j * ldx), d = load8(row + (long long)jp * ldx);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        h0[r].v[e] = wxp * a.v[e] + wxc0 * c.v[e];
+        h1[r].v[e] = wxc1 * c.v[e] + wxn * d.v[e];
+      }
+    }
+    F8 o00, o01, o10, o11;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      o00.v[e] = wyp * h0[0].v[e] + wyc0 * h0[1].v[e];
+      o01.v[e] = wyp * h1[0].v[e] + wyc0 * h1[1].v[e];
+      o10.v[e] = wyc1 * h0[1].v[e] + wyn * h0[2].v[e];
+      o11.v[e] = wyc1 * h1[1].v[e] + wyn * h1[2].v[e];
+    }
+    T* o = out + (((long long)b * Ho + 2 * k) * Wo + 2 * j) * ldo + cg * 8;
+    store8(o, o00);
+    store8(o + ldo, o01);
+    store8(o + (long long)Wo * ldo, o10);
+    store8(o + (long long)Wo * ldo + ldo, o11);
+  }
+}
+
+// adjoint: input pixel (k,j) gathers output rows 2k-1..2k+2 with weights [.25,.75,.75,.25] (edges: see header)
+template <typename T>
+__global__ void upsample2_bwd_kernel(const T* __restrict__ dout, int ldo, T* __restrict__ dx, int ldx, int B, int H, int W,
+                                     int C) {
+  const int G = C >> 3;
+  const long long items = (long long)B * H * W * G;
+  const int Wo = 2 * W, Ho = 2 * H;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % G);
+    long long q = i / G;
+    const int j = (int)(q % W); q /= W;
+    const int k = (int)(q % H);
+    const int b = (int)(q / H);
+    const float wy[4] = {k > 0 ? 0.25f : 0.f, k > 0 ? 0.75f : 1.f, k < H - 1 ? 0.75f : 1.f, k < H - 1 ? 0.25f : 0.f};
+    const float wx[4] = {j > 0 ? 0.25f : 0.f, j > 0 ? 0.75f : 1.f, j < W - 1 ? 0.75f : 1.f, j < W - 1 ? 0.25f : 0.f};
+    F8 acc;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc.v[e] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (wy[r] == 0.f) continue;
+      const int oy = 2 * k - 1 + r;
+      F8 rowacc;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) rowacc.v[e] = 0.f;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        if (wx[s] == 0.f) continue;
+        const int ox = 2 * j - 1 + s;
+        const F8 g = load8(dout + (((long long)b * Ho + oy) * Wo + ox) * ldo + cg * 8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) rowacc.v[e] += wx[s] * g.v[e];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc.v[e] += wy[r] * rowacc.v[e];
+    }
+    store8(dx + (((long long)b * H + k) * W + j) * ldx + cg * 8, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm + ReLU backward
+// ------------------------------------------------------------------------------------------------
+// Block = 256 threads = G channel groups x R pixel lanes (G = C/8 divides 256).
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const T* __restrict__ dact, int ldd, const T* __restrict__ y, int ldy, long long M, int C,
+                     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                     const float* __restrict__ invstd, double* __restrict__ sums) {
+  __shared__ float red[2][256 * 8];
+  const int G = C >> 3, R = 256 / G;
+  const int cg = threadIdx.x % G, r = threadIdx.x / G;
+  const F8 sc = load8(scale + cg * 8), sh = load8(shift + cg * 8), mu = load8(mean + cg * 8), is = load8(invstd + cg * 8);
+  float sg[8], sgx[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sg[e] = sgx[e] = 0.f;
+  for (long long p = (long long)blockIdx.x * R + r; p < M; p += (long long)gridDim.x * R) {
+    const F8 d = load8(dact + p * ldd + cg * 8), v = load8(y + p * ldy + cg * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float g = fmaf(v.v[e], sc.v[e], sh.v[e]) > 0.f ? d.v[e] : 0.f;
+      sg[e] += g;
+      sgx[e] += g * ((v.v[e] - mu.v[e]) * is.v[e]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    red[0][r * C + cg * 8 + e] = sg[e];
+    red[1][r * C + cg * 8 + e] = sgx[e];
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 2 * C; t += 256) {
+    const int which = t / C, c = t % C;
+    float s = 0.f;
+    for (int rr = 0; rr < R; ++rr) s += red[which][rr * C + c];
+    atomicAdd(&sums[which * C + c], (double)s);
+  }
+}
+
+template <typename T>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ dact, int ldd, const T* __restrict__ y, int ldy, T* __restrict__ dy,
+                                    int lddy, long long M, int C, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const double* __restrict__ sums,
+                                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int G = C >> 3;
+  if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      if (dbeta) dbeta[c] = (float)sums[c];
+      if (dgamma) dgamma[c] = (float)sums[C + c];
+    }
+  }
+  const double invM = 1.0 / (double)M;
+  const long long items = M * G;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % G);
+    const long long p = i / G;
+    const F8 sc = load8(scale + cg * 8), sh = load8(shift + cg * 8), mu = load8(mean + cg * 8), is = load8(invstd + cg * 8);
+    const F8 d = load8(dact + p * ldd + cg * 8), v = load8(y + p * ldy + cg * 8);
+    F8 o;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = cg * 8 + e;
+      const float k1 = (float)(sums[c] * invM), k2 = (float)(sums[C + c] * invM);
+      const float g = fmaf(v.v[e], sc.v[e], sh.v[e]) > 0.f ? d.v[e] : 0.f;
+      const float xhat = (v.v[e] - mu.v[e]) * is.v[e];
+      o.v[e] = sc.v[e] * (g - k1 - xhat * k2);
+    }
+    store8(dy + p * lddy + cg * 8, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// packing
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pack_input_kernel(const float* __restrict__ x, T* __restrict__ out, int B, int C, int H, int W, int Cpad) {
+  const long long items = (long long)B * H * W;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < items; p += (long long)gridDim.x * blockDim.x) {
+    const long long hw = p % ((long long)H * W);
+    const long long b = p / ((long long)H * W);
+    for (int c0 = 0; c0 < Cpad; c0 += 8) {
+      F8 v;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = c0 + e;
+        v.v[e] = c < C ? x[(b * C + c) * (long long)H * W + hw] : 0.f;
+      }
+      store8(out + p * Cpad + c0, v);
+    }
+  }
+}
+
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int Co, int Ci, int CoPad, int CiPad,
+                                   int transpose_flip) {
+  // output rows R = transpose_flip ? CiPad : CoPad, inner K = transpose_flip ? CoPad : CiPad
+  const int rows = transpose_flip ? CiPad : CoPad, inner = transpose_flip ? CoPad : CiPad;
+  const long long items = (long long)rows * 9 * inner;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % inner);
+    const int tap = (int)((i / inner) % 9);
+    const int r = (int)(i / ((long long)inner * 9));
+    float v = 0.f;
+    if (!transpose_flip) {
+      if (r < Co && k < Ci) v = w[((long long)r * Ci + k) * 9 + tap];
+    } else {
+      if (k < Co && r < Ci) v = w[((long long)k * Ci + r) * 9 + (8 - tap)];
+    }
+    out[i] = from_f32<T>(v);
+  }
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Co, int Ci, int CiPad) {
+  const long long items = (long long)Co * Ci * 9;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % 9);
+    const int ci = (int)((i / 9) % Ci);
+    const int co = (int)(i / (9LL * Ci));
+    dw[i] = dwp[((long long)co * 9 + tap) * CiPad + ci];
+  }
+}
+
+__global__ void cast_f64_f32_kernel(const double* __restrict__ s, float* __restrict__ d, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    d[i] = (float)s[i];
+}
+
+static int check_vec(const void* p, int ld, int C, const char* what) {
+  EUNET_REQUIRE(C > 0 && (C & 7) == 0, "%s: channel count %d must be a multiple of 8", what, C);
+  EUNET_REQUIRE((ld & 7) == 0 && ld >= C, "%s: ld %d must be a multiple of 8 and >= C=%d", what, ld, C);
+  EUNET_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0, "%s: pointer %p not 16-byte aligned", what, p);
+  return 0;
+}
+
+}  // namespace eunet
+
+using namespace eunet;
+
+extern "C" {
+
+int eunet_bn_finalize(const double* stats, long long count, const float* gamma, const float* beta, const float* conv_bias,
+                      float* running_mean, float* running_var, long long* nbt, float momentum, float eps, float* scale,
+                      float* shift, float* mean, float* invstd, int C, void* stream) {
+  EUNET_REQUIRE(C > 0 && count > 0, "bn_finalize: bad C=%d count=%lld", C, count);
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(stats, count, gamma, beta, conv_bias, running_mean,
+                                                                         running_var, nbt, momentum, eps, scale, shift, mean,
+                                                                         invstd, C);
+  return check_launch("bn_finalize");
+}
+
+int eunet_bn_fold_eval(const float* gamma, const float* beta, const float* conv_bias, const float* running_mean,
+                       const float* running_var, float eps, float* scale, float* shift, int C, void* stream) {
+  EUNET_REQUIRE(C > 0, "bn_fold_eval: bad C=%d", C);
+  bn_fold_eval_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(gamma, beta, conv_bias, running_mean, running_var,
+                                                                          eps, scale, shift, C);
+  return check_launch("bn_fold_eval");
+}
+
+int eunet_bn_apply_relu(const void* y, int ldy, void* out, int ldo, void* pooled, int ldp, int dtype, int B, int H, int W,
+                        int C, const float* scale, const float* shift, void* stream) {
+  if (check_vec(y, ldy, C, "bn_apply_relu(y)") || check_vec(out, ldo, C, "bn_apply_relu(out)")) return -1;
+  const long long M = (long long)B * H * W;
+  EUNET_REQUIRE(M > 0, "bn_apply_relu: empty tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pooled) {
+    if (check_vec(pooled, ldp, C, "bn_apply_relu(pooled)")) return -1;
+    EUNET_REQUIRE((H & 1) == 0 && (W & 1) == 0, "bn_apply_relu: fused pool needs even H,W (got %dx%d)", H, W);
+    DISPATCH_DTYPE(dtype, bn_apply_relu_pool_kernel<T><<<ew_grid(M / 4 * (C / 8)), 256, 0, st>>>(
+                              (const T*)y, ldy, (T*)out, ldo, (T*)pooled, ldp, B, H, W, C, scale, shift));
+  } else {
+    DISPATCH_DTYPE(dtype, bn_apply_relu_kernel<T><<<ew_grid(M * (C / 8)), 256, 0, st>>>((const T*)y, ldy, (T*)out, ldo, M, C,
+                                                                                         scale, shift));
+  }
+  return check_launch("bn_apply_relu");
+}
+
+int eunet_bn_bwd_reduce(const void* dact, int ldd, const void* y, int ldy, int dtype, long long M, int C, const float* scale,
+                        const float* shift, const float* mean, const float* invstd, double* sums, void* stream) {
+  if (check_vec(dact, ldd, C, "bn_bwd_reduce(dact)") || check_vec(y, ldy, C, "bn_bwd_reduce(y)")) return -1;
+  EUNET_REQUIRE(C <= 2048 && 256 % (C / 8) == 0, "bn_bwd_reduce: C/8=%d must divide 256", C / 8);
+  EUNET_REQUIRE(M > 0, "bn_bwd_reduce: empty tensor");
+  const int R = 256 / (C / 8);
+  const int grid = clamp_grid((M + R - 1) / R, 8);
+  DISPATCH_DTYPE(dtype, bn_bwd_reduce_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)dact, ldd, (const T*)y, ldy,
+                                                                                         M, C, scale, shift, mean, invstd,
+                                                                                         sums));
+  return check_launch("bn_bwd_reduce");
+}
+
+int eunet_bn_bwd_apply(const void* dact, int ldd, const void* y, int ldy, void* dy, int lddy, int dtype, long long M, int C,
+                       const float* scale, const float* shift, const float* mean, const float* invstd, const double* sums,
+                       float* dgamma, float* dbeta, void* stream) {
+  if (check_vec(dact, ldd, C, "bn_bwd_apply(dact)") || check_vec(y, ldy, C, "bn_bwd_apply(y)") ||
+      check_vec(dy, lddy, C, "bn_bwd_apply(dy)"))
+    return -1;
+  EUNET_REQUIRE(M > 0, "bn_bwd_apply: empty tensor");
+  DISPATCH_DTYPE(dtype, bn_bwd_apply_kernel<T><<<ew_grid(M * (C / 8)), 256, 0, (cudaStream_t)stream>>>(
+                            (const T*)dact, ldd, (const T*)y, ldy, (T*)dy, lddy, M, C, scale, shift, mean, invstd, sums, dgamma,
+                            dbeta));
+  return check_launch("bn_bwd_apply");
+}
+
+int eunet_maxpool2_fwd(const void* x, int ldx, void* out, int ldo, int dtype, int B, int H, int W, int C, void* stream) {
+  if (check_vec(x, ldx, C, "maxpool2_fwd(x)") || check_vec(out, ldo, C, "maxpool2_fwd(out)")) return -1;
+  EUNET_REQUIRE(B > 0 && H > 0 && W > 0 && (H & 1) == 0 && (W & 1) == 0, "maxpool2_fwd: H,W must be even (got %dx%d)", H, W);
+  const long long items = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  DISPATCH_DTYPE(dtype, maxpool2_fwd_kernel<T><<<ew_grid(items), 256, 0, (cudaStream_t)stream>>>((const T*)x, ldx, (T*)out, ldo,
+                                                                                                  B, H, W, C));
+  return check_launch("maxpool2_fwd");
+}
+
+int eunet_maxpool2_bwd(const void* dpool, int ldp, const void* x, int ldx, void* dx, int lddx, int accumulate, int dtype,
+                       int B, int H, int W, int C, void* stream) {
+  if (check_vec(dpool, ldp, C, "maxpool2_bwd(dpool)") || check_vec(x, ldx, C, "maxpool2_bwd(x)") ||
+      check_vec(dx, lddx, C, "maxpool2_bwd(dx)"))
+    return -1;
+  EUNET_REQUIRE(B > 0 && H > 0 && W > 0 && (H & 1) == 0 && (W & 1) == 0, "maxpool2_bwd: H,W must be even (got %dx%d)", H, W);
+  const long long items = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (accumulate)
+    DISPATCH_DTYPE(dtype, maxpool2_bwd_kernel<T, true><<<ew_grid(items), 256, 0, st>>>((const T*)dpool, ldp, (const T*)x, ldx,
+                                                                                        (T*)dx, lddx, B, H, W, C));
+  else
+    DISPATCH_DTYPE(dtype, maxpool2_bwd_kernel<T, false><<<ew_grid(items), 256, 0, st>>>((const T*)dpool, ldp, (const T*)x, ldx,
+                                                                                         (T*)dx, lddx, B, H, W, C));
+  return check_launch("maxpool2_bwd");
+}
+
+int eunet_upsample2_fwd(const void* x, int ldx, void* out, int ldo, int dtype, int B, int H, int W, int C, void* stream) {
+  if (check_vec(x, ldx, C, "upsample2_fwd(x)") || check_vec(out, ldo, C, "upsample2_fwd(out)")) return -1;
+  EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "upsample2_fwd: empty tensor");
+  const long long items = (long long)B * H * W * (C / 8);
+  DISPATCH_DTYPE(dtype, upsample2_fwd_kernel<T><<<ew_grid(items), 256, 0, (cudaStream_t)stream>>>((const T*)x, ldx, (T*)out,
+                                                                                                   ldo, B, H, W, C));
+  return check_launch("upsample2_fwd");
+}
+
+int eunet_upsample2_bwd(const void* dout, int ldo, void* dx, int ldx, int dtype, int B, int H, int W, int C, void* stream) {
+  if (check_vec(dout, ldo, C, "upsample2_bwd(dout)") || check_vec(dx, ldx, C, "upsample2_bwd(dx)")) return -1;
+  EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "upsample2_bwd: empty tensor");
+  const long long items = (long long)B * H * W * (C / 8);
+  DISPATCH_DTYPE(dtype, upsample2_bwd_kernel<T><<<ew_grid(items), 256, 0, (cudaStream_t)stream>>>((const T*)dout, ldo, (T*)dx,
+                                                                                                   ldx, B, H, W, C));
+  return check_launch("upsample2_bwd");
+}
+
+int eunet_pack_input_nchw(const float* x, void* out, int dtype, int B, int C, int H, int W, int Cpad, void* stream) {
+  EUNET_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && Cpad >= C && (Cpad & 7) == 0, "pack_input: bad shape");
+  DISPATCH_DTYPE(dtype, pack_input_kernel<T><<<ew_grid((long long)B * H * W), 256, 0, (cudaStream_t)stream>>>(x, (T*)out, B, C,
+                                                                                                               H, W, Cpad));
+  return check_launch("pack_input_nchw");
+}
+
+int eunet_pack_weight3x3(const float* w, void* out, int dtype, int Co, int Ci, int CoPad, int CiPad, int transpose_flip,
+                         void* stream) {
+  EUNET_REQUIRE(Co > 0 && Ci > 0 && CoPad >= Co && CiPad >= Ci, "pack_weight3x3: bad shape");
+  const long long items = (long long)CoPad * 9 * CiPad;
+  DISPATCH_DTYPE(dtype, pack_weight_kernel<T><<<ew_grid(items), 256, 0, (cudaStream_t)stream>>>(w, (T*)out, Co, Ci, CoPad,
+                                                                                                 CiPad, transpose_flip));
+  return check_launch("pack_weight3x3");
+}
+
+int eunet_unpack_wgrad3x3(const float* dw_packed, float* dw, int Co, int Ci, int CiPad, void* stream) {
+  EUNET_REQUIRE(Co > 0 && Ci > 0 && CiPad >= Ci, "unpack_wgrad3x3: bad shape");
+  unpack_wgrad_kernel<<<ew_grid((long long)Co * Ci * 9), 256, 0, (cudaStream_t)stream>>>(dw_packed, dw, Co, Ci, CiPad);
+  return check_launch("unpack_wgrad3x3");
+}
+
+int eunet_cast_f64_f32(const double* src, float* dst, long long n, void* stream) {
+  EUNET_REQUIRE(n > 0, "cast_f64_f32: n=%lld", n);
+  cast_f64_f32_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(src, dst, n);
+  return check_launch("cast_f64_f32");
+}
+
+}  // extern "C"

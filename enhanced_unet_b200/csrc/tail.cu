@@ -1,0 +1,418 @@
+// The 2Hx2W tail of EnhancedUNet (models.py:212 dec1, 236 final upsample, 308-313 enhance head,
+// 337 residual) - bandwidth kernels around the generic 3x3 convolution:
+//   z   = dec1(d2)                       1x1, computed at HxW (commutes with bilinear interpolation)
+//   d1  = up(z)                          3 channels @ 2Hx2W, stored padded to 16 ch for the conv kernels
+//   mid = conv3x3(d1; enhance.0)         generic conv kernel (+ BN batch statistics)
+//   out = d1 + b3 + W3 . relu(bn(mid))   [B,3,2H,2W] fp32 NCHW (the model's output tensor)
+// and the matching backward pieces.  64-channel pixels are processed by 8 lanes x 8 channels with
+// a 3-step shuffle reduction; per-channel gradient sums go through shared memory + fp64 atomics.
+#include "common.cuh"
+#include "../../include/eunet.h"
+
+namespace eunet {
+
+#define DISPATCH_DTYPE(dtype, ...)                          \
+  do {                                                      \
+    if ((dtype) == EUNET_BF16) {                            \
+      using T = __nv_bfloat16;                              \
+      __VA_ARGS__;                                          \
+    } else if ((dtype) == EUNET_F32) {                      \
+      using T = float;                                      \
+      __VA_ARGS__;                                          \
+    } else {                                                \
+      set_error("unknown dtype %d", (int)(dtype));          \
+      return -1;                                            \
+    }                                                       \
+  } while (0)
+
+__device__ __forceinline__ float group8_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+
+// bilinear x2 sample of the 3-channel z4 map at output pixel (oy, ox) of the 2Hx2W grid
+__device__ __forceinline__ void up_sample3(const float* __restrict__ z4, int b, int oy, int ox, int H, int W, float d[3]) {
+  const int k = oy >> 1, j = ox >> 1;
+  int k0, k1, j0, j1;
+  float wy0, wy1, wx0, wx1;
+  if (oy & 1) { k0 = k; k1 = k < H - 1 ? k + 1 : k; wy0 = k < H - 1 ? 0.75f : 1.f; wy1 = k < H - 1 ? 0.25f : 0.f; }
+  else        { k0 = k > 0 ? k - 1 : 0; k1 = k; wy0 = k > 0 ? 0.25f : 0.f; wy1 = k > 0 ? 0.75f : 1.f; }
+  if (ox & 1) { j0 = j; j1 = j < W - 1 ? j + 1 : j; wx0 = j < W - 1 ? 0.75f : 1.f; wx1 = j < W - 1 ? 0.25f : 0.f; }
+  else        { j0 = j > 0 ? j - 1 : 0; j1 = j; wx0 = j > 0 ? 0.25f : 0.f; wx1 = j > 0 ? 0.75f : 1.f; }
+  const float4* zb = reinterpret_cast<const float4*>(z4) + (long long)b * H * W;
+  const float4 a = __ldg(zb + (long long)k0 * W + j0), c = __ldg(zb + (long long)k0 * W + j1);
+  const float4 e = __ldg(zb + (long long)k1 * W + j0), f = __ldg(zb + (long long)k1 * W + j1);
+  d[0] = wy0 * (wx0 * a.x + wx1 * c.x) + wy1 * (wx0 * e.x + wx1 * f.x);
+  d[1] = wy0 * (wx0 * a.y + wx1 * c.y) + wy1 * (wx0 * e.y + wx1 * f.y);
+  d[2] = wy0 * (wx0 * a.z + wx1 * c.z) + wy1 * (wx0 * e.z + wx1 * f.z);
+}
+
+// ---- z = dec1(d2): 8 lanes per pixel ----
+template <typename T>
+__global__ void __launch_bounds__(256)
+tail_dec1_fwd_kernel(const T* __restrict__ d2, int ld, const float* __restrict__ w1, const float* __restrict__ b1,
+                     float* __restrict__ z4, long long M) {
+  const int cg = threadIdx.x & 7;
+  float w[3][8];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const F8 t = load8(w1 + k * 64 + cg * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) w[k][e] = t.v[e];
+  }
+  const float bb0 = b1[0], bb1 = b1[1], bb2 = b1[2];
+  const long long stride = (long long)gridDim.x * 32;
+  const long long Mr = (M + stride - 1) / stride * stride;   // keep whole warps in the loop (shuffles)
+  for (long long p = (long long)blockIdx.x * 32 + (threadIdx.x >> 3); p < Mr; p += stride) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    if (p < M) {
+      const F8 v = load8(d2 + p * ld + cg * 8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        s0 = fmaf(v.v[e], w[0][e], s0);
+        s1 = fmaf(v.v[e], w[1][e], s1);
+        s2 = fmaf(v.v[e], w[2][e], s2);
+      }
+    }
+    s0 = group8_sum(s0); s1 = group8_sum(s1); s2 = group8_sum(s2);
+    if (cg == 0 && p < M) reinterpret_cast<float4*>(z4)[p] = make_float4(s0 + bb0, s1 + bb1, s2 + bb2, 0.f);
+  }
+}
+
+// ---- d1p = up(z) padded to 16 channels: one thread per output pixel ----
+template <typename T>
+__global__ void tail_up_fwd_kernel(const float* __restrict__ z4, T* __restrict__ d1p, int B, int H, int W) {
+  const long long items = 4LL * B * H * W;
+  const int Wo = 2 * W, Ho = 2 * H;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % Wo);
+    const int oy = (int)((i / Wo) % Ho);
+    const int b = (int)(i / ((long long)Wo * Ho));
+    float d[3];
+    up_sample3(z4, b, oy, ox, H, W, d);
+    F8 lo, hi;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) lo.v[e] = hi.v[e] = 0.f;
+    lo.v[0] = d[0]; lo.v[1] = d[1]; lo.v[2] = d[2];
+    store8(d1p + i * 16, lo);
+    store8(d1p + i * 16 + 8, hi);
+  }
+}
+
+// ---- out = up(z) + b3 + W3 . relu(mid*scale+shift): 8 lanes per output pixel ----
+template <typename T>
+__global__ void __launch_bounds__(256)
+tail_out_fwd_kernel(const float* __restrict__ z4, const T* __restrict__ mid, const float* __restrict__ scale,
+                    const float* __restrict__ shift, const float* __restrict__ w3, const float* __restrict__ b3,
+                    float* __restrict__ out, int B, int H, int W) {
+  const int cg = threadIdx.x & 7;
+  const int Wo = 2 * W, Ho = 2 * H;
+  const long long M = (long long)B * Ho * Wo;
+  const F8 sc = load8(scale + cg * 8), sh = load8(shift + cg * 8);
+  float w[3][8];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const F8 t = load8(w3 + k * 64 + cg * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) w[k][e] = t.v[e];
+  }
+  const float bb[3] = {b3[0], b3[1], b3[2]};
+  const long long stride = (long long)gridDim.x * 32;
+  const long long Mr = (M + stride - 1) / stride * stride;
+  for (long long p = (long long)blockIdx.x * 32 + (threadIdx.x >> 3); p < Mr; p += stride) {
+    float s[3] = {0.f, 0.f, 0.f};
+    if (p < M) {
+      const F8 v = load8(mid + p * 64 + cg * 8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float a = fmaxf(fmaf(v.v[e], sc.v[e], sh.v[e]), 0.f);
+        s[0] = fmaf(a, w[0][e], s[0]);
+        s[1] = fmaf(a, w[1][e], s[1]);
+        s[2] = fmaf(a, w[2][e], s[2]);
+      }
+    }
+    s[0] = group8_sum(s[0]); s[1] = group8_sum(s[1]); s[2] = group8_sum(s[2]);
+    if (cg < 3 && p < M) {   // lanes 0..2 of the group write one class plane each
+      const int ox = (int)(p % Wo);
+      const int oy = (int)((p / Wo) % Ho);
+      const int b = (int)(p / ((long long)Wo * Ho));
+      float d[3];
+      up_sample3(z4, b, oy, ox, H, W, d);
+      const float sv = cg == 0 ? s[0] : (cg == 1 ? s[1] : s[2]);
+      const float dv = cg == 0 ? d[0] : (cg == 1 ? d[1] : d[2]);
+      out[((long long)b * 3 + cg) * Ho * Wo + (long long)oy * Wo + ox] = dv + bb[cg] + sv;
+    }
+  }
+}
+
+// Shared helper: reduce per-thread arrays (thread = 8 channels of group cg, 32 pixel rows per block)
+// over the block's pixel rows and atomically add to fp64 accumulators acc[base + cg*8 + e].
+__device__ __forceinline__ void block_reduce64(const float v[8], float (*red)[64], int cg, int row, double* acc_base) {
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[row][cg * 8 + e] = v[e];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) s += red[r][threadIdx.x];
+    atomicAdd(acc_base + threadIdx.x, (double)s);
+  }
+}
+
+// ---- backward pass 1 over (dout, mid): BN sums + enhance.3 weight/bias gradients ----
+// acc layout: [0,64) sum_g, [64,128) sum_g*xhat, [128,320) dW3[k][c], [320,323) db3[k]
+template <typename T>
+__global__ void __launch_bounds__(256)
+tail_bwd_reduce_kernel(const float* __restrict__ dout, const T* __restrict__ mid, const float* __restrict__ scale,
+                       const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
+                       const float* __restrict__ w3, double* __restrict__ acc, int B, int H, int W) {
+  __shared__ float red[32][64];
+  const int cg = threadIdx.x & 7, row = threadIdx.x >> 3;
+  const int Wo = 2 * W, Ho = 2 * H;
+  const long long HWo = (long long)Ho * Wo, M = (long long)B * HWo;
+  const F8 sc = load8(scale + cg * 8), sh = load8(shift + cg * 8), mu = load8(mean + cg * 8), is = load8(invstd + cg * 8);
+  float w[3][8];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const F8 t = load8(w3 + k * 64 + cg * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) w[k][e] = t.v[e];
+  }
+  float sg[8], sgx[8], dw[3][8], db[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { sg[e] = sgx[e] = 0.f; dw[0][e] = dw[1][e] = dw[2][e] = 0.f; }
+  for (long long p = (long long)blockIdx.x * 32 + row; p < M; p += (long long)gridDim.x * 32) {
+    const long long b = p / HWo, hw = p % HWo;
+    const float* dp = dout + b * 3 * HWo + hw;
+    const float g0 = __ldg(dp), g1 = __ldg(dp + HWo), g2 = __ldg(dp + 2 * HWo);
+    const F8 v = load8(mid + p * 64 + cg * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float pre = fmaf(v.v[e], sc.v[e], sh.v[e]);
+      const float a = fmaxf(pre, 0.f);
+      const float da = g0 * w[0][e] + g1 * w[1][e] + g2 * w[2][e];
+      const float g = pre > 0.f ? da : 0.f;
+      sg[e] += g;
+      sgx[e] += g * ((v.v[e] - mu.v[e]) * is.v[e]);
+      dw[0][e] = fmaf(g0, a, dw[0][e]);
+      dw[1][e] = fmaf(g1, a, dw[1][e]);
+      dw[2][e] = fmaf(g2, a, dw[2][e]);
+    }
+    if (cg == 0) { db[0] += g0; db[1] += g1; db[2] += g2; }
+  }
+  block_reduce64(sg, red, cg, row, acc);
+  block_reduce64(sgx, red, cg, row, acc + 64);
+  block_reduce64(dw[0], red, cg, row, acc + 128);
+  block_reduce64(dw[1], red, cg, row, acc + 192);
+  block_reduce64(dw[2], red, cg, row, acc + 256);
+  // bias gradient: rows' lane-0 partials
+  __syncthreads();
+  if (cg == 0) { red[row][0] = db[0]; red[row][1] = db[1]; red[row][2] = db[2]; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float s = 0.f;
+    for (int r = 0; r < 32; ++r) s += red[r][threadIdx.x];
+    atomicAdd(acc + 320 + threadIdx.x, (double)s);
+  }
+}
+
+// ---- backward pass 2: dmid = scale * (g - mean(g) - xhat * mean(g*xhat)) ----
+template <typename T>
+__global__ void __launch_bounds__(256)
+tail_bwd_dmid_kernel(const float* __restrict__ dout, const T* __restrict__ mid, T* __restrict__ dmid,
+                     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                     const float* __restrict__ invstd, const float* __restrict__ w3, const double* __restrict__ acc, int B,
+                     int H, int W) {
+  const int cg = threadIdx.x & 7, row = threadIdx.x >> 3;
+  const int Wo = 2 * W, Ho = 2 * H;
+  const long long HWo = (long long)Ho * Wo, M = (long long)B * HWo;
+  const F8 sc = load8(scale + cg * 8), sh = load8(shift + cg * 8), mu = load8(mean + cg * 8), is = load8(invstd + cg * 8);
+  float w[3][8], k1[8], k2[8];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const F8 t = load8(w3 + k * 64 + cg * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) w[k][e] = t.v[e];
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    k1[e] = (float)(acc[cg * 8 + e] / (double)M);
+    k2[e] = (float)(acc[64 + cg * 8 + e] / (double)M);
+  }
+  for (long long p = (long long)blockIdx.x * 32 + row; p < M; p += (long long)gridDim.x * 32) {
+    const long long b = p / HWo, hw = p % HWo;
+    const float* dp = dout + b * 3 * HWo + hw;
+    const float g0 = __ldg(dp), g1 = __ldg(dp + HWo), g2 = __ldg(dp + 2 * HWo);
+    const F8 v = load8(mid + p * 64 + cg * 8);
+    F8 o;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float pre = fmaf(v.v[e], sc.v[e], sh.v[e]);
+      const float da = g0 * w[0][e] + g1 * w[1][e] + g2 * w[2][e];
+      const float g = pre > 0.f ? da : 0.f;
+      const float xhat = (v.v[e] - mu.v[e]) * is.v[e];
+      o.v[e] = sc.v[e] * (g - k1[e] - xhat * k2[e]);
+    }
+    store8(dmid + p * 64 + cg * 8, o);
+  }
+}
+
+// ---- dz = up^T(dd1[:3] + dout): one thread per HxW pixel gathers the 4x4 output neighbourhood ----
+template <typename T>
+__device__ __forceinline__ void load3(const T* p, float v[3]);
+template <>
+__device__ __forceinline__ void load3<float>(const float* p, float v[3]) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z;
+}
+template <>
+__device__ __forceinline__ void load3<__nv_bfloat16>(const __nv_bfloat16* p, float v[3]) {
+  const uint2 t = *reinterpret_cast<const uint2*>(p);
+  v[0] = __uint_as_float(t.x << 16);
+  v[1] = __uint_as_float(t.x & 0xffff0000u);
+  v[2] = __uint_as_float(t.y << 16);
+}
+
+template <typename T>
+__global__ void tail_up_bwd_kernel(const T* __restrict__ dd1p, const float* __restrict__ dout, float* __restrict__ dz4, int B,
+                                   int H, int W) {
+  const long long items = (long long)B * H * W;
+  const int Wo = 2 * W, Ho = 2 * H;
+  const long long HWo = (long long)Ho * Wo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % W);
+    const int k = (int)((i / W) % H);
+    const int b = (int)(i / ((long long)W * H));
+    const float wy[4] = {k > 0 ? 0.25f : 0.f, k > 0 ? 0.75f : 1.f, k < H - 1 ? 0.75f : 1.f, k < H - 1 ? 0.25f : 0.f};
+    const float wx[4] = {j > 0 ? 0.25f : 0.f, j > 0 ? 0.75f : 1.f, j < W - 1 ? 0.75f : 1.f, j < W - 1 ? 0.25f : 0.f};
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (wy[r] == 0.f) continue;
+      const int oy = 2 * k - 1 + r;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        if (wx[s] == 0.f) continue;
+        const int ox = 2 * j - 1 + s;
+        const long long op = (long long)b * HWo + (long long)oy * Wo + ox;
+        float v[3];
+        load3<T>(dd1p + op * 16, v);
+        const float* dp = dout + (long long)b * 3 * HWo + (long long)oy * Wo + ox;
+        const float wgt = wy[r] * wx[s];
+        a0 += wgt * (v[0] + __ldg(dp));
+        a1 += wgt * (v[1] + __ldg(dp + HWo));
+        a2 += wgt * (v[2] + __ldg(dp + 2 * HWo));
+      }
+    }
+    reinterpret_cast<float4*>(dz4)[i] = make_float4(a0, a1, a2, 0.f);
+  }
+}
+
+// ---- dec1 backward: dd2 = dz . W1 ; dW1 += dz^T d2 ; db1 += dz.  acc: [0,192) dW1[k][c], [192,195) db1 ----
+template <typename T>
+__global__ void __launch_bounds__(256)
+tail_dec1_bwd_kernel(const float* __restrict__ dz4, const T* __restrict__ d2, int ldd2, T* __restrict__ dd2, int lddd2,
+                     const float* __restrict__ w1, double* __restrict__ acc, long long M) {
+  __shared__ float red[32][64];
+  const int cg = threadIdx.x & 7, row = threadIdx.x >> 3;
+  float w[3][8], dw[3][8], db[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const F8 t = load8(w1 + k * 64 + cg * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { w[k][e] = t.v[e]; dw[k][e] = 0.f; }
+  }
+  for (long long p = (long long)blockIdx.x * 32 + row; p < M; p += (long long)gridDim.x * 32) {
+    const float4 dz = __ldg(reinterpret_cast<const float4*>(dz4) + p);
+    const F8 v = load8(d2 + p * ldd2 + cg * 8);
+    F8 o;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      o.v[e] = dz.x * w[0][e] + dz.y * w[1][e] + dz.z * w[2][e];
+      dw[0][e] = fmaf(dz.x, v.v[e], dw[0][e]);
+      dw[1][e] = fmaf(dz.y, v.v[e], dw[1][e]);
+      dw[2][e] = fmaf(dz.z, v.v[e], dw[2][e]);
+    }
+    store8(dd2 + p * lddd2 + cg * 8, o);
+    if (cg == 0) { db[0] += dz.x; db[1] += dz.y; db[2] += dz.z; }
+  }
+  block_reduce64(dw[0], red, cg, row, acc);
+  block_reduce64(dw[1], red, cg, row, acc + 64);
+  block_reduce64(dw[2], red, cg, row, acc + 128);
+  __syncthreads();
+  if (cg == 0) { red[row][0] = db[0]; red[row][1] = db[1]; red[row][2] = db[2]; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float s = 0.f;
+    for (int r = 0; r < 32; ++r) s += red[r][threadIdx.x];
+    atomicAdd(acc + 192 + threadIdx.x, (double)s);
+  }
+}
+
+static inline int rows_grid(long long M) { return clamp_grid((M + 31) / 32, 8); }
+static inline int ew_grid(long long items) { return clamp_grid((items + 255) / 256, 16); }
+
+}  // namespace eunet
+
+using namespace eunet;
+
+extern "C" {
+
+int eunet_tail_dec1_fwd(const void* d2, int ldd2, int dtype, const float* w1, const float* b1, float* z4, long long M,
+                        void* stream) {
+  EUNET_REQUIRE(M > 0 && ldd2 >= 64 && (ldd2 & 7) == 0, "tail_dec1_fwd: bad shape M=%lld ld=%d", M, ldd2);
+  DISPATCH_DTYPE(dtype, tail_dec1_fwd_kernel<T><<<rows_grid(M), 256, 0, (cudaStream_t)stream>>>((const T*)d2, ldd2, w1, b1, z4, M));
+  return check_launch("tail_dec1_fwd");
+}
+
+int eunet_tail_up_fwd(const float* z4, void* d1p, int dtype, int B, int H, int W, void* stream) {
+  EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "tail_up_fwd: bad shape");
+  DISPATCH_DTYPE(dtype, tail_up_fwd_kernel<T><<<ew_grid(4LL * B * H * W), 256, 0, (cudaStream_t)stream>>>(z4, (T*)d1p, B, H, W));
+  return check_launch("tail_up_fwd");
+}
+
+int eunet_tail_out_fwd(const float* z4, const void* mid, int dtype, const float* scale, const float* shift, const float* w3,
+                       const float* b3, float* out, int B, int H, int W, void* stream) {
+  EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "tail_out_fwd: bad shape");
+  DISPATCH_DTYPE(dtype, tail_out_fwd_kernel<T><<<rows_grid(4LL * B * H * W), 256, 0, (cudaStream_t)stream>>>(
+                            z4, (const T*)mid, scale, shift, w3, b3, out, B, H, W));
+  return check_launch("tail_out_fwd");
+}
+
+int eunet_tail_bwd_reduce(const float* dout, const void* mid, int dtype, const float* scale, const float* shift,
+                          const float* mean, const float* invstd, const float* w3, double* acc, int B, int H, int W,
+                          void* stream) {
+  EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "tail_bwd_reduce: bad shape");
+  DISPATCH_DTYPE(dtype, tail_bwd_reduce_kernel<T><<<rows_grid(4LL * B * H * W), 256, 0, (cudaStream_t)stream>>>(
+                            dout, (const T*)mid, scale, shift, mean, invstd, w3, acc, B, H, W));
+  return check_launch("tail_bwd_reduce");
+}
+
+int eunet_tail_bwd_dmid(const float* dout, const void* mid, void* dmid, int dtype, const float* scale, const float* shift,
+                        const float* mean, const float* invstd, const float* w3, const double* acc, int B, int H, int W,
+                        void* stream) {
+  EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "tail_bwd_dmid: bad shape");
+  DISPATCH_DTYPE(dtype, tail_bwd_dmid_kernel<T><<<rows_grid(4LL * B * H * W), 256, 0, (cudaStream_t)stream>>>(
+                            dout, (const T*)mid, (T*)dmid, scale, shift, mean, invstd, w3, acc, B, H, W));
+  return check_launch("tail_bwd_dmid");
+}
+
+int eunet_tail_up_bwd(const void* dd1p, int dtype, const float* dout, float* dz4, int B, int H, int W, void* stream) {
+  EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "tail_up_bwd: bad shape");
+  DISPATCH_DTYPE(dtype, tail_up_bwd_kernel<T><<<ew_grid((long long)B * H * W), 256, 0, (cudaStream_t)stream>>>(
+                            (const T*)dd1p, dout, dz4, B, H, W));
+  return check_launch("tail_up_bwd");
+}
+
+int eunet_tail_dec1_bwd(const float* dz4, const void* d2, int ldd2, void* dd2, int lddd2, int dtype, const float* w1,
+                        double* acc, long long M, void* stream) {
+  EUNET_REQUIRE(M > 0 && ldd2 >= 64 && lddd2 >= 64, "tail_dec1_bwd: bad shape");
+  DISPATCH_DTYPE(dtype, tail_dec1_bwd_kernel<T><<<rows_grid(M), 256, 0, (cudaStream_t)stream>>>(dz4, (const T*)d2, ldd2, (T*)dd2,
+                                                                                               lddd2, w1, acc, M));
+  return check_launch("tail_dec1_bwd");
+}
+
+}  // extern "C"

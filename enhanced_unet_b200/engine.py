@@ -1,0 +1,337 @@
+"""Host-side schedule of the Enhanced-UNet hot path over the C-ABI kernels (libeunet_b200.so).
+
+Mirrors ``BasicUNet.forward`` (reference models.py:227-238) + the enhance head (308-313, 337) and its
+autograd backward, but laid out B200-first:
+
+* activations are NHWC in HBM (bf16 by default, fp32 in "fp32 mode"); ``torch.cat([up, skip])`` is never
+  materialised - producers write straight into channel slices of one concat buffer per level;
+* conv -> BN(train) is "conv with fused fp64 batch statistics" + a tiny finalize + one apply/ReLU pass
+  (fused with the 2x2 max-pool in the encoder); eval-mode BN is folded into the conv epilogue;
+* the 2Hx2W tail computes dec1 (1x1) BEFORE the last upsample (they commute) so no 64-channel tensor
+  is materialised at 2Hx2W except the enhance conv's own output;
+* dgrad = the same conv kernel over dY with flipped/transposed packed filters; wgrad has its own kernel.
+
+torch is used for device memory (caching allocator) and the current stream only.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import lib
+from .lib import call, ptr
+
+BLOCKS = [  # (prefix, Cin, Cout) - reference models.py:203-211
+    ("model.enc1", 3, 64), ("model.enc2", 64, 128), ("model.enc3", 128, 256), ("model.enc4", 256, 512),
+    ("model.dec4", 768, 256), ("model.dec3", 384, 128), ("model.dec2", 192, 64),
+]
+BN_MOMENTUM = 0.1
+BN_EPS = 1e-5
+
+
+def _pad16(c: int) -> int:
+    return (c + 15) // 16 * 16
+
+
+class _Ctx:
+    """Per-call helpers bound to a device / activation dtype."""
+
+    def __init__(self, device: torch.device, act_dtype: torch.dtype):
+        self.dev = device
+        self.dt = act_dtype
+        self.code = lib.dtype_code(act_dtype)
+
+    def empty(self, *shape, dtype=None):
+        return torch.empty(*shape, device=self.dev, dtype=dtype or self.dt)
+
+    def zeros(self, *shape, dtype=None):
+        return torch.zeros(*shape, device=self.dev, dtype=dtype or self.dt)
+
+
+def _ld(t: torch.Tensor) -> int:
+    assert t.dim() == 2 and t.stride(1) == 1, "activation operands are [pixels, channels] views with unit channel stride"
+    return t.stride(0)
+
+
+# ---------------------------------------------------------------------------------------------
+# packed-filter cache (invalidated by the parameter's in-place version counter)
+# ---------------------------------------------------------------------------------------------
+class PackCache:
+    def __init__(self):
+        self._c: Dict[Tuple[str, int, int], Tuple[int, int, torch.Tensor]] = {}
+
+    def get(self, cx: _Ctx, name: str, w: torch.Tensor, flip: bool) -> torch.Tensor:
+        key = (name, int(flip), cx.code)
+        ver = (w._version, w.data_ptr())
+        hit = self._c.get(key)
+        if hit is not None and hit[0] == ver and hit[2].device == w.device:
+            return hit[2]
+        co, ci = w.shape[0], w.shape[1]
+        cop, cip = _pad16(co), _pad16(ci)
+        rows, inner = (cip, cop) if flip else (cop, cip)
+        out = cx.empty(rows, 9, inner)
+        call("eunet_pack_weight3x3", ptr(w), ptr(out), cx.code, co, ci, cop, cip, int(flip))
+        self._c[key] = (ver, 0, out)
+        return out
+
+    def clear(self):
+        self._c.clear()
+
+
+def conv3x3(cx: _Ctx, x: torch.Tensor, wp: torch.Tensor, y: torch.Tensor, B: int, H: int, W: int, cin: int, cout: int,
+            stats: Optional[torch.Tensor] = None, scale: Optional[torch.Tensor] = None,
+            shift: Optional[torch.Tensor] = None, relu: bool = False) -> None:
+    call("eunet_conv3x3_fwd", ptr(x), _ld(x), ptr(wp), ptr(y), _ld(y), cx.code, B, H, W, cin, cout, ptr(stats), ptr(scale),
+         ptr(shift), int(relu))
+
+
+def conv3x3_wgrad(cx: _Ctx, x: torch.Tensor, dy: torch.Tensor, B: int, H: int, W: int, cin: int, cout: int) -> torch.Tensor:
+    dwp = cx.zeros(cout, 9, cin, dtype=torch.float32)
+    call("eunet_conv3x3_wgrad", ptr(x), _ld(x), ptr(dy), _ld(dy), ptr(dwp), cx.code, B, H, W, cin, cout)
+    return dwp
+
+
+def unpack_wgrad(dwp: torch.Tensor, co: int, ci: int) -> torch.Tensor:
+    dw = torch.empty(co, ci, 3, 3, device=dwp.device, dtype=torch.float32)
+    call("eunet_unpack_wgrad3x3", ptr(dwp), ptr(dw), co, ci, dwp.shape[2])
+    return dw
+
+
+class _BNSaved:
+    __slots__ = ("y", "scale", "shift", "mean", "invstd")
+
+    def __init__(self, y, scale, shift, mean, invstd):
+        self.y, self.scale, self.shift, self.mean, self.invstd = y, scale, shift, mean, invstd
+
+
+def _conv_bn_train(cx: _Ctx, packs: PackCache, sd: Dict[str, torch.Tensor], conv: str, bn: str, x: torch.Tensor, B, H, W, cin_p,
+                   cout, out: torch.Tensor, pooled: Optional[torch.Tensor]) -> _BNSaved:
+    M = B * H * W
+    y = cx.empty(M, cout)
+    stats = cx.zeros(2 * cout, dtype=torch.float64)
+    conv3x3(cx, x, packs.get(cx, conv, sd[conv + ".weight"], False), y, B, H, W, cin_p, cout, stats=stats)
+    f32 = torch.float32
+    scale, shift, mean, invstd = (cx.empty(cout, dtype=f32) for _ in range(4))
+    call("eunet_bn_finalize", ptr(stats), M, ptr(sd[bn + ".weight"]), ptr(sd[bn + ".bias"]), ptr(sd[conv + ".bias"]),
+         ptr(sd[bn + ".running_mean"]), ptr(sd[bn + ".running_var"]), ptr(sd[bn + ".num_batches_tracked"]), BN_MOMENTUM, BN_EPS,
+         ptr(scale), ptr(shift), ptr(mean), ptr(invstd), cout)
+    call("eunet_bn_apply_relu", ptr(y), _ld(y), ptr(out), _ld(out), ptr(pooled), _ld(pooled) if pooled is not None else 0,
+         cx.code, B, H, W, cout, ptr(scale), ptr(shift))
+    return _BNSaved(y, scale, shift, mean, invstd)
+
+
+def _conv_bn_eval(cx: _Ctx, packs: PackCache, sd, conv: str, bn: str, x, B, H, W, cin_p, cout, out) -> None:
+    f32 = torch.float32
+    scale, shift = cx.empty(cout, dtype=f32), cx.empty(cout, dtype=f32)
+    call("eunet_bn_fold_eval", ptr(sd[bn + ".weight"]), ptr(sd[bn + ".bias"]), ptr(sd[conv + ".bias"]),
+         ptr(sd[bn + ".running_mean"]), ptr(sd[bn + ".running_var"]), BN_EPS, ptr(scale), ptr(shift), cout)
+    conv3x3(cx, x, packs.get(cx, conv, sd[conv + ".weight"], False), out, B, H, W, cin_p, cout, scale=scale, shift=shift, relu=True)
+
+
+class Saved:
+    """Everything the backward pass needs (activations stay resident in HBM between fwd and bwd)."""
+
+    def __init__(self):
+        self.B = self.H = self.W = 0
+        self.x16 = None
+        self.bn: Dict[str, _BNSaved] = {}
+        self.act: Dict[str, torch.Tensor] = {}
+
+
+def _check_input(x: torch.Tensor) -> Tuple[int, int, int]:
+    if x.dim() != 4 or x.shape[1] != 3:
+        raise RuntimeError(f"EnhancedUNet expects input [B,3,H,W], got {tuple(x.shape)}")
+    B, _, H, W = x.shape
+    if H % 8 or W % 8 or H == 0 or W == 0 or B == 0:
+        raise RuntimeError(f"EnhancedUNet needs H and W to be non-zero multiples of 8 (got {H}x{W})")
+    if not x.is_cuda:
+        raise RuntimeError("EnhancedUNet (B200) runs on CUDA tensors only; there is no CPU fallback")
+    return B, H, W
+
+
+def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, train: bool, act_dtype: torch.dtype, packs: PackCache,
+            want_saved: bool) -> Tuple[torch.Tensor, Optional[Saved]]:
+    """Returns logits [B,3,2H,2W] fp32 (NCHW) and, in train mode, the saved state for ``backward``."""
+    B, H, W = _check_input(x)
+    cx = _Ctx(x.device, act_dtype)
+    x = x.contiguous().float()
+    sv = Saved()
+    sv.B, sv.H, sv.W = B, H, W
+    dims = [(H, W), (H // 2, W // 2), (H // 4, W // 4), (H // 8, W // 8)]
+    Ms = [B * h * w for h, w in dims]
+
+    x16 = cx.empty(Ms[0], 16)
+    call("eunet_pack_input_nchw", ptr(x), ptr(x16), cx.code, B, 3, H, W, 16)
+    sv.x16 = x16
+
+    cat2 = cx.empty(Ms[0], 192)   # [up(d3) | e1]
+    cat3 = cx.empty(Ms[1], 384)   # [up(d4) | e2]
+    cat4 = cx.empty(Ms[2], 768)   # [up(e4) | e3]
+    e1, e2, e3 = cat2[:, 128:192], cat3[:, 256:384], cat4[:, 512:768]
+    p1, p2, p3 = cx.empty(Ms[1], 64), cx.empty(Ms[2], 128), cx.empty(Ms[3], 256)
+    e4 = cx.empty(Ms[3], 512)
+    d4, d3, d2 = cx.empty(Ms[2], 256), cx.empty(Ms[1], 128), cx.empty(Ms[0], 64)
+
+    def block(prefix, xin, lvl, cin_p, cout, out, pooled=None):
+        h, w = dims[lvl]
+        mid = cx.empty(Ms[lvl], cout)
+        if train:
+            sv.bn[prefix + ".1"] = _conv_bn_train(cx, packs, sd, prefix + ".0", prefix + ".1", xin, B, h, w, cin_p, cout, mid, None)
+            sv.bn[prefix + ".4"] = _conv_bn_train(cx, packs, sd, prefix + ".3", prefix + ".4", mid, B, h, w, cout, cout, out, pooled)
+            sv.act[prefix + ".in"] = xin
+            sv.act[prefix + ".mid"] = mid
+        else:
+            _conv_bn_eval(cx, packs, sd, prefix + ".0", prefix + ".1", xin, B, h, w, cin_p, cout, mid)
+            _conv_bn_eval(cx, packs, sd, prefix + ".3", prefix + ".4", mid, B, h, w, cout, cout, out)
+            if pooled is not None:
+                call("eunet_maxpool2_fwd", ptr(out), _ld(out), ptr(pooled), _ld(pooled), cx.code, B, h, w, cout)
+
+    def up(src, lvl_src, c, dst):
+        h, w = dims[lvl_src]
+        call("eunet_upsample2_fwd", ptr(src), _ld(src), ptr(dst), _ld(dst), cx.code, B, h, w, c)
+
+    block("model.enc1", x16, 0, 16, 64, e1, p1)
+    block("model.enc2", p1, 1, 64, 128, e2, p2)
+    block("model.enc3", p2, 2, 128, 256, e3, p3)
+    block("model.enc4", p3, 3, 256, 512, e4)
+    up(e4, 3, 512, cat4[:, 0:512])
+    block("model.dec4", cat4, 2, 768, 256, d4)
+    up(d4, 2, 256, cat3[:, 0:256])
+    block("model.dec3", cat3, 1, 384, 128, d3)
+    up(d3, 1, 128, cat2[:, 0:128])
+    block("model.dec2", cat2, 0, 192, 64, d2)
+
+    # ---- tail: z = dec1(d2) @HxW, d1 = up(z), mid = enhance.0(d1), out = d1 + enhance.3(relu(bn(mid))) ----
+    f32 = torch.float32
+    M1, M2x = Ms[0], 4 * Ms[0]
+    w1 = sd["model.dec1.weight"].reshape(3, 64)
+    w3 = sd["enhance.3.weight"].reshape(3, 64)
+    z4 = cx.empty(M1, 4, dtype=f32)
+    call("eunet_tail_dec1_fwd", ptr(d2), _ld(d2), cx.code, ptr(w1), ptr(sd["model.dec1.bias"]), ptr(z4), M1)
+    d1p = cx.empty(M2x, 16)
+    call("eunet_tail_up_fwd", ptr(z4), ptr(d1p), cx.code, B, H, W)
+    out = torch.empty(B, 3, 2 * H, 2 * W, device=x.device, dtype=f32)
+    midt = cx.empty(M2x, 64)
+    if train:
+        stats = cx.zeros(128, dtype=torch.float64)
+        conv3x3(cx, d1p, packs.get(cx, "enhance.0", sd["enhance.0.weight"], False), midt, B, 2 * H, 2 * W, 16, 64, stats=stats)
+        scale, shift, mean, invstd = (cx.empty(64, dtype=f32) for _ in range(4))
+        call("eunet_bn_finalize", ptr(stats), M2x, ptr(sd["enhance.1.weight"]), ptr(sd["enhance.1.bias"]),
+             ptr(sd["enhance.0.bias"]), ptr(sd["enhance.1.running_mean"]), ptr(sd["enhance.1.running_var"]),
+             ptr(sd["enhance.1.num_batches_tracked"]), BN_MOMENTUM, BN_EPS, ptr(scale), ptr(shift), ptr(mean), ptr(invstd), 64)
+        sv.bn["enhance.1"] = _BNSaved(midt, scale, shift, mean, invstd)
+    else:
+        _conv_bn_eval(cx, packs, sd, "enhance.0", "enhance.1", d1p, B, 2 * H, 2 * W, 16, 64, midt)
+        scale, shift = torch.ones(64, device=x.device, dtype=f32), torch.zeros(64, device=x.device, dtype=f32)
+    call("eunet_tail_out_fwd", ptr(z4), ptr(midt), cx.code, ptr(scale), ptr(shift), ptr(w3), ptr(sd["enhance.3.bias"]), ptr(out),
+         B, H, W)
+    if train and want_saved:
+        sv.act.update(dict(cat2=cat2, cat3=cat3, cat4=cat4, d2=d2, d1p=d1p, z4=z4))
+        return out, sv
+    return out, None
+
+
+def backward(sd: Dict[str, torch.Tensor], sv: Saved, dout: torch.Tensor, act_dtype: torch.dtype, packs: PackCache
+             ) -> Dict[str, torch.Tensor]:
+    """Gradients (fp32, parameter layout) for every parameter of the state_dict."""
+    B, H, W = sv.B, sv.H, sv.W
+    cx = _Ctx(dout.device, act_dtype)
+    f32, f64 = torch.float32, torch.float64
+    dims = [(H, W), (H // 2, W // 2), (H // 4, W // 4), (H // 8, W // 8)]
+    Ms = [B * h * w for h, w in dims]
+    grads: Dict[str, torch.Tensor] = {}
+    dout = dout.contiguous().float()
+
+    def cast64(src: torch.Tensor, shape) -> torch.Tensor:
+        dst = torch.empty(shape, device=dout.device, dtype=f32)
+        call("eunet_cast_f64_f32", ptr(src), ptr(dst), dst.numel())
+        return dst
+
+    # ---- tail ----
+    M1, M2x = Ms[0], 4 * Ms[0]
+    bn = sv.bn["enhance.1"]
+    w1 = sd["model.dec1.weight"].reshape(3, 64)
+    w3 = sd["enhance.3.weight"].reshape(3, 64)
+    acc = cx.zeros(328, dtype=f64)
+    call("eunet_tail_bwd_reduce", ptr(dout), ptr(bn.y), cx.code, ptr(bn.scale), ptr(bn.shift), ptr(bn.mean), ptr(bn.invstd),
+         ptr(w3), ptr(acc), B, H, W)
+    dmid = cx.empty(M2x, 64)
+    call("eunet_tail_bwd_dmid", ptr(dout), ptr(bn.y), ptr(dmid), cx.code, ptr(bn.scale), ptr(bn.shift), ptr(bn.mean),
+         ptr(bn.invstd), ptr(w3), ptr(acc), B, H, W)
+    grads["enhance.1.bias"] = cast64(acc[0:64], (64,))
+    grads["enhance.1.weight"] = cast64(acc[64:128], (64,))
+    grads["enhance.3.weight"] = cast64(acc[128:320], (3, 64, 1, 1))
+    grads["enhance.3.bias"] = cast64(acc[320:323], (3,))
+    d1p = sv.act["d1p"]
+    dwp = conv3x3_wgrad(cx, d1p, dmid, B, 2 * H, 2 * W, 16, 64)
+    grads["enhance.0.weight"] = unpack_wgrad(dwp, 64, 3)
+    grads["enhance.0.bias"] = torch.zeros(64, device=dout.device, dtype=f32)   # cancelled by train-mode BN
+    dd1p = cx.empty(M2x, 16)
+    conv3x3(cx, dmid, packs.get(cx, "enhance.0", sd["enhance.0.weight"], True), dd1p, B, 2 * H, 2 * W, 64, 16)
+    dz4 = cx.empty(M1, 4, dtype=f32)
+    call("eunet_tail_up_bwd", ptr(dd1p), cx.code, ptr(dout), ptr(dz4), B, H, W)
+    acc2 = cx.zeros(200, dtype=f64)
+    d2 = sv.act["d2"]
+    dd2 = cx.empty(M1, 64)
+    call("eunet_tail_dec1_bwd", ptr(dz4), ptr(d2), _ld(d2), ptr(dd2), _ld(dd2), cx.code, ptr(w1), ptr(acc2), M1)
+    grads["model.dec1.weight"] = cast64(acc2[0:192], (3, 64, 1, 1))
+    grads["model.dec1.bias"] = cast64(acc2[192:195], (3,))
+
+    def bn_bwd(name: str, dact: torch.Tensor, M: int, C: int) -> torch.Tensor:
+        s = sv.bn[name]
+        sums = cx.zeros(2 * C, dtype=f64)
+        call("eunet_bn_bwd_reduce", ptr(dact), _ld(dact), ptr(s.y), _ld(s.y), cx.code, M, C, ptr(s.scale), ptr(s.shift),
+             ptr(s.mean), ptr(s.invstd), ptr(sums))
+        dy = cx.empty(M, C)
+        dg, db = torch.empty(C, device=dout.device, dtype=f32), torch.empty(C, device=dout.device, dtype=f32)
+        call("eunet_bn_bwd_apply", ptr(dact), _ld(dact), ptr(s.y), _ld(s.y), ptr(dy), _ld(dy), cx.code, M, C, ptr(s.scale),
+             ptr(s.shift), ptr(s.mean), ptr(s.invstd), ptr(sums), ptr(dg), ptr(db))
+        grads[name + ".weight"] = dg
+        grads[name + ".bias"] = db
+        return dy
+
+    def block_bwd(prefix: str, dact: torch.Tensor, lvl: int, cin: int, cout: int, need_dx: bool) -> Optional[torch.Tensor]:
+        h, w = dims[lvl]
+        M = Ms[lvl]
+        cin_p = _pad16(cin)
+        xin, mid = sv.act[prefix + ".in"], sv.act[prefix + ".mid"]
+        dy_b = bn_bwd(prefix + ".4", dact, M, cout)
+        grads[prefix + ".3.weight"] = unpack_wgrad(conv3x3_wgrad(cx, mid, dy_b, B, h, w, cout, cout), cout, cout)
+        grads[prefix + ".3.bias"] = torch.zeros(cout, device=dout.device, dtype=f32)
+        dmid_act = cx.empty(M, cout)
+        conv3x3(cx, dy_b, packs.get(cx, prefix + ".3", sd[prefix + ".3.weight"], True), dmid_act, B, h, w, cout, cout)
+        dy_a = bn_bwd(prefix + ".1", dmid_act, M, cout)
+        grads[prefix + ".0.weight"] = unpack_wgrad(conv3x3_wgrad(cx, xin, dy_a, B, h, w, cin_p, cout), cout, cin)
+        grads[prefix + ".0.bias"] = torch.zeros(cout, device=dout.device, dtype=f32)
+        if not need_dx:
+            return None
+        dx = cx.empty(M, cin_p)
+        conv3x3(cx, dy_a, packs.get(cx, prefix + ".0", sd[prefix + ".0.weight"], True), dx, B, h, w, cout, cin_p)
+        return dx
+
+    def up_bwd(dsrc: torch.Tensor, lvl_in: int, c: int) -> torch.Tensor:
+        h, w = dims[lvl_in]
+        dx = cx.empty(Ms[lvl_in], c)
+        call("eunet_upsample2_bwd", ptr(dsrc), _ld(dsrc), ptr(dx), _ld(dx), cx.code, B, h, w, c)
+        return dx
+
+    def pool_bwd_into(dpool: torch.Tensor, xact: torch.Tensor, dx: torch.Tensor, lvl: int, c: int) -> None:
+        h, w = dims[lvl]
+        call("eunet_maxpool2_bwd", ptr(dpool), _ld(dpool), ptr(xact), _ld(xact), ptr(dx), _ld(dx), 1, cx.code, B, h, w, c)
+
+    cat2, cat3, cat4 = sv.act["cat2"], sv.act["cat3"], sv.act["cat4"]
+    dcat2 = block_bwd("model.dec2", dd2, 0, 192, 64, True)
+    dd3 = up_bwd(dcat2[:, 0:128], 1, 128)
+    dcat3 = block_bwd("model.dec3", dd3, 1, 384, 128, True)
+    dd4 = up_bwd(dcat3[:, 0:256], 2, 256)
+    dcat4 = block_bwd("model.dec4", dd4, 2, 768, 256, True)
+    de4 = up_bwd(dcat4[:, 0:512], 3, 512)
+    dp3 = block_bwd("model.enc4", de4, 3, 256, 512, True)
+    pool_bwd_into(dp3, cat4[:, 512:768], dcat4[:, 512:768], 2, 256)
+    dp2 = block_bwd("model.enc3", dcat4[:, 512:768], 2, 128, 256, True)
+    pool_bwd_into(dp2, cat3[:, 256:384], dcat3[:, 256:384], 1, 128)
+    dp1 = block_bwd("model.enc2", dcat3[:, 256:384], 1, 64, 128, True)
+    pool_bwd_into(dp1, cat2[:, 128:192], dcat2[:, 128:192], 0, 64)
+    block_bwd("model.enc1", dcat2[:, 128:192], 0, 3, 64, False)
+    return grads

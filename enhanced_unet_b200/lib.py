@@ -1,0 +1,116 @@
+"""ctypes binding of libeunet_b200.so (the C ABI declared in include/eunet.h).
+
+The product path has no CPU fallback: if the library is missing or a call fails, a RuntimeError is
+raised (``eunet_last_error`` text included).  torch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libeunet_b200.so")
+
+F32, BF16 = 0, 1
+ABI_VERSION = 1
+
+_p = C.c_void_p
+_i = C.c_int
+_ll = C.c_longlong
+_f = C.c_float
+
+# name -> argtypes (restype is always int unless listed in _RESTYPES)
+SIGNATURES = {
+    "eunet_abi_version": [],
+    "eunet_device_info": [_p, _p, _p, _p],
+    "eunet_confusion4x4": [_p, _p, _i, _ll, _ll, _p, _p],
+    "eunet_pack_input_nchw": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "eunet_pack_weight3x3": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "eunet_unpack_wgrad3x3": [_p, _p, _i, _i, _i, _p],
+    "eunet_conv3x3_fwd": [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p],
+    "eunet_conv3x3_wgrad": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p],
+    "eunet_bn_finalize": [_p, _ll, _p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _i, _p],
+    "eunet_bn_fold_eval": [_p, _p, _p, _p, _p, _f, _p, _p, _i, _p],
+    "eunet_bn_apply_relu": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p],
+    "eunet_bn_bwd_reduce": [_p, _i, _p, _i, _i, _ll, _i, _p, _p, _p, _p, _p, _p],
+    "eunet_bn_bwd_apply": [_p, _i, _p, _i, _p, _i, _i, _ll, _i, _p, _p, _p, _p, _p, _p, _p, _p],
+    "eunet_maxpool2_fwd": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p],
+    "eunet_maxpool2_bwd": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "eunet_upsample2_fwd": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p],
+    "eunet_upsample2_bwd": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p],
+    "eunet_tail_dec1_fwd": [_p, _i, _i, _p, _p, _p, _ll, _p],
+    "eunet_tail_up_fwd": [_p, _p, _i, _i, _i, _i, _p],
+    "eunet_tail_out_fwd": [_p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "eunet_tail_bwd_reduce": [_p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "eunet_tail_bwd_dmid": [_p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "eunet_tail_up_bwd": [_p, _i, _p, _p, _i, _i, _i, _p],
+    "eunet_tail_dec1_bwd": [_p, _p, _i, _p, _i, _i, _p, _p, _ll, _p],
+    "eunet_cast_f64_f32": [_p, _p, _ll, _p],
+    "eunet_loss_fwd": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p],
+    "eunet_loss_bwd": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p],
+    "eunet_sumsq": [_p, _ll, _p, _p],
+    "eunet_adamw_step": [_p, _p, _p, _p, _ll, _p, _f, _f, _f, _f, _f, _f, _i, _f, _p],
+    "eunet_probe_umma": [_p, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p, _p, _i, _p],
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def library_path() -> str:
+    return LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load (once) and type the shared library.  Raises RuntimeError when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -m enhanced_unet_b200.build` "
+            "(there is no CPU / PyTorch fallback for the Enhanced-UNet hot path)")
+    lib = C.CDLL(LIB_PATH)
+    lib.eunet_last_error.restype = C.c_char_p
+    lib.eunet_last_error.argtypes = []
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError if the symbol is not exported
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    v = lib.eunet_abi_version()
+    if v != ABI_VERSION:
+        raise RuntimeError(f"libeunet_b200.so ABI version {v} != expected {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().eunet_last_error().decode("utf-8", "replace")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def call(name: str, *args) -> None:
+    """Invoke ``name`` with the current torch CUDA stream appended; raise on a non-zero status."""
+    lib = load()
+    rc = getattr(lib, name)(*args, stream_ptr())
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {last_error()}")
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.bfloat16:
+        return BF16
+    if dt == torch.float32:
+        return F32
+    raise ValueError(f"unsupported activation dtype {dt}")

@@ -1,0 +1,145 @@
+"""Drop-in for the hot-path classes of the reference ``models.py``.
+
+``EnhancedUNet(num_classes=3)`` keeps the reference constructor, ``forward(x)`` signature,
+``get_aux_outputs()``, attribute ``num_classes`` and - bit for bit - the 109-key ``state_dict`` of the
+reference's fallback body (``UNet(num_classes).model`` = BasicUNet, reference models.py:199-238, plus the
+``enhance`` head, 308-313), so reference checkpoints load unchanged and the reference Trainer / optimizer
+/ clip code works on its ``nn.Parameter``s.  The arithmetic runs in libeunet_b200.so (sm_100a); the torch
+modules below only HOLD parameters (same construction order => same default init for a given seed).
+
+There is no CPU path: calling ``forward`` on a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import engine
+
+_DTYPES = {"bf16": torch.bfloat16, "bfloat16": torch.bfloat16, "fp32": torch.float32, "float32": torch.float32}
+
+
+def _conv_block(in_ch: int, out_ch: int) -> nn.Sequential:
+    # parameter container with the reference's module indices (0 conv, 1 bn, 2 relu, 3 conv, 4 bn, 5 relu)
+    return nn.Sequential(
+        nn.Conv2d(in_ch, out_ch, 3, padding=1), nn.BatchNorm2d(out_ch), nn.ReLU(inplace=True),
+        nn.Conv2d(out_ch, out_ch, 3, padding=1), nn.BatchNorm2d(out_ch), nn.ReLU(inplace=True))
+
+
+class _BasicUNetParams(nn.Module):
+    """Holds the parameters of the reference BasicUNet (models.py:200-215) under the same names."""
+
+    def __init__(self, num_classes: int):
+        super().__init__()
+        self.enc1 = _conv_block(3, 64)
+        self.enc2 = _conv_block(64, 128)
+        self.enc3 = _conv_block(128, 256)
+        self.enc4 = _conv_block(256, 512)
+        self.dec4 = _conv_block(512 + 256, 256)
+        self.dec3 = _conv_block(256 + 128, 128)
+        self.dec2 = _conv_block(128 + 64, 64)
+        self.dec1 = nn.Conv2d(64, num_classes, 1)
+
+    def forward(self, x):  # pragma: no cover - never used as a compute path
+        raise RuntimeError("BasicUNet parameters are executed by EnhancedUNet.forward (CUDA kernels), not directly")
+
+
+class _UNetFunction(torch.autograd.Function):
+    """Whole-network autograd node: forward and backward are fixed kernel schedules (engine.py)."""
+
+    @staticmethod
+    def forward(ctx, module: "EnhancedUNet", x: torch.Tensor, *params: torch.Tensor):
+        sd = module._tensor_dict()
+        out, saved = engine.forward(sd, x, True, module.act_dtype, module._packs, want_saved=True)
+        ctx.module = module
+        ctx.saved_state = saved
+        ctx.n_params = len(params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout: torch.Tensor):
+        module = ctx.module
+        sv = ctx.saved_state
+        if sv is None:
+            raise RuntimeError("EnhancedUNet backward called twice (saved activations were released)")
+        sd = module._tensor_dict()
+        grads = engine.backward(sd, sv, dout, module.act_dtype, module._packs)
+        ctx.saved_state = None
+        names = module._param_names
+        return (None, None) + tuple(grads[n] for n in names)
+
+
+class EnhancedUNet(nn.Module):
+    """Reference models.py:246-343 (fallback body).  Extra keyword ``dtype``: 'bf16' (default, tcgen05
+    tensor-core convolutions, fp32 accumulation / statistics) or 'fp32' (CUDA-core fp32 mode)."""
+
+    def __init__(self, num_classes: int = 3, dtype: str = "bf16"):
+        super().__init__()
+        if num_classes != 3:
+            raise ValueError("the B200 hot path implements the reference configuration num_classes=3")
+        if dtype not in _DTYPES:
+            raise ValueError(f"dtype must be one of {sorted(_DTYPES)}")
+        self.num_classes = num_classes
+        self.act_dtype = _DTYPES[dtype]
+        self.model = _BasicUNetParams(num_classes)
+        self.enhance = nn.Sequential(
+            nn.Conv2d(num_classes, 64, 3, padding=1), nn.BatchNorm2d(64), nn.ReLU(inplace=True), nn.Conv2d(64, num_classes, 1))
+        self._aux_outputs = None
+        self._packs = engine.PackCache()
+        self._param_names = [n for n, _ in self.named_parameters()]
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _tensor_dict(self) -> Dict[str, torch.Tensor]:
+        d: Dict[str, torch.Tensor] = dict(self.named_parameters())
+        d.update(dict(self.named_buffers()))
+        return d
+
+    def set_compute_dtype(self, dtype: str) -> "EnhancedUNet":
+        self.act_dtype = _DTYPES[dtype]
+        self._packs.clear()
+        return self
+
+    def _apply(self, fn, *args, **kwargs):
+        r = super()._apply(fn, *args, **kwargs)
+        self._packs.clear()   # parameters may have moved
+        return r
+
+    # -- reference surface -----------------------------------------------------------------------
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        self._aux_outputs = None
+        p0 = next(self.parameters())
+        if not p0.is_cuda:
+            raise RuntimeError("EnhancedUNet (B200) parameters must live on a CUDA device: call .to('cuda'); no CPU fallback")
+        if x.device != p0.device:
+            raise RuntimeError(f"input on {x.device} but parameters on {p0.device}")
+        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if need_grad:
+            if not self.training:
+                raise NotImplementedError("gradients through eval-mode (running-statistics) BatchNorm are not implemented; "
+                                          "call .train() for training or torch.no_grad() for inference")
+            params = [p for _, p in self.named_parameters()]
+            return _UNetFunction.apply(self, x, *params)
+        with torch.no_grad():
+            out, _ = engine.forward(self._tensor_dict(), x, self.training, self.act_dtype, self._packs, want_saved=False)
+        return out
+
+    def get_aux_outputs(self) -> Optional[Dict[str, torch.Tensor]]:
+        """Reference models.py:341-343; always None in the fallback body."""
+        return getattr(self, "_aux_outputs", None)
+
+
+def get_model(model_name: str, num_classes: int = 3, device: str = "cuda", train_mode: bool = False, data_dir: str = None,
+              max_size: int = 640, dtype: str = "bf16") -> nn.Module:
+    """Reference models.py:590-624.  Same signature (the last three reference kwargs are ignored there
+    too); does NOT move the model to ``device`` (the caller does, train_eval.py:1079)."""
+    print(f"Initializing model: {model_name}")
+    if model_name == "enhanced_unet":
+        model = EnhancedUNet(num_classes=num_classes, dtype=dtype)
+    elif model_name in ("segnet", "unet", "fcn", "pspnet", "linknet"):
+        raise NotImplementedError(f"model '{model_name}' is outside the B200 hot path (only 'enhanced_unet' is accelerated)")
+    else:
+        raise ValueError(f"Unknown model: {model_name}")
+    print(f"Model {model_name} initialized")
+    return model

@@ -1,0 +1,139 @@
+/* eunet.h - C ABI of libeunet_b200.so: the B200-native (sm_100a) kernels behind the Enhanced-UNet hot path.
+ *
+ * The reference (whh1747012859/Enhanced-UNet) is pure PyTorch and has NO FFI / plugin layer for this
+ * path: the arithmetic is reached through torch.nn modules.  Each entry point below
+ * therefore cites the reference Python interface whose arithmetic it replaces (file:line in
+ * /root/reference); INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller (the PyTorch
+ *    caching allocator in our host code).  The library never allocates, frees or retains pointers.
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it asynchronously.
+ *  - return 0 on success, negative on error; eunet_last_error() returns the (thread-local) message.
+ *    There is no CPU fallback and no silent degradation.
+ *  - activations are NHWC ("channels last"), dtype EUNET_BF16 (default) or EUNET_F32 ("fp32 mode"),
+ *    addressed as base pointer + `ld` = elements per pixel of the underlying buffer, so a channel
+ *    slice of a wider (concat) buffer is a first-class operand.  Channel counts are multiples of 8
+ *    (bandwidth kernels) / 16 (convolutions).
+ *  - packed 3x3 filters: [Cout][9][Cin] (tap = ky*3+kx, Cin contiguous) in the activation dtype.
+ */
+#ifndef EUNET_H_
+#define EUNET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EUNET_ABI_VERSION 1
+#define EUNET_F32 0
+#define EUNET_BF16 1
+
+const char* eunet_last_error(void);
+int eunet_abi_version(void);
+int eunet_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin);
+
+/* ---- metrics.py:12-58 (calculate_iou / calculate_dice / calculate_semantic_metrics) and the confusion
+ * counts of visualization.py:294-311, 1484-1492.  Per image i: counts[i][g][p] = #pixels with gt class g
+ * and predicted class p, classes {0,1,2} and 3 = "any other value" (e.g. ignore label 255).  Integer,
+ * bit-exact.  elem_bytes in {1,4,8} (uint8 / int32 / int64 masks; the reference passes int64). */
+int eunet_confusion4x4(const void* pred, const void* gt, int elem_bytes, long long n_images, long long px_per_image,
+                       long long* counts /* [n_images][4][4], overwritten */, void* stream);
+
+/* ---- layout / parameter packing (host glue of models.py:227-238: NCHW fp32 tensors at the boundary) ---- */
+/* x [B,C,H,W] fp32 -> NHWC with Cpad channels (zero padded), dtype */
+int eunet_pack_input_nchw(const float* x, void* out, int dtype, int B, int C, int H, int W, int Cpad, void* stream);
+/* w [Co,Ci,3,3] fp32 (nn.Conv2d.weight) -> packed [CoPad][9][CiPad] dtype.
+ * transpose_flip = 0: forward form out[co][tap][ci] = w[co][ci][tap];
+ * transpose_flip = 1: dgrad form   out[ci][8-tap][co] = w[co][ci][tap] (so dgrad is a forward conv over dY). */
+int eunet_pack_weight3x3(const float* w, void* out, int dtype, int Co, int Ci, int CoPad, int CiPad, int transpose_flip,
+                         void* stream);
+/* dw_packed [Co][9][CiPad] fp32 -> dw [Co,Ci,3,3] fp32 (layout of nn.Conv2d.weight.grad) */
+int eunet_unpack_wgrad3x3(const float* dw_packed, float* dw, int Co, int Ci, int CiPad, void* stream);
+
+/* ---- nn.Conv2d(k=3, padding=1) forward (models.py:219,222,309) and its autograd dgrad/wgrad
+ * (loss.backward(), train_eval.py:338).  bf16: tcgen05/TMEM implicit GEMM with TMA-staged tiles;
+ * fp32: CUDA-core direct convolution ("fp32 mode").
+ * y[p,co] = sum_{tap,ci} x[p+tap,ci] * w[co][tap][ci], zero padding.  Epilogue options:
+ *   stats != NULL: accumulate per-channel sum / sum of squares of the fp32 results into stats[0..Cout)
+ *                  and stats[Cout..2Cout) (double, caller zeroes) - the BatchNorm batch statistics.
+ *   scale/shift != NULL: y = y*scale[co] + shift[co] (folded eval-mode BN and/or bias); relu: max(y,0). */
+int eunet_conv3x3_fwd(const void* x, int ldx, const void* w_packed, void* y, int ldy, int dtype, int B, int H, int W,
+                      int Cin, int Cout, double* stats, const float* scale, const float* shift, int relu, void* stream);
+/* dw[co][tap][ci] += sum_p dy[p,co] * x[p+tap,ci]   (fp32 accumulate into caller-zeroed dw_packed) */
+int eunet_conv3x3_wgrad(const void* x, int ldx, const void* dy, int lddy, float* dw_packed, int dtype, int B, int H, int W,
+                        int Cin, int Cout, void* stream);
+
+/* ---- nn.BatchNorm2d (models.py:220,223,310): train-mode statistics -> affine, running stats ---- */
+int eunet_bn_finalize(const double* stats, long long count, const float* gamma, const float* beta, const float* conv_bias,
+                      float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
+                      float* scale, float* shift, float* mean, float* invstd, int C, void* stream);
+int eunet_bn_fold_eval(const float* gamma, const float* beta, const float* conv_bias, const float* running_mean,
+                       const float* running_var, float eps, float* scale, float* shift, int C, void* stream);
+/* out = relu(y*scale+shift) (BN apply + nn.ReLU, models.py:220-221); optional fused nn.MaxPool2d(2)
+ * (models.py:214) writing pooled [B,H/2,W/2,C] when pooled != NULL. */
+int eunet_bn_apply_relu(const void* y, int ldy, void* out, int ldo, void* pooled, int ldp, int dtype, int B, int H, int W,
+                        int C, const float* scale, const float* shift, void* stream);
+/* BatchNorm+ReLU backward, pass 1: g = dact * [y*scale+shift > 0]; sums[0..C) += sum g, sums[C..2C) += sum g*xhat */
+int eunet_bn_bwd_reduce(const void* dact, int ldd, const void* y, int ldy, int dtype, long long M, int C, const float* scale,
+                        const float* shift, const float* mean, const float* invstd, double* sums, void* stream);
+/* pass 2: dy = scale*(g - sum_g/M - xhat*sum_gx/M); also writes dgamma = sum_gx, dbeta = sum_g (fp32) */
+int eunet_bn_bwd_apply(const void* dact, int ldd, const void* y, int ldy, void* dy, int lddy, int dtype, long long M, int C,
+                       const float* scale, const float* shift, const float* mean, const float* invstd, const double* sums,
+                       float* dgamma, float* dbeta, void* stream);
+
+/* ---- nn.MaxPool2d(2) (models.py:214) and nn.Upsample(x2, bilinear, align_corners=False) (models.py:215) ---- */
+int eunet_maxpool2_fwd(const void* x, int ldx, void* out, int ldo, int dtype, int B, int H, int W, int C, void* stream);
+/* dx (+)= route(dpool) to the first maximum of each 2x2 window (ATen tie-break) */
+int eunet_maxpool2_bwd(const void* dpool, int ldp, const void* x, int ldx, void* dx, int lddx, int accumulate, int dtype,
+                       int B, int H, int W, int C, void* stream);
+int eunet_upsample2_fwd(const void* x, int ldx, void* out, int ldo, int dtype, int B, int H, int W, int C, void* stream);
+int eunet_upsample2_bwd(const void* dout, int ldo, void* dx, int ldx, int dtype, int B, int H, int W, int C, void* stream);
+
+/* ---- the 2Hx2W tail (models.py:212, 236, 308-313, 337): dec1 1x1, final upsample, enhance head, residual.
+ * z = dec1(d2) is computed at HxW (a 1x1 conv commutes with bilinear interpolation), d1 = up(z). ---- */
+int eunet_tail_dec1_fwd(const void* d2, int ldd2, int dtype, const float* w1 /*[3][64]*/, const float* b1, float* z4 /*[M][4]*/,
+                        long long M, void* stream);
+int eunet_tail_up_fwd(const float* z4, void* d1p /*[B,2H,2W,16]*/, int dtype, int B, int H, int W, void* stream);
+int eunet_tail_out_fwd(const float* z4, const void* mid /*[B,2H,2W,64]*/, int dtype, const float* scale, const float* shift,
+                       const float* w3 /*[3][64]*/, const float* b3, float* out /*[B,3,2H,2W]*/, int B, int H, int W,
+                       void* stream);
+int eunet_tail_bwd_reduce(const float* dout, const void* mid, int dtype, const float* scale, const float* shift,
+                          const float* mean, const float* invstd, const float* w3, double* acc /*[128 + 192 + 3]*/, int B,
+                          int H, int W, void* stream);
+int eunet_tail_bwd_dmid(const float* dout, const void* mid, void* dmid, int dtype, const float* scale, const float* shift,
+                        const float* mean, const float* invstd, const float* w3, const double* acc, int B, int H, int W,
+                        void* stream);
+int eunet_tail_up_bwd(const void* dd1p /*[B,2H,2W,16]*/, int dtype, const float* dout, float* dz4, int B, int H, int W,
+                      void* stream);
+int eunet_tail_dec1_bwd(const float* dz4, const void* d2, int ldd2, void* dd2, int lddd2, int dtype, const float* w1,
+                        double* acc /*[192 + 3]*/, long long M, void* stream);
+/* double accumulators -> fp32 parameter gradients */
+int eunet_cast_f64_f32(const double* src, float* dst, long long n, void* stream);
+
+/* ---- loss (train_eval.py:37-60 FocalLoss, 134-157 dice_loss, 159-181 tversky_loss, 183-197 combined,
+ * 261-337 per-sample loop, 306-310 logit resize == 2x2 mean) ---- */
+int eunet_loss_fwd(const float* logits /*[B,3,2H,2W]*/, const long long* target /*[B,H,W]*/, int B, int H, int W,
+                   int logits_scale /*2: logits at 2Hx2W, 1: at HxW*/, double* partial /*[B][10], zeroed by callee*/,
+                   float* loss /*scalar*/, float* per_sample /*[B] or NULL*/, double* coef /*[B][8]*/, void* stream);
+int eunet_loss_bwd(const float* logits, const long long* target, int B, int H, int W, int logits_scale, const double* coef,
+                   const float* grad_out /*scalar, device*/, float* dlogits, void* stream);
+
+/* ---- optimiser step (train_eval.py:120, 341-343): global-norm clip + AdamW over flat fp32 buffers ---- */
+int eunet_sumsq(const float* g, long long n, double* out /*scalar, accumulates; caller zeroes*/, void* stream);
+int eunet_adamw_step(float* p, const float* g, float* m, float* v, long long n, const double* gradsq /*scalar*/,
+                     float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                     float grad_scale, void* stream);
+
+/* ---- bring-up / verification: UMMA + TMA probe (tests/test_gpu_probe.py) ---- */
+int eunet_probe_umma(const void* a, int a_rows, int a_cols, int a_box_rows, int a_box_cols, int a_swizzle, const void* b,
+                     int b_rows, int b_cols, int b_box_rows, int b_box_cols, int b_swizzle, const void* x, const int* x_dims,
+                     const int* x_box, int x_swizzle, const void* params_blob, int params_bytes, float* out_tmem,
+                     void* out_smem, int smem_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EUNET_H_ */

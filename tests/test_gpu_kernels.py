@@ -1,0 +1,338 @@
+"""Per-kernel parity through the C ABI (libeunet_b200.so via ctypes) against plain torch fp32 references
+and the CPU oracle.  Integer work is bit-exact; fp32-mode kernels <= 1e-4 (normalised max error, the
+north-star tolerance); bf16 kernels are compared against the same op evaluated on the bf16-rounded
+inputs with a tolerance that only covers accumulation-order / output-rounding differences."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DT = {"fp32": torch.float32, "bf16": torch.bfloat16}
+TOL = {"fp32": 1e-5, "bf16": 6e-3}   # output rounding of bf16 is 2^-9 relative
+
+
+@pytest.fixture(scope="module")
+def k():
+    from enhanced_unet_b200 import lib
+    lib.load()
+    return lib
+
+
+def nhwc(x: torch.Tensor, dt, ld=None, off=0):
+    """[B,C,H,W] fp32 (cpu) -> CUDA [M, C] view (of an [M, ld] buffer when ld is given)."""
+    B, C, H, W = x.shape
+    flat = x.permute(0, 2, 3, 1).reshape(-1, C)
+    if ld is None:
+        return flat.to(dt).cuda().contiguous()
+    buf = torch.full((flat.shape[0], ld), 7.0, dtype=dt, device="cuda")
+    buf[:, off:off + C] = flat.to(dt).cuda()
+    return buf[:, off:off + C]
+
+
+def nchw(t: torch.Tensor, B, H, W):
+    return t.float().cpu().reshape(B, H, W, -1).permute(0, 3, 1, 2).contiguous()
+
+
+def nerr(got: torch.Tensor, want: torch.Tensor) -> float:
+    return float((got.double() - want.double()).abs().max() / (want.double().abs().max() + 1e-12))
+
+
+def rnd(dtn, t):   # what the kernel actually reads
+    return t.to(DT[dtn]).float()
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.int64, torch.int32, torch.uint8])
+@pytest.mark.parametrize("shape", [(1, 64, 64), (3, 37, 41), (2, 1, 7), (5, 128, 130), (1, 1, 1)])
+def test_confusion_counts_bit_exact(k, dtype, shape):
+    import oracle
+    from enhanced_unet_b200.ops import confusion_counts
+    rng = np.random.default_rng(hash((str(dtype), shape)) % (2 ** 31))
+    pred = rng.integers(0, 3, shape)
+    gt = rng.integers(0, 3, shape)
+    gt[rng.random(shape) < 0.05] = 255      # ignore label
+    pred[rng.random(shape) < 0.01] = 7
+    want = oracle.confusion_counts(pred, gt)
+    got = confusion_counts(torch.from_numpy(pred).to(dtype).cuda(), torch.from_numpy(gt).to(dtype).cuda())
+    assert got.dtype == torch.int64
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_confusion_counts_large_checksum(k):
+    """Full inference-config size (32 x 1024^2, uint8): the counts of every image must sum to the pixel
+    count and match a torch bincount."""
+    from enhanced_unet_b200.ops import confusion_counts
+    g = torch.Generator(device="cuda").manual_seed(5)
+    pred = torch.randint(0, 3, (32, 1024, 1024), device="cuda", dtype=torch.uint8, generator=g)
+    gt = torch.randint(0, 4, (32, 1024, 1024), device="cuda", dtype=torch.uint8, generator=g)
+    got = confusion_counts(pred, gt)
+    assert torch.equal(got.sum((1, 2)), torch.full((32,), 1024 * 1024, device="cuda"))
+    code = (gt.clamp(max=3).long() * 4 + pred.long()).reshape(32, -1)
+    want = torch.stack([torch.bincount(code[i], minlength=16) for i in range(32)]).reshape(32, 4, 4)
+    assert torch.equal(got, want)
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtn", ["fp32", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 64, 8, 12), (1, 128, 6, 6), (3, 16, 2, 2)])
+def test_maxpool_fwd_bwd(k, dtn, shape):
+    B, C, H, W = shape
+    dt = DT[dtn]
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(shape, generator=g).relu()            # many exact ties at 0, like post-ReLU activations
+    xr = rnd(dtn, x).requires_grad_(True)
+    want = F.max_pool2d(xr, 2)
+    dp = torch.randn(want.shape, generator=g)
+    want.backward(rnd(dtn, dp))
+    xd = nhwc(x, dt, ld=C + 16, off=8)
+    out = torch.empty(B * H * W // 4, C, dtype=dt, device="cuda")
+    k.call("eunet_maxpool2_fwd", xd.data_ptr(), xd.stride(0), out.data_ptr(), C, k.dtype_code(dt), B, H, W, C)
+    assert torch.equal(nchw(out, B, H // 2, W // 2), want.detach())
+    dpd = nhwc(dp, dt)
+    dx = torch.full((B * H * W, C), 3.0, dtype=dt, device="cuda")
+    k.call("eunet_maxpool2_bwd", dpd.data_ptr(), C, xd.data_ptr(), xd.stride(0), dx.data_ptr(), C, 0, k.dtype_code(dt), B, H, W, C)
+    assert torch.equal(nchw(dx, B, H, W), xr.grad)        # first-max tie-break of ATen
+    base = torch.randn(B * H * W, C, generator=g).to(dt).cuda()
+    dx2 = base.clone()
+    k.call("eunet_maxpool2_bwd", dpd.data_ptr(), C, xd.data_ptr(), xd.stride(0), dx2.data_ptr(), C, 1, k.dtype_code(dt), B, H, W, C)
+    want2 = (base.float() + dx.float()).to(dt)
+    assert torch.equal(dx2, want2)
+
+
+@pytest.mark.parametrize("dtn", ["fp32", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 64, 5, 7), (1, 16, 1, 1), (1, 8, 1, 4), (2, 128, 8, 8)])
+def test_upsample_fwd_bwd(k, dtn, shape):
+    B, C, H, W = shape
+    dt = DT[dtn]
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(shape, generator=g)
+    xr = rnd(dtn, x).requires_grad_(True)
+    want = F.interpolate(xr, scale_factor=2, mode="bilinear", align_corners=False)
+    do = torch.randn(want.shape, generator=g)
+    want.backward(rnd(dtn, do))
+    xd = nhwc(x, dt)
+    out = torch.empty(B * 4 * H * W, C + 8, dtype=dt, device="cuda")[:, 8:]
+    k.call("eunet_upsample2_fwd", xd.data_ptr(), C, out.data_ptr(), out.stride(0), k.dtype_code(dt), B, H, W, C)
+    assert nerr(nchw(out, B, 2 * H, 2 * W), want.detach()) < TOL[dtn]
+    dod = nhwc(do, dt)
+    dx = torch.empty(B * H * W, C, dtype=dt, device="cuda")
+    k.call("eunet_upsample2_bwd", dod.data_ptr(), C, dx.data_ptr(), C, k.dtype_code(dt), B, H, W, C)
+    assert nerr(nchw(dx, B, H, W), xr.grad) < TOL[dtn]
+
+
+@pytest.mark.parametrize("dtn", ["fp32", "bf16"])
+@pytest.mark.parametrize("C", [64, 128, 512])
+def test_bn_train_apply_pool_and_backward(k, dtn, C):
+    """conv output y -> batch stats -> finalize (+running stats) -> apply+ReLU(+pool) and the full backward,
+    against torch BatchNorm2d + ReLU (+max_pool2d) in fp32 on the same (rounded) y."""
+    B, H, W = 2, 6, 8
+    dt = DT[dtn]
+    g = torch.Generator().manual_seed(3)
+    y = torch.randn(B, C, H, W, generator=g) * 1.7 + 0.3
+    bias = torch.randn(C, generator=g) * 0.1
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.2
+    rm0, rv0 = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5
+    yr = rnd(dtn, y)
+    # reference: BN sees conv output + bias
+    bn = torch.nn.BatchNorm2d(C)
+    with torch.no_grad():
+        bn.weight.copy_(gamma); bn.bias.copy_(beta); bn.running_mean.copy_(rm0); bn.running_var.copy_(rv0)
+    yin = (yr + bias[None, :, None, None]).requires_grad_(True)
+    act = F.relu(bn(yin))
+    pooled = F.max_pool2d(act, 2)
+    dact = torch.randn(act.shape, generator=g)
+    dpool = torch.randn(pooled.shape, generator=g)
+    (act * rnd(dtn, dact)).sum().backward(retain_graph=True)
+    g_act_only = yin.grad.clone()
+    # kernels
+    M = B * H * W
+    yd = nhwc(y, dt)
+    stats = torch.stack([yd.double().sum(0), (yd.double() ** 2).sum(0)]).reshape(-1).contiguous()
+    dev = lambda t: t.clone().cuda()
+    gm, bt, bs, rm, rv = dev(gamma), dev(beta), dev(bias), dev(rm0), dev(rv0)
+    nbt = torch.zeros((), dtype=torch.int64, device="cuda")
+    scale, shift, mean, invstd = (torch.empty(C, device="cuda") for _ in range(4))
+    k.call("eunet_bn_finalize", stats.data_ptr(), M, gm.data_ptr(), bt.data_ptr(), bs.data_ptr(), rm.data_ptr(), rv.data_ptr(),
+           nbt.data_ptr(), 0.1, 1e-5, scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), C)
+    assert int(nbt) == 1
+    assert nerr(rm.cpu(), bn.running_mean) < 1e-5 and nerr(rv.cpu(), bn.running_var) < 1e-5
+    out = torch.empty(M, C + 8, dtype=dt, device="cuda")[:, :C]
+    pl = torch.empty(M // 4, C, dtype=dt, device="cuda")
+    k.call("eunet_bn_apply_relu", yd.data_ptr(), C, out.data_ptr(), out.stride(0), pl.data_ptr(), C, k.dtype_code(dt), B, H, W, C,
+           scale.data_ptr(), shift.data_ptr())
+    assert nerr(nchw(out, B, H, W), act.detach()) < TOL[dtn]
+    assert torch.equal(nchw(pl, B, H // 2, W // 2), F.max_pool2d(nchw(out, B, H, W), 2))
+    out2 = torch.empty(M, C, dtype=dt, device="cuda")
+    k.call("eunet_bn_apply_relu", yd.data_ptr(), C, out2.data_ptr(), C, None, 0, k.dtype_code(dt), B, H, W, C,
+           scale.data_ptr(), shift.data_ptr())
+    assert torch.equal(out2, out.contiguous())
+    # backward
+    dad = nhwc(dact, dt)
+    sums = torch.zeros(2 * C, dtype=torch.float64, device="cuda")
+    k.call("eunet_bn_bwd_reduce", dad.data_ptr(), C, yd.data_ptr(), C, k.dtype_code(dt), M, C, scale.data_ptr(), shift.data_ptr(),
+           mean.data_ptr(), invstd.data_ptr(), sums.data_ptr())
+    dy = torch.empty(M, C, dtype=dt, device="cuda")
+    dg, db = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    k.call("eunet_bn_bwd_apply", dad.data_ptr(), C, yd.data_ptr(), C, dy.data_ptr(), C, k.dtype_code(dt), M, C, scale.data_ptr(),
+           shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), sums.data_ptr(), dg.data_ptr(), db.data_ptr())
+    assert nerr(nchw(dy, B, H, W), g_act_only) < 2 * TOL[dtn]
+    assert nerr(dg.cpu(), bn.weight.grad) < 1e-4 and nerr(db.cpu(), bn.bias.grad) < 1e-4
+    # eval fold: conv epilogue affine == BN(eval)(y + bias)
+    bn.eval()
+    s2, h2 = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    k.call("eunet_bn_fold_eval", gm.data_ptr(), bt.data_ptr(), bs.data_ptr(), rm.data_ptr(), rv.data_ptr(), 1e-5, s2.data_ptr(),
+           h2.data_ptr(), C)
+    with torch.no_grad():
+        want_eval = bn(yr + bias[None, :, None, None])
+    got_eval = yr * s2.cpu()[None, :, None, None] + h2.cpu()[None, :, None, None]
+    assert nerr(got_eval, want_eval) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+CONV_CASES = [
+    # B, H, W, Cin, Cout
+    (2, 16, 16, 64, 64),
+    (1, 8, 24, 128, 128),
+    (2, 8, 8, 256, 256),
+    (1, 4, 4, 512, 512),      # two N tiles of 256
+    (1, 8, 8, 192, 64),       # concat-sized Cin
+    (2, 12, 20, 16, 64),      # 16-channel chunks (first layer / enhance.0), ragged tile
+    (1, 16, 16, 64, 16),      # dgrad of enhance.0 (N = 16)
+    (3, 2, 2, 64, 128),       # tiny spatial extent: batch folded into the pixel tile
+    (1, 40, 24, 64, 64),      # overhanging tiles
+]
+
+
+def _conv_ref(x, w):
+    return F.conv2d(x, w, None, padding=1)
+
+
+@pytest.mark.parametrize("dtn", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv3x3_fwd_stats_and_epilogue(k, dtn, case):
+    B, H, W, Cin, Cout = case
+    dt = DT[dtn]
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)
+    want = _conv_ref(rnd(dtn, x), rnd(dtn, w))
+    xd = nhwc(x, dt, ld=Cin + 16, off=16)
+    wp = torch.empty(Cout, 9, Cin, dtype=dt, device="cuda")
+    k.call("eunet_pack_weight3x3", w.cuda().data_ptr(), wp.data_ptr(), k.dtype_code(dt), Cout, Cin, Cout, Cin, 0)
+    assert torch.equal(wp.float().cpu(), rnd(dtn, w).permute(0, 2, 3, 1).reshape(Cout, 9, Cin))
+    M = B * H * W
+    ybuf = torch.full((M, Cout + 8), 5.0, dtype=dt, device="cuda")
+    y = ybuf[:, 8:]
+    stats = torch.zeros(2 * Cout, dtype=torch.float64, device="cuda")
+    k.call("eunet_conv3x3_fwd", xd.data_ptr(), xd.stride(0), wp.data_ptr(), y.data_ptr(), y.stride(0), k.dtype_code(dt), B, H, W,
+           Cin, Cout, stats.data_ptr(), None, None, 0)
+    torch.cuda.synchronize()
+    assert nerr(nchw(y, B, H, W), want) < TOL[dtn]
+    assert torch.all(ybuf[:, :8] == 5.0)                       # neighbouring channels of the wider buffer untouched
+    s = stats.cpu()
+    assert nerr(s[:Cout], want.double().sum((0, 2, 3))) < 1e-4
+    assert nerr(s[Cout:], (want.double() ** 2).sum((0, 2, 3))) < 1e-4
+    # fused eval epilogue: affine + ReLU
+    sc, sh = (torch.rand(Cout, generator=g) + 0.5).cuda(), torch.randn(Cout, generator=g).cuda()
+    y2 = torch.empty(M, Cout, dtype=dt, device="cuda")
+    k.call("eunet_conv3x3_fwd", xd.data_ptr(), xd.stride(0), wp.data_ptr(), y2.data_ptr(), Cout, k.dtype_code(dt), B, H, W,
+           Cin, Cout, None, sc.data_ptr(), sh.data_ptr(), 1)
+    want2 = F.relu(want * sc.cpu()[None, :, None, None] + sh.cpu()[None, :, None, None])
+    assert nerr(nchw(y2, B, H, W), want2) < TOL[dtn]
+
+
+@pytest.mark.parametrize("dtn", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv3x3_dgrad_and_wgrad(k, dtn, case):
+    B, H, W, Cin, Cout = case
+    dt = DT[dtn]
+    g = torch.Generator().manual_seed(hash(case) % 1000 + 1)
+    x = rnd(dtn, torch.randn(B, Cin, H, W, generator=g)).requires_grad_(True)
+    w = rnd(dtn, torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).requires_grad_(True)
+    dy = rnd(dtn, torch.randn(B, Cout, H, W, generator=g))
+    _conv_ref(x, w).backward(dy)
+    xd, dyd = nhwc(x.detach(), dt), nhwc(dy, dt, ld=Cout + 8, off=0)
+    M = B * H * W
+    # dgrad = forward conv over dY with the flipped / transposed pack
+    wpT = torch.empty(Cin, 9, Cout, dtype=dt, device="cuda")
+    k.call("eunet_pack_weight3x3", w.detach().cuda().data_ptr(), wpT.data_ptr(), k.dtype_code(dt), Cout, Cin, Cout, Cin, 1)
+    dx = torch.empty(M, Cin, dtype=dt, device="cuda")
+    k.call("eunet_conv3x3_fwd", dyd.data_ptr(), dyd.stride(0), wpT.data_ptr(), dx.data_ptr(), Cin, k.dtype_code(dt), B, H, W,
+           Cout, Cin, None, None, None, 0)
+    assert nerr(nchw(dx, B, H, W), x.grad) < TOL[dtn]
+    dwp = torch.zeros(Cout, 9, Cin, dtype=torch.float32, device="cuda")
+    k.call("eunet_conv3x3_wgrad", xd.data_ptr(), Cin, dyd.data_ptr(), dyd.stride(0), dwp.data_ptr(), k.dtype_code(dt), B, H, W,
+           Cin, Cout)
+    dw = torch.empty(Cout, Cin, 3, 3, device="cuda")
+    k.call("eunet_unpack_wgrad3x3", dwp.data_ptr(), dw.data_ptr(), Cout, Cin, Cin)
+    assert nerr(dw.cpu(), w.grad) < 2e-5     # fp32 accumulation in both modes (inputs are identical)
+
+
+def test_pack_input_and_padded_weights(k):
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand(2, 3, 8, 8, generator=g)
+    out = torch.empty(2 * 64, 16, dtype=torch.bfloat16, device="cuda")
+    k.call("eunet_pack_input_nchw", x.cuda().data_ptr(), out.data_ptr(), k.BF16, 2, 3, 8, 8, 16)
+    want = torch.zeros(2, 16, 8, 8); want[:, :3] = x.to(torch.bfloat16).float()
+    assert torch.equal(nchw(out, 2, 8, 8), want)
+    w = torch.randn(64, 3, 3, 3, generator=g)
+    wp = torch.empty(64, 9, 16, dtype=torch.float32, device="cuda")
+    k.call("eunet_pack_weight3x3", w.cuda().data_ptr(), wp.data_ptr(), k.F32, 64, 3, 64, 16, 0)
+    ref = torch.zeros(64, 9, 16); ref[:, :, :3] = w.permute(0, 2, 3, 1).reshape(64, 9, 3)
+    assert torch.equal(wp.cpu(), ref)
+    wpT = torch.empty(16, 9, 64, dtype=torch.float32, device="cuda")
+    k.call("eunet_pack_weight3x3", w.cuda().data_ptr(), wpT.data_ptr(), k.F32, 64, 3, 64, 16, 1)
+    refT = torch.zeros(16, 9, 64); refT[:3] = w.flip(2, 3).permute(1, 2, 3, 0).reshape(3, 9, 64)
+    assert torch.equal(wpT.cpu(), refT)
+
+
+# ---------------------------------------------------------------------------------------------
+def test_loss_matches_reference_fixture_and_oracle(k, golden_dir):
+    import os
+    import oracle
+    from enhanced_unet_b200.ops import combined_loss
+    gold = np.load(os.path.join(golden_dir, "loss.npz"))
+    for name in "abc":
+        logits = torch.from_numpy(gold[f"{name}/logits"]).cuda().requires_grad_(True)
+        t = torch.from_numpy(gold[f"{name}/target"]).cuda()
+        loss = combined_loss(logits, t)
+        ref = float(gold[f"{name}/loss"])
+        assert abs(loss.item() - ref) <= 1e-5 * abs(ref), (name, loss.item(), ref)
+        (loss * 1.0).backward()
+        rg = torch.from_numpy(gold[f"{name}/grad"])
+        assert nerr(logits.grad.cpu(), rg) < 2e-5, name
+    # same-resolution logits (scale 1) against the oracle
+    g = torch.Generator().manual_seed(12)
+    lg = torch.randn(2, 3, 24, 40, generator=g) * 2
+    tg = torch.randint(0, 3, (2, 24, 40), generator=g)
+    lr = lg.clone().requires_grad_(True)
+    want = oracle.batch_loss(lr, tg)
+    want.backward()
+    lc = lg.cuda().requires_grad_(True)
+    got = combined_loss(lc, tg.cuda())
+    (got * 3.0).backward()
+    assert abs(got.item() - want.item()) <= 1e-5 * abs(want.item())
+    assert nerr(lc.grad.cpu(), 3.0 * lr.grad) < 2e-5
+
+
+def test_adamw_and_clip_against_torch(k):
+    g = torch.Generator().manual_seed(13)
+    n = 10007
+    p0, g0 = torch.randn(n, generator=g), torch.randn(n, generator=g) * 3
+    pr = p0.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([pr], lr=4e-3, weight_decay=1e-4, betas=(0.9, 0.999))
+    p, m, v = p0.clone().cuda(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    for step in range(1, 4):
+        gi = g0 * step
+        pr.grad = gi.clone()
+        torch.nn.utils.clip_grad_norm_([pr], 1.0)
+        opt.step()
+        gd = gi.cuda()
+        sq = torch.zeros((), dtype=torch.float64, device="cuda")
+        k.call("eunet_sumsq", gd.data_ptr(), n, sq.data_ptr())
+        assert abs(sq.item() - float((gi.double() ** 2).sum())) < 1e-6 * sq.item()
+        k.call("eunet_adamw_step", p.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), n, sq.data_ptr(), 1.0, 4e-3, 0.9,
+               0.999, 1e-8, 1e-4, step, 1.0)
+        assert nerr(p.cpu(), pr.detach()) < 1e-5

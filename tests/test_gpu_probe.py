@@ -1,0 +1,160 @@
+"""Pins the tcgen05 shared-memory / instruction descriptor encodings and the TMA box layouts used by
+csrc/conv_tc.cu against numpy matmuls, through the probe kernel (csrc/probe.cu).  Each experiment also
+records alternatives in gpurun_out/probe_report.json so a failed hypothesis tells us what WOULD work."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+REPORT = {}
+
+
+def _save():
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "probe_report.json"), "w") as f:
+        json.dump(REPORT, f, indent=1, sort_keys=True)
+
+
+def _err(got, want):
+    return float(np.abs(got - want).max() / (np.abs(want).max() + 1e-9))
+
+
+@pytest.fixture(scope="module")
+def pu():
+    from tests import probe_util
+    return probe_util
+
+
+def _dummy_x():
+    return torch.zeros(1, 8, 8, 64, device="cuda", dtype=torch.bfloat16)
+
+
+def test_kmajor_sw128(pu):
+    """Forward conv operand layout: rows of 64 bf16 (128 B), 128B swizzle, SBO = 1024, K advance = +32 B."""
+    a = pu.rand_bf16(128, 64, seed=1).cuda()
+    b = pu.rand_bf16(64, 64, seed=2).cuda()
+    want = pu.f32(a) @ pu.f32(b).T
+    loads = [(0, (0, 0), 0), (1, (0, 0), 16384)]
+    res = {}
+    for lbo in (16, 0, 1024):
+        mmas = [(pu.smem_desc(0 + 32 * j, lbo, 1024, pu.SW128), pu.smem_desc(16384 + 32 * j, lbo, 1024, pu.SW128),
+                 pu.idesc_bf16(128, 64, 0, 0), int(j > 0), 0) for j in range(4)]
+        t, s = pu.run_probe(a, (128, 64), 128, b, (64, 64), 128, _dummy_x(), (64, 8, 8, 1), 128, loads, 16384 + 8192, mmas, 64,
+                            32768, 32768)
+        res[f"lbo{lbo}"] = _err(t[:, :64], want)
+    # the TMA 128B swizzle: 16-byte chunk c of row r lands at chunk (c ^ (r & 7))
+    raw = s[:16384].view(np.uint16).reshape(128, 8, 8)
+    src = a.cpu().view(torch.int16).numpy().view(np.uint16).reshape(128, 8, 8)
+    unsw = np.stack([raw[r, [c ^ (r & 7) for c in range(8)]] for r in range(128)])
+    res["tma_swizzle_ok"] = bool((unsw == src).all())
+    REPORT["kmajor_sw128"] = res
+    _save()
+    assert res["lbo16"] < 1e-5, res
+    assert res["tma_swizzle_ok"]
+
+
+def test_kmajor_sw32(pu):
+    """16-channel chunks (first layer / enhance head): rows of 16 bf16 (32 B), 32B swizzle, SBO = 256."""
+    a = pu.rand_bf16(128, 16, seed=3).cuda()
+    b = pu.rand_bf16(64, 16, seed=4).cuda()
+    want = pu.f32(a) @ pu.f32(b).T
+    loads = [(0, (0, 0), 0), (1, (0, 0), 4096)]
+    res = {}
+    for sbo in (256, 512):
+        mmas = [(pu.smem_desc(0, 16, sbo, pu.SW32), pu.smem_desc(4096, 16, sbo, pu.SW32), pu.idesc_bf16(128, 64, 0, 0), 0, 0)]
+        t, _ = pu.run_probe(a, (128, 16), 32, b, (64, 16), 32, _dummy_x(), (64, 8, 8, 1), 128, loads, 4096 + 2048, mmas, 64, 8192,
+                            8192)
+        res[f"sbo{sbo}"] = _err(t[:, :64], want)
+    REPORT["kmajor_sw32"] = res
+    _save()
+    assert res["sbo256"] < 1e-5, res
+
+
+def test_mnmajor_sw128(pu):
+    """wgrad operand layout: tiles [64 pixels (K)][64 channels (MN)] exactly as TMA writes NHWC boxes,
+    consumed MN-major.  A' = 2 blocks (128 channels), B' = 3 blocks (192), LBO = block stride 8192,
+    SBO = 8-pixel group stride 1024, K advance = 16 rows = 2048 B."""
+    at = pu.rand_bf16(64, 128, seed=5).cuda()     # [k, m]
+    bt = pu.rand_bf16(64, 192, seed=6).cuda()     # [k, n]
+    want = pu.f32(at).T @ pu.f32(bt)
+    loads = [(0, (0, 0), 0), (0, (64, 0), 8192)] + [(1, (64 * i, 0), 16384 + 8192 * i) for i in range(3)]
+    res = {}
+    for name, (lbo, sbo) in {"lbo8192_sbo1024": (8192, 1024), "lbo1024_sbo8192": (1024, 8192)}.items():
+        mmas = [(pu.smem_desc(0 + 2048 * j, lbo, sbo, pu.SW128), pu.smem_desc(16384 + 2048 * j, lbo, sbo, pu.SW128),
+                 pu.idesc_bf16(128, 192, 1, 1), int(j > 0), 0) for j in range(4)]
+        t, _ = pu.run_probe(at, (64, 64), 128, bt, (64, 64), 128, _dummy_x(), (64, 8, 8, 1), 128, loads, 5 * 8192, mmas, 256, 65536,
+                            16)
+        res[name] = _err(t[:, :192], want)
+    REPORT["mnmajor_sw128"] = res
+    _save()
+    assert res["lbo8192_sbo1024"] < 1e-5, res
+
+
+def test_mnmajor_sw32_b_operand(pu):
+    """wgrad with 16-channel input chunks: B' = 9 tap tiles [64 px][16 ch] (32B swizzle), N = 144."""
+    at = pu.rand_bf16(64, 128, seed=7).cuda()
+    bt = pu.rand_bf16(64, 144, seed=8).cuda()
+    want = pu.f32(at).T @ pu.f32(bt)
+    loads = [(0, (0, 0), 0), (0, (64, 0), 8192)] + [(1, (16 * i, 0), 16384 + 2048 * i) for i in range(9)]
+    res = {}
+    for name, (lbo, sbo, kadv) in {"lbo2048_sbo256_k512": (2048, 256, 512), "lbo256_sbo2048_k512": (256, 2048, 512)}.items():
+        mmas = [(pu.smem_desc(0 + 2048 * j, 8192, 1024, pu.SW128), pu.smem_desc(16384 + kadv * j, lbo, sbo, pu.SW32),
+                 pu.idesc_bf16(128, 144, 1, 1), int(j > 0), 0) for j in range(4)]
+        t, _ = pu.run_probe(at, (64, 64), 128, bt, (64, 16), 32, _dummy_x(), (64, 8, 8, 1), 128, loads, 16384 + 9 * 2048, mmas, 256,
+                            65536, 16)
+        res[name] = _err(t[:, :144], want)
+    REPORT["mnmajor_sw32"] = res
+    _save()
+    assert res["lbo2048_sbo256_k512"] < 1e-5, res
+
+
+def test_tma_4d_box_zero_fill_and_row_order(pu):
+    """The conv A operand: one 4-D box {64 ch, bw, bh, bb} at a shifted origin; out-of-bounds pixels must
+    read as zero and box row r must be pixel (bb, y, x) = (r / (bh*bw), (r / bw) % bh, r % bw)."""
+    B, H, W, Cc = 2, 6, 10, 64
+    x = pu.rand_bf16(B, H, W, Cc, seed=9).cuda()
+    eye = torch.eye(64, dtype=torch.bfloat16).cuda()
+    bw, bh, bb = 16, 4, 2
+    x0, y0, b0 = -1, -1, 0     # tap (0,0) of the tile at the image origin
+    loads = [(2, (0, x0, y0, b0), 0), (1, (0, 0), 16384)]
+    mmas = [(pu.smem_desc(32 * j, 16, 1024, pu.SW128), pu.smem_desc(16384 + 32 * j, 16, 1024, pu.SW128),
+             pu.idesc_bf16(128, 64, 0, 0), int(j > 0), 0) for j in range(4)]
+    dummy = torch.zeros(128, 64, device="cuda", dtype=torch.bfloat16)
+    t, _ = pu.run_probe(dummy, (128, 64), 128, eye, (64, 64), 128, x, (64, bw, bh, bb), 128, loads, 16384 + 8192, mmas, 64, 32768,
+                        16)
+    xf = pu.f32(x)
+    want = np.zeros((128, 64), np.float32)
+    for r in range(128):
+        xx, yy, b_ = r % bw, (r // bw) % bh, r // (bw * bh)
+        gx, gy, gb = x0 + xx, y0 + yy, b0 + b_
+        if 0 <= gx < W and 0 <= gy < H and 0 <= gb < B:
+            want[r] = xf[gb, gy, gx]
+    err = _err(t[:, :64], want)
+    REPORT["tma_4d"] = {"err": err}
+    _save()
+    assert err < 1e-6, err
+
+
+def test_row_shifted_descriptor_start(pu):
+    """Exploratory (feeds the halo-reuse optimisation): does a K-major SW128 A operand whose start address
+    is shifted by r rows (r*128 B) read rows r..r+127?  Variants: base_offset = 0 / r.  Reported, not required."""
+    a = pu.rand_bf16(256, 64, seed=10).cuda()
+    b = pu.rand_bf16(64, 64, seed=11).cuda()
+    loads = [(0, (0, 0), 0), (0, (0, 128), 16384), (1, (0, 0), 32768)]
+    res = {}
+    for r in (1, 2, 3, 8, 16, 19):
+        want = pu.f32(a)[r:r + 128] @ pu.f32(b).T
+        for bo_name, bo in (("bo0", 0), ("bor", r & 7)):
+            mmas = [(pu.smem_desc(128 * r + 32 * j, 16, 1024, pu.SW128, bo), pu.smem_desc(32768 + 32 * j, 16, 1024, pu.SW128),
+                     pu.idesc_bf16(128, 64, 0, 0), int(j > 0), 0) for j in range(4)]
+            t, _ = pu.run_probe(a, (128, 64), 128, b, (64, 64), 128, _dummy_x(), (64, 8, 8, 1), 128, loads, 2 * 16384 + 8192, mmas,
+                                64, 65536, 16)
+            res[f"shift{r}_{bo_name}"] = _err(t[:, :64], want)
+    REPORT["row_shift"] = res
+    _save()
+    assert res["shift8_bo0"] < 1e-5 and res["shift16_bo0"] < 1e-5, res   # whole swizzle atoms must work
