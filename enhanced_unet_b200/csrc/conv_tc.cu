@@ -429,7 +429,7 @@ static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDY, ConvWgr
 
 static int conv3x3_wgrad_bf16(const void* x, int ldx, const void* dy, int lddy, float* dw, int B, int H, int W, int Cin, int Cout,
                               cudaStream_t st) {
-  EUNET_REQUIRE(Cin % 16 == 0 && Cout % 16 == 0, "conv3x3_wgrad(bf16): Cin=%d and Cout=%d must be multiples of 16", Cin, Cout);
+  EUNET_REQUIRE(Cin % 16 == 0 && Cout % 64 == 0, "conv3x3_wgrad(bf16): Cin=%d must be a multiple of 16 and Cout=%d of 64", Cin, Cout);
   EUNET_REQUIRE(ldx % 8 == 0 && lddy % 8 == 0 && ldx >= Cin && lddy >= Cout, "conv3x3_wgrad(bf16): bad ld (%d, %d)", ldx, lddy);
   const int KC = (Cin % 64 == 0) ? 64 : 16;
   const PixelTile t = choose_pixel_tile(B, H, W, 64);

@@ -83,12 +83,13 @@ def conv3x3(cx: _Ctx, x: torch.Tensor, wp: torch.Tensor, y: torch.Tensor, B: int
             stats: Optional[torch.Tensor] = None, scale: Optional[torch.Tensor] = None,
             shift: Optional[torch.Tensor] = None, relu: bool = False) -> None:
     call("eunet_conv3x3_fwd", ptr(x), _ld(x), ptr(wp), ptr(y), _ld(y), cx.code, B, H, W, cin, cout, ptr(stats), ptr(scale),
-         ptr(shift), int(relu))
+         ptr(shift), int(relu), flops=2.0 * B * H * W * cout * 9 * cin)
 
 
 def conv3x3_wgrad(cx: _Ctx, x: torch.Tensor, dy: torch.Tensor, B: int, H: int, W: int, cin: int, cout: int) -> torch.Tensor:
     dwp = cx.zeros(cout, 9, cin, dtype=torch.float32)
-    call("eunet_conv3x3_wgrad", ptr(x), _ld(x), ptr(dy), _ld(dy), ptr(dwp), cx.code, B, H, W, cin, cout)
+    call("eunet_conv3x3_wgrad", ptr(x), _ld(x), ptr(dy), _ld(dy), ptr(dwp), cx.code, B, H, W, cin, cout,
+         flops=2.0 * B * H * W * cout * 9 * cin)
     return dwp
 
 

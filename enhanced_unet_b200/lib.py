@@ -100,12 +100,36 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return t.data_ptr()
 
 
-def call(name: str, *args) -> None:
+# number of C-ABI calls per entry point since the last COUNTERS.clear() (each call launches >= 1 kernel)
+COUNTERS: dict = {}
+# when a list: every call is bracketed by CUDA events on the launching stream -> (name, e0, e1, flops)
+PROFILE: Optional[list] = None
+
+
+def call(name: str, *args, flops: float = 0.0) -> None:
     """Invoke ``name`` with the current torch CUDA stream appended; raise on a non-zero status."""
     lib = load()
-    rc = getattr(lib, name)(*args, stream_ptr())
+    COUNTERS[name] = COUNTERS.get(name, 0) + 1
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args, stream_ptr())
+        e1.record()
+        PROFILE.append((name, e0, e1, flops))
+    else:
+        rc = getattr(lib, name)(*args, stream_ptr())
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {last_error()}")
+
+
+def collect_profile() -> dict:
+    """name -> (total flops, total ms, launches) for the calls recorded since PROFILE was set."""
+    torch.cuda.synchronize()
+    out: dict = {}
+    for name, e0, e1, fl in PROFILE or []:
+        f, ms, n = out.get(name, (0.0, 0.0, 0))
+        out[name] = (f + fl, ms + e0.elapsed_time(e1), n + 1)
+    return out
 
 
 def dtype_code(dt: torch.dtype) -> int:
