@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -63,11 +64,41 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const F8& r) {
   u.w = pack_bf16x2(r.v[6], r.v[7]);
   *reinterpret_cast<uint4*>(p) = u;
 }
+// fp16 storage is used for the RAW (pre-BatchNorm) convolution outputs in bf16 mode: 11 mantissa bits keep the
+// rounding error of values whose mean is large against their spread 8x below bf16 ("raw fp16").
+__device__ __forceinline__ F8 load8(const __half* p) {
+  F8 r;
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    r.v[2 * i] = f.x;
+    r.v[2 * i + 1] = f.y;
+  }
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  lo = fminf(fmaxf(lo, -65504.f), 65504.f);   // saturate instead of overflowing to inf
+  hi = fminf(fmaxf(hi, -65504.f), 65504.f);
+  __half2 t = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void store8(__half* p, const F8& r) {
+  uint4 u;
+  u.x = pack_f16x2(r.v[0], r.v[1]);
+  u.y = pack_f16x2(r.v[2], r.v[3]);
+  u.z = pack_f16x2(r.v[4], r.v[5]);
+  u.w = pack_f16x2(r.v[6], r.v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
 __device__ __forceinline__ float to_f32(float x) { return x; }
+__device__ __forceinline__ float to_f32(__half x) { return __half2float(x); }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 x) { return __bfloat162float(x); }
 template <typename T> __device__ __forceinline__ T from_f32(float x);
 template <> __device__ __forceinline__ float from_f32<float>(float x) { return x; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+template <> __device__ __forceinline__ __half from_f32<__half>(float x) { return __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f)); }
 
 // value after a round trip through the storage type (so that statistics / masks computed from
 // fp32 accumulators agree with what later kernels read back)

@@ -47,6 +47,7 @@ struct ConvFwdParams {
   const float* scale;
   const float* shift;
   int relu;
+  int out_f16;   // 1: store fp16 (raw pre-BN tensor), 0: store bf16 (activation / gradient)
 };
 
 struct ConvWgradParams {
@@ -198,10 +199,17 @@ conv3x3_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             o[e] = f;
           }
           uint4 u;
-          u.x = pack_bf16x2(o[0], o[1]);
-          u.y = pack_bf16x2(o[2], o[3]);
-          u.z = pack_bf16x2(o[4], o[5]);
-          u.w = pack_bf16x2(o[6], o[7]);
+          if (p.out_f16) {
+            u.x = pack_f16x2(o[0], o[1]);
+            u.y = pack_f16x2(o[2], o[3]);
+            u.z = pack_f16x2(o[4], o[5]);
+            u.w = pack_f16x2(o[6], o[7]);
+          } else {
+            u.x = pack_bf16x2(o[0], o[1]);
+            u.y = pack_bf16x2(o[2], o[3]);
+            u.z = pack_bf16x2(o[4], o[5]);
+            u.w = pack_bf16x2(o[6], o[7]);
+          }
           *reinterpret_cast<uint4*>(yrow + c0 + g8 * 8) = u;
         }
       }
@@ -367,7 +375,7 @@ static int launch_fwd(const CUtensorMap& tmX, const CUtensorMap& tmW, const Conv
 }
 
 static int conv3x3_fwd_bf16(const void* x, int ldx, const void* w, void* y, int ldy, int B, int H, int W, int Cin, int Cout,
-                            double* stats, const float* scale, const float* shift, int relu, cudaStream_t st) {
+                            double* stats, const float* scale, const float* shift, int relu, int out_raw, cudaStream_t st) {
   EUNET_REQUIRE(Cin % 16 == 0 && Cout % 16 == 0, "conv3x3_fwd(bf16): Cin=%d and Cout=%d must be multiples of 16", Cin, Cout);
   EUNET_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && ldx >= Cin && ldy >= Cout, "conv3x3_fwd(bf16): bad ld (%d, %d)", ldx, ldy);
   EUNET_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0, "conv3x3_fwd(bf16): y not 16-byte aligned");
@@ -385,7 +393,7 @@ static int conv3x3_fwd_bf16(const void* x, int ldx, const void* w, void* y, int 
   p.y = (__nv_bfloat16*)y; p.ldy = ldy;
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.bw = t.bw; p.bh = t.bh; p.bb = t.bb; p.tiles_x = t.tiles_x; p.tiles_y = t.tiles_y;
-  p.stats = stats; p.scale = scale; p.shift = shift; p.relu = relu;
+  p.stats = stats; p.scale = scale; p.shift = shift; p.relu = relu; p.out_f16 = out_raw ? 1 : 0;
   const long long mt = t.tiles();
   const int nt = Cout / BN;
   EUNET_REQUIRE(mt <= 0x7fffffffLL, "conv3x3_fwd(bf16): too many tiles");
@@ -453,12 +461,12 @@ using namespace eunet;
 
 extern "C" int eunet_conv3x3_fwd(const void* x, int ldx, const void* w_packed, void* y, int ldy, int dtype, int B, int H, int W,
                                  int Cin, int Cout, double* stats, const float* scale, const float* shift, int relu,
-                                 void* stream) {
+                                 int out_raw, void* stream) {
   EUNET_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv3x3_fwd: bad shape");
   EUNET_REQUIRE((scale == nullptr) == (shift == nullptr), "conv3x3_fwd: scale and shift must be given together");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == EUNET_BF16)
-    return conv3x3_fwd_bf16(x, ldx, w_packed, y, ldy, B, H, W, Cin, Cout, stats, scale, shift, relu, st);
+    return conv3x3_fwd_bf16(x, ldx, w_packed, y, ldy, B, H, W, Cin, Cout, stats, scale, shift, relu, out_raw, st);
   if (dtype == EUNET_F32) {
     EUNET_REQUIRE(Cin % 16 == 0 && Cout % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "conv3x3_fwd(f32): Cin%%16, Cout%%4, ld%%4");
     return conv3x3_fwd_f32((const float*)x, ldx, (const float*)w_packed, (float*)y, ldy, B, H, W, Cin, Cout, stats, scale, shift,

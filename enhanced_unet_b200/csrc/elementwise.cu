@@ -10,9 +10,11 @@ namespace eunet {
   do {                                                      \
     if ((dtype) == EUNET_BF16) {                            \
       using T = __nv_bfloat16;                              \
+      using TY = __half;                                    \
       __VA_ARGS__;                                          \
     } else if ((dtype) == EUNET_F32) {                      \
       using T = float;                                      \
+      using TY = float;                                     \
       __VA_ARGS__;                                          \
     } else {                                                \
       set_error("unknown dtype %d", (int)(dtype));          \
@@ -72,8 +74,8 @@ __global__ void bn_fold_eval_kernel(const float* __restrict__ gamma, const float
 // ------------------------------------------------------------------------------------------------
 // BN apply + ReLU (+ fused 2x2 max-pool)
 // ------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void bn_apply_relu_kernel(const T* __restrict__ y, int ldy, T* __restrict__ out, int ldo, long long M, int C,
+template <typename T, typename TY>
+__global__ void bn_apply_relu_kernel(const TY* __restrict__ y, int ldy, T* __restrict__ out, int ldo, long long M, int C,
                                      const float* __restrict__ scale, const float* __restrict__ shift) {
   const int G = C >> 3;
   const long long items = M * G;
@@ -88,8 +90,8 @@ __global__ void bn_apply_relu_kernel(const T* __restrict__ y, int ldy, T* __rest
   }
 }
 
-template <typename T>
-__global__ void bn_apply_relu_pool_kernel(const T* __restrict__ y, int ldy, T* __restrict__ out, int ldo,
+template <typename T, typename TY>
+__global__ void bn_apply_relu_pool_kernel(const TY* __restrict__ y, int ldy, T* __restrict__ out, int ldo,
                                           T* __restrict__ pooled, int ldp, int B, int H, int W, int C,
                                           const float* __restrict__ scale, const float* __restrict__ shift) {
   const int G = C >> 3, Hp = H >> 1, Wp = W >> 1;
@@ -288,9 +290,9 @@ __global__ void upsample2_bwd_kernel(const T* __restrict__ dout, int ldo, T* __r
 // BatchNorm + ReLU backward
 // ------------------------------------------------------------------------------------------------
 // Block = 256 threads = G channel groups x R pixel lanes (G = C/8 divides 256).
-template <typename T>
+template <typename T, typename TY>
 __global__ void __launch_bounds__(256)
-bn_bwd_reduce_kernel(const T* __restrict__ dact, int ldd, const T* __restrict__ y, int ldy, long long M, int C,
+bn_bwd_reduce_kernel(const T* __restrict__ dact, int ldd, const TY* __restrict__ y, int ldy, long long M, int C,
                      const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                      const float* __restrict__ invstd, double* __restrict__ sums) {
   __shared__ float red[2][256 * 8];
@@ -323,34 +325,38 @@ bn_bwd_reduce_kernel(const T* __restrict__ dact, int ldd, const T* __restrict__ 
   }
 }
 
-template <typename T>
-__global__ void bn_bwd_apply_kernel(const T* __restrict__ dact, int ldd, const T* __restrict__ y, int ldy, T* __restrict__ dy,
-                                    int lddy, long long M, int C, const float* __restrict__ scale,
-                                    const float* __restrict__ shift, const float* __restrict__ mean,
-                                    const float* __restrict__ invstd, const double* __restrict__ sums,
-                                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int G = C >> 3;
+template <typename T, typename TY>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const T* __restrict__ dact, int ldd, const TY* __restrict__ y, int ldy, T* __restrict__ dy, int lddy,
+                    long long M, int C, const float* __restrict__ scale, const float* __restrict__ shift,
+                    const float* __restrict__ mean, const float* __restrict__ invstd, const double* __restrict__ sums,
+                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  // block = 256 threads = G channel groups x R pixel lanes (G = C/8 divides 256): every thread keeps ONE channel
+  // group, so the per-channel constants are loaded once
+  const int G = C >> 3, R = 256 / G;
   if (blockIdx.x == 0) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       if (dbeta) dbeta[c] = (float)sums[c];
       if (dgamma) dgamma[c] = (float)sums[C + c];
     }
   }
+  const int cg = threadIdx.x % G, r = threadIdx.x / G;
   const double invM = 1.0 / (double)M;
-  const long long items = M * G;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % G);
-    const long long p = i / G;
-    const F8 sc = load8(scale + cg * 8), sh = load8(shift + cg * 8), mu = load8(mean + cg * 8), is = load8(invstd + cg * 8);
+  const F8 sc = load8(scale + cg * 8), sh = load8(shift + cg * 8), mu = load8(mean + cg * 8), is = load8(invstd + cg * 8);
+  float k1[8], k2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    k1[e] = (float)(sums[cg * 8 + e] * invM);
+    k2[e] = (float)(sums[C + cg * 8 + e] * invM);
+  }
+  for (long long p = (long long)blockIdx.x * R + r; p < M; p += (long long)gridDim.x * R) {
     const F8 d = load8(dact + p * ldd + cg * 8), v = load8(y + p * ldy + cg * 8);
     F8 o;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int c = cg * 8 + e;
-      const float k1 = (float)(sums[c] * invM), k2 = (float)(sums[C + c] * invM);
       const float g = fmaf(v.v[e], sc.v[e], sh.v[e]) > 0.f ? d.v[e] : 0.f;
       const float xhat = (v.v[e] - mu.v[e]) * is.v[e];
-      o.v[e] = sc.v[e] * (g - k1 - xhat * k2);
+      o.v[e] = sc.v[e] * (g - k1[e] - xhat * k2[e]);
     }
     store8(dy + p * lddy + cg * 8, o);
   }
@@ -452,10 +458,10 @@ int eunet_bn_apply_relu(const void* y, int ldy, void* out, int ldo, void* pooled
   if (pooled) {
     if (check_vec(pooled, ldp, C, "bn_apply_relu(pooled)")) return -1;
     EUNET_REQUIRE((H & 1) == 0 && (W & 1) == 0, "bn_apply_relu: fused pool needs even H,W (got %dx%d)", H, W);
-    DISPATCH_DTYPE(dtype, bn_apply_relu_pool_kernel<T><<<ew_grid(M / 4 * (C / 8)), 256, 0, st>>>(
-                              (const T*)y, ldy, (T*)out, ldo, (T*)pooled, ldp, B, H, W, C, scale, shift));
+    DISPATCH_DTYPE(dtype, bn_apply_relu_pool_kernel<T, TY><<<ew_grid(M / 4 * (C / 8)), 256, 0, st>>>(
+                              (const TY*)y, ldy, (T*)out, ldo, (T*)pooled, ldp, B, H, W, C, scale, shift));
   } else {
-    DISPATCH_DTYPE(dtype, bn_apply_relu_kernel<T><<<ew_grid(M * (C / 8)), 256, 0, st>>>((const T*)y, ldy, (T*)out, ldo, M, C,
+    DISPATCH_DTYPE(dtype, bn_apply_relu_kernel<T, TY><<<ew_grid(M * (C / 8)), 256, 0, st>>>((const TY*)y, ldy, (T*)out, ldo, M, C,
                                                                                          scale, shift));
   }
   return check_launch("bn_apply_relu");
@@ -468,7 +474,7 @@ int eunet_bn_bwd_reduce(const void* dact, int ldd, const void* y, int ldy, int d
   EUNET_REQUIRE(M > 0, "bn_bwd_reduce: empty tensor");
   const int R = 256 / (C / 8);
   const int grid = clamp_grid((M + R - 1) / R, 8);
-  DISPATCH_DTYPE(dtype, bn_bwd_reduce_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)dact, ldd, (const T*)y, ldy,
+  DISPATCH_DTYPE(dtype, bn_bwd_reduce_kernel<T, TY><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)dact, ldd, (const TY*)y, ldy,
                                                                                          M, C, scale, shift, mean, invstd,
                                                                                          sums));
   return check_launch("bn_bwd_reduce");
@@ -481,8 +487,9 @@ int eunet_bn_bwd_apply(const void* dact, int ldd, const void* y, int ldy, void* 
       check_vec(dy, lddy, C, "bn_bwd_apply(dy)"))
     return -1;
   EUNET_REQUIRE(M > 0, "bn_bwd_apply: empty tensor");
-  DISPATCH_DTYPE(dtype, bn_bwd_apply_kernel<T><<<ew_grid(M * (C / 8)), 256, 0, (cudaStream_t)stream>>>(
-                            (const T*)dact, ldd, (const T*)y, ldy, (T*)dy, lddy, M, C, scale, shift, mean, invstd, sums, dgamma,
+  EUNET_REQUIRE(C <= 2048 && 256 % (C / 8) == 0, "bn_bwd_apply: C/8=%d must divide 256", C / 8);
+  DISPATCH_DTYPE(dtype, bn_bwd_apply_kernel<T, TY><<<clamp_grid((M + 256 / (C / 8) - 1) / (256 / (C / 8)), 16), 256, 0, (cudaStream_t)stream>>>(
+                            (const T*)dact, ldd, (const TY*)y, ldy, (T*)dy, lddy, M, C, scale, shift, mean, invstd, sums, dgamma,
                             dbeta));
   return check_launch("bn_bwd_apply");
 }

@@ -1,0 +1,142 @@
+// Inference post-processing between logits and metrics ("next" row 1 of SURVEY.md §8f):
+//   * logits -> probabilities: bilinear 2x-down resize (== 2x2 mean) + softmax over 3 classes
+//     (Evaluator._run_model_single, train_eval.py:411-412);
+//   * probabilities -> semantic mask: argmax + the order-dependent rule cascade and the two global
+//     pixel-ratio filters of Evaluator._convert_probs_to_mask (train_eval.py:455-568).
+// Per-pixel float32 arithmetic in the same order as the reference's tensor ops; the ratio filters need
+// the per-image live/dead pixel counts first, hence two bandwidth passes with an integer reduction between.
+#include "common.cuh"
+#include "../../include/eunet.h"
+
+namespace eunet {
+
+template <int SCALE>
+__global__ void __launch_bounds__(256)
+softmax_probs_kernel(const float* __restrict__ logits, float* __restrict__ probs, int H, int W) {
+  const int b = blockIdx.y;
+  const long long HW = (long long)H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
+    float z[3];
+    if (SCALE == 2) {
+      const int h = (int)(i / W), w = (int)(i % W);
+      const long long plane = 4 * HW;
+      const float* base = logits + (long long)b * 3 * plane + (long long)(2 * h) * (2 * W) + 2 * w;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float2 r0 = *reinterpret_cast<const float2*>(base + c * plane);
+        const float2 r1 = *reinterpret_cast<const float2*>(base + c * plane + 2 * W);
+        z[c] = 0.25f * ((r0.x + r0.y) + (r1.x + r1.y));
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) z[c] = logits[((long long)b * 3 + c) * HW + i];
+    }
+    const float m = fmaxf(z[0], fmaxf(z[1], z[2]));
+    const float e0 = expf(z[0] - m), e1 = expf(z[1] - m), e2 = expf(z[2] - m);
+    const float s = e0 + e1 + e2;
+    float* o = probs + (long long)b * 3 * HW + i;
+    o[0] = e0 / s;
+    o[HW] = e1 / s;
+    o[2 * HW] = e2 / s;
+  }
+}
+
+// the per-pixel cascade, train_eval.py:470-524
+__device__ __forceinline__ int cascade(float bg, float live, float dead) {
+  int pred = 0;   // torch.argmax: first maximum
+  float mx = bg;
+  if (live > mx) { mx = live; pred = 1; }
+  if (dead > mx) { mx = dead; pred = 2; }
+  if (pred == 1 && ((live < 0.42f) || (live <= bg * 1.15f))) pred = 0;
+  if (pred == 2 && ((dead < 0.5f) || (dead <= bg * 1.3f) || (bg > 0.3f) || (live > dead * 0.9f))) pred = 0;
+  const bool hi_live = (pred == 0) && (live > 0.42f) && (live > bg * 1.15f) && (live > dead * 1.05f);
+  if (hi_live) pred = 1;
+  const bool hi_dead = (pred == 0) && (dead > 0.5f) && (dead > bg * 1.3f) && (dead > live * 1.1f) && (bg < 0.3f) && !hi_live;
+  if (hi_dead) pred = 2;
+  if (pred == 1 && (dead > live * 1.15f) && (dead > 0.45f)) pred = 2;
+  if (pred == 2 && (live > dead * 1.15f) && (live > 0.42f)) pred = 1;
+  if (mx < 0.3f) pred = 0;
+  return pred;
+}
+
+__global__ void __launch_bounds__(256)
+mask_pass1_kernel(const float* __restrict__ probs, unsigned char* __restrict__ mask, int* __restrict__ counts, long long HW) {
+  const int b = blockIdx.y;
+  const float* p = probs + (long long)b * 3 * HW;
+  int nl = 0, nd = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
+    const int c = cascade(p[i], p[HW + i], p[2 * HW + i]);
+    mask[(long long)b * HW + i] = (unsigned char)c;
+    nl += (c == 1);
+    nd += (c == 2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    nl += __shfl_xor_sync(0xffffffffu, nl, o);
+    nd += __shfl_xor_sync(0xffffffffu, nd, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (nl) atomicAdd(&counts[2 * b], nl);
+    if (nd) atomicAdd(&counts[2 * b + 1], nd);
+  }
+}
+
+// the global ratio filters, train_eval.py:526-563 (ratios are float64 in the reference: python ints / ints)
+__global__ void __launch_bounds__(256)
+mask_pass2_kernel(const float* __restrict__ probs, unsigned char* __restrict__ mask, const int* __restrict__ counts,
+                  long long HW) {
+  const int b = blockIdx.y;
+  const double live_ratio = (double)counts[2 * b] / (double)HW, dead_ratio = (double)counts[2 * b + 1] / (double)HW;
+  const bool f_live = live_ratio > 0.5, f_dead = dead_ratio > 0.15;
+  if (!f_live && !f_dead) return;
+  const int tier = dead_ratio > 0.4 ? 2 : (dead_ratio > 0.25 ? 1 : 0);
+  const float* p = probs + (long long)b * 3 * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
+    int c = mask[(long long)b * HW + i];
+    if (c == 0) continue;
+    const float bg = p[i], live = p[HW + i], dead = p[2 * HW + i];
+    if (c == 1 && f_live) {
+      const bool keep = (live > 0.5f) && (live > bg * 1.3f) && (bg < 0.3f);
+      if (!keep) c = 0;
+    } else if (c == 2 && f_dead) {
+      bool keep;
+      if (tier == 2) keep = (dead > 0.65f) && (dead > bg * 1.6f) && (bg < 0.2f) && (live < dead * 0.7f);
+      else if (tier == 1) keep = (dead > 0.6f) && (dead > bg * 1.5f) && (bg < 0.25f) && (live < dead * 0.8f);
+      else keep = (dead > 0.55f) && (dead > bg * 1.4f) && (bg < 0.25f);
+      if (!keep) c = 0;
+    }
+    mask[(long long)b * HW + i] = (unsigned char)c;
+  }
+}
+
+static inline dim3 img_grid(long long HW, int B) {
+  long long want = (HW + 255) / 256, cap = ((long long)kNumSMs * 8 + B - 1) / B;
+  return dim3((unsigned)(want < cap ? want : cap), (unsigned)B);
+}
+
+}  // namespace eunet
+
+using namespace eunet;
+
+extern "C" int eunet_softmax_probs(const float* logits, float* probs, int B, int H, int W, int logits_scale, void* stream) {
+  EUNET_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, "softmax_probs: bad shape");
+  EUNET_REQUIRE(logits_scale == 1 || logits_scale == 2, "softmax_probs: logits_scale must be 1 or 2");
+  const dim3 grid = img_grid((long long)H * W, B);
+  if (logits_scale == 2) softmax_probs_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(logits, probs, H, W);
+  else softmax_probs_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(logits, probs, H, W);
+  return check_launch("softmax_probs");
+}
+
+extern "C" int eunet_probs_to_mask(const float* probs, unsigned char* mask, int* counts, int B, int H, int W, void* stream) {
+  EUNET_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, "probs_to_mask: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(int) * 2 * B, st);
+  EUNET_REQUIRE(e == cudaSuccess, "probs_to_mask: memset: %s", cudaGetErrorString(e));
+  const long long HW = (long long)H * W;
+  EUNET_REQUIRE(HW < (1LL << 31), "probs_to_mask: image too large");
+  const dim3 grid = img_grid(HW, B);
+  mask_pass1_kernel<<<grid, 256, 0, st>>>(probs, mask, counts, HW);
+  if (check_launch("probs_to_mask(pass1)")) return -2;
+  mask_pass2_kernel<<<grid, 256, 0, st>>>(probs, mask, counts, HW);
+  return check_launch("probs_to_mask(pass2)");
+}

@@ -15,9 +15,11 @@ namespace eunet {
   do {                                                      \
     if ((dtype) == EUNET_BF16) {                            \
       using T = __nv_bfloat16;                              \
+      using TY = __half;                                    \
       __VA_ARGS__;                                          \
     } else if ((dtype) == EUNET_F32) {                      \
       using T = float;                                      \
+      using TY = float;                                     \
       __VA_ARGS__;                                          \
     } else {                                                \
       set_error("unknown dtype %d", (int)(dtype));          \
@@ -102,9 +104,9 @@ __global__ void tail_up_fwd_kernel(const float* __restrict__ z4, T* __restrict__
 }
 
 // ---- out = up(z) + b3 + W3 . relu(mid*scale+shift): 8 lanes per output pixel ----
-template <typename T>
+template <typename TY>
 __global__ void __launch_bounds__(256)
-tail_out_fwd_kernel(const float* __restrict__ z4, const T* __restrict__ mid, const float* __restrict__ scale,
+tail_out_fwd_kernel(const float* __restrict__ z4, const TY* __restrict__ mid, const float* __restrict__ scale,
                     const float* __restrict__ shift, const float* __restrict__ w3, const float* __restrict__ b3,
                     float* __restrict__ out, int B, int H, int W) {
   const int cg = threadIdx.x & 7;
@@ -164,9 +166,9 @@ __device__ __forceinline__ void block_reduce64(const float v[8], float (*red)[64
 
 // ---- backward pass 1 over (dout, mid): BN sums + enhance.3 weight/bias gradients ----
 // acc layout: [0,64) sum_g, [64,128) sum_g*xhat, [128,320) dW3[k][c], [320,323) db3[k]
-template <typename T>
+template <typename TY>
 __global__ void __launch_bounds__(256)
-tail_bwd_reduce_kernel(const float* __restrict__ dout, const T* __restrict__ mid, const float* __restrict__ scale,
+tail_bwd_reduce_kernel(const float* __restrict__ dout, const TY* __restrict__ mid, const float* __restrict__ scale,
                        const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
                        const float* __restrict__ w3, double* __restrict__ acc, int B, int H, int W) {
   __shared__ float red[32][64];
@@ -220,9 +222,9 @@ tail_bwd_reduce_kernel(const float* __restrict__ dout, const T* __restrict__ mid
 }
 
 // ---- backward pass 2: dmid = scale * (g - mean(g) - xhat * mean(g*xhat)) ----
-template <typename T>
+template <typename T, typename TY>
 __global__ void __launch_bounds__(256)
-tail_bwd_dmid_kernel(const float* __restrict__ dout, const T* __restrict__ mid, T* __restrict__ dmid,
+tail_bwd_dmid_kernel(const float* __restrict__ dout, const TY* __restrict__ mid, T* __restrict__ dmid,
                      const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                      const float* __restrict__ invstd, const float* __restrict__ w3, const double* __restrict__ acc, int B,
                      int H, int W) {
@@ -377,8 +379,8 @@ int eunet_tail_up_fwd(const float* z4, void* d1p, int dtype, int B, int H, int W
 int eunet_tail_out_fwd(const float* z4, const void* mid, int dtype, const float* scale, const float* shift, const float* w3,
                        const float* b3, float* out, int B, int H, int W, void* stream) {
   EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "tail_out_fwd: bad shape");
-  DISPATCH_DTYPE(dtype, tail_out_fwd_kernel<T><<<rows_grid(4LL * B * H * W), 256, 0, (cudaStream_t)stream>>>(
-                            z4, (const T*)mid, scale, shift, w3, b3, out, B, H, W));
+  DISPATCH_DTYPE(dtype, tail_out_fwd_kernel<TY><<<rows_grid(4LL * B * H * W), 256, 0, (cudaStream_t)stream>>>(
+                            z4, (const TY*)mid, scale, shift, w3, b3, out, B, H, W));
   return check_launch("tail_out_fwd");
 }
 
@@ -386,8 +388,8 @@ int eunet_tail_bwd_reduce(const float* dout, const void* mid, int dtype, const f
                           const float* mean, const float* invstd, const float* w3, double* acc, int B, int H, int W,
                           void* stream) {
   EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "tail_bwd_reduce: bad shape");
-  DISPATCH_DTYPE(dtype, tail_bwd_reduce_kernel<T><<<rows_grid(4LL * B * H * W), 256, 0, (cudaStream_t)stream>>>(
-                            dout, (const T*)mid, scale, shift, mean, invstd, w3, acc, B, H, W));
+  DISPATCH_DTYPE(dtype, tail_bwd_reduce_kernel<TY><<<rows_grid(4LL * B * H * W), 256, 0, (cudaStream_t)stream>>>(
+                            dout, (const TY*)mid, scale, shift, mean, invstd, w3, acc, B, H, W));
   return check_launch("tail_bwd_reduce");
 }
 
@@ -395,8 +397,8 @@ int eunet_tail_bwd_dmid(const float* dout, const void* mid, void* dmid, int dtyp
                         const float* mean, const float* invstd, const float* w3, const double* acc, int B, int H, int W,
                         void* stream) {
   EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "tail_bwd_dmid: bad shape");
-  DISPATCH_DTYPE(dtype, tail_bwd_dmid_kernel<T><<<rows_grid(4LL * B * H * W), 256, 0, (cudaStream_t)stream>>>(
-                            dout, (const T*)mid, (T*)dmid, scale, shift, mean, invstd, w3, acc, B, H, W));
+  DISPATCH_DTYPE(dtype, tail_bwd_dmid_kernel<T, TY><<<rows_grid(4LL * B * H * W), 256, 0, (cudaStream_t)stream>>>(
+                            dout, (const TY*)mid, (T*)dmid, scale, shift, mean, invstd, w3, acc, B, H, W));
   return check_launch("tail_bwd_dmid");
 }
 

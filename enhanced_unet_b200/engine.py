@@ -41,6 +41,7 @@ class _Ctx:
         self.dev = device
         self.dt = act_dtype
         self.code = lib.dtype_code(act_dtype)
+        self.raw = lib.raw_dtype(act_dtype)   # pre-BN conv outputs: fp16 in bf16 mode, fp32 in fp32 mode
 
     def empty(self, *shape, dtype=None):
         return torch.empty(*shape, device=self.dev, dtype=dtype or self.dt)
@@ -82,8 +83,10 @@ class PackCache:
 def conv3x3(cx: _Ctx, x: torch.Tensor, wp: torch.Tensor, y: torch.Tensor, B: int, H: int, W: int, cin: int, cout: int,
             stats: Optional[torch.Tensor] = None, scale: Optional[torch.Tensor] = None,
             shift: Optional[torch.Tensor] = None, relu: bool = False) -> None:
+    out_raw = int(y.dtype == cx.raw and cx.raw != cx.dt)
+    assert y.dtype in (cx.dt, cx.raw) and x.dtype == cx.dt
     call("eunet_conv3x3_fwd", ptr(x), _ld(x), ptr(wp), ptr(y), _ld(y), cx.code, B, H, W, cin, cout, ptr(stats), ptr(scale),
-         ptr(shift), int(relu), flops=2.0 * B * H * W * cout * 9 * cin)
+         ptr(shift), int(relu), out_raw, flops=2.0 * B * H * W * cout * 9 * cin)
 
 
 def conv3x3_wgrad(cx: _Ctx, x: torch.Tensor, dy: torch.Tensor, B: int, H: int, W: int, cin: int, cout: int) -> torch.Tensor:
@@ -109,7 +112,7 @@ class _BNSaved:
 def _conv_bn_train(cx: _Ctx, packs: PackCache, sd: Dict[str, torch.Tensor], conv: str, bn: str, x: torch.Tensor, B, H, W, cin_p,
                    cout, out: torch.Tensor, pooled: Optional[torch.Tensor]) -> _BNSaved:
     M = B * H * W
-    y = cx.empty(M, cout)
+    y = cx.empty(M, cout, dtype=cx.raw)
     stats = cx.zeros(2 * cout, dtype=torch.float64)
     conv3x3(cx, x, packs.get(cx, conv, sd[conv + ".weight"], False), y, B, H, W, cin_p, cout, stats=stats)
     f32 = torch.float32
@@ -213,7 +216,7 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, train: bool, act_dtype
     d1p = cx.empty(M2x, 16)
     call("eunet_tail_up_fwd", ptr(z4), ptr(d1p), cx.code, B, H, W)
     out = torch.empty(B, 3, 2 * H, 2 * W, device=x.device, dtype=f32)
-    midt = cx.empty(M2x, 64)
+    midt = cx.empty(M2x, 64, dtype=cx.raw)
     if train:
         stats = cx.zeros(128, dtype=torch.float64)
         conv3x3(cx, d1p, packs.get(cx, "enhance.0", sd["enhance.0.weight"], False), midt, B, 2 * H, 2 * W, 16, 64, stats=stats)

@@ -30,7 +30,7 @@ SIGNATURES = {
     "eunet_pack_input_nchw": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
     "eunet_pack_weight3x3": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
     "eunet_unpack_wgrad3x3": [_p, _p, _i, _i, _i, _p],
-    "eunet_conv3x3_fwd": [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p],
+    "eunet_conv3x3_fwd": [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _i, _p],
     "eunet_conv3x3_wgrad": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p],
     "eunet_bn_finalize": [_p, _ll, _p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _i, _p],
     "eunet_bn_fold_eval": [_p, _p, _p, _p, _p, _f, _p, _p, _i, _p],
@@ -51,6 +51,8 @@ SIGNATURES = {
     "eunet_cast_f64_f32": [_p, _p, _ll, _p],
     "eunet_loss_fwd": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p],
     "eunet_loss_bwd": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p],
+    "eunet_softmax_probs": [_p, _p, _i, _i, _i, _i, _p],
+    "eunet_probs_to_mask": [_p, _p, _p, _i, _i, _i, _p],
     "eunet_sumsq": [_p, _ll, _p, _p],
     "eunet_adamw_step": [_p, _p, _p, _p, _ll, _p, _f, _f, _f, _f, _f, _f, _i, _f, _p],
     "eunet_probe_umma": [_p, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p, _p, _i, _p],
@@ -130,6 +132,11 @@ def collect_profile() -> dict:
         f, ms, n = out.get(name, (0.0, 0.0, 0))
         out[name] = (f + fl, ms + e0.elapsed_time(e1), n + 1)
     return out
+
+
+def raw_dtype(act: torch.dtype) -> torch.dtype:
+    """Storage dtype of RAW (pre-BatchNorm) conv outputs for a given activation dtype."""
+    return torch.float16 if act == torch.bfloat16 else torch.float32
 
 
 def dtype_code(dt: torch.dtype) -> int:

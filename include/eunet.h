@@ -59,9 +59,13 @@ int eunet_unpack_wgrad3x3(const float* dw_packed, float* dw, int Co, int Ci, int
  * y[p,co] = sum_{tap,ci} x[p+tap,ci] * w[co][tap][ci], zero padding.  Epilogue options:
  *   stats != NULL: accumulate per-channel sum / sum of squares of the fp32 results into stats[0..Cout)
  *                  and stats[Cout..2Cout) (double, caller zeroes) - the BatchNorm batch statistics.
- *   scale/shift != NULL: y = y*scale[co] + shift[co] (folded eval-mode BN and/or bias); relu: max(y,0). */
+ *   scale/shift != NULL: y = y*scale[co] + shift[co] (folded eval-mode BN and/or bias); relu: max(y,0).
+ *   out_raw: element type of y.  0 = the activation dtype (bf16 / fp32); 1 = the RAW dtype used for tensors
+ *            that feed a BatchNorm (fp16 in bf16 mode - 8x finer than bf16 where the batch mean dominates -
+ *            and fp32 in fp32 mode).  The bn_* / tail_* entry points read raw tensors in that dtype. */
 int eunet_conv3x3_fwd(const void* x, int ldx, const void* w_packed, void* y, int ldy, int dtype, int B, int H, int W,
-                      int Cin, int Cout, double* stats, const float* scale, const float* shift, int relu, void* stream);
+                      int Cin, int Cout, double* stats, const float* scale, const float* shift, int relu, int out_raw,
+                      void* stream);
 /* dw[co][tap][ci] += sum_p dy[p,co] * x[p+tap,ci]   (fp32 accumulate into caller-zeroed dw_packed) */
 int eunet_conv3x3_wgrad(const void* x, int ldx, const void* dy, int lddy, float* dw_packed, int dtype, int B, int H, int W,
                         int Cin, int Cout, void* stream);
@@ -120,6 +124,14 @@ int eunet_loss_fwd(const float* logits /*[B,3,2H,2W]*/, const long long* target 
                    float* loss /*scalar*/, float* per_sample /*[B] or NULL*/, double* coef /*[B][8]*/, void* stream);
 int eunet_loss_bwd(const float* logits, const long long* target, int B, int H, int W, int logits_scale, const double* coef,
                    const float* grad_out /*scalar, device*/, float* dlogits, void* stream);
+
+/* ---- inference post-processing ("next" row: Evaluator._run_model_single train_eval.py:411-412 and
+ * Evaluator._convert_probs_to_mask train_eval.py:455-568) ---- */
+/* probs[b,c,h,w] = softmax_c(resize(logits)); logits_scale 2: logits are [B,3,2H,2W] and are 2x2-averaged first */
+int eunet_softmax_probs(const float* logits, float* probs /*[B,3,H,W]*/, int B, int H, int W, int logits_scale, void* stream);
+/* argmax + threshold cascade + the two global pixel-ratio filters, per image; mask uint8 [B,H,W];
+ * counts int32 [B][2] = (live, dead) pixel counts after the cascade and before the ratio filters (overwritten) */
+int eunet_probs_to_mask(const float* probs, unsigned char* mask, int* counts, int B, int H, int W, void* stream);
 
 /* ---- optimiser step (train_eval.py:120, 341-343): global-norm clip + AdamW over flat fp32 buffers ---- */
 int eunet_sumsq(const float* g, long long n, double* out /*scalar, accumulates; caller zeroes*/, void* stream);

@@ -69,8 +69,34 @@ def model_case(ref_models, ref_te, name, batch, h, w, pseed, xseed, tseed):
         out["gval/" + k] = flat[idx].numpy()
         if g.numel() <= 4096 or k in ("model.enc1.0.weight", "enhance.0.weight", "model.dec1.weight", "enhance.3.weight"):
             out["gfull/" + k] = g.numpy()
+    # PyTorch's OWN bf16 path on the unmodified reference (torch.autocast): the yardstick for what bf16
+    # arithmetic can deliver on this network (train-mode BN makes it ~20x more sensitive than eval mode)
+    def nerr(a, b):
+        return float((a.double() - b.double()).abs().max() / b.double().abs().max())
+    m2 = _ref_model(ref_models, sd).eval()
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        ya = m2(x).float()
+    out["autocast/logits_eval_err"] = np.array(nerr(ya, y_eval))
+    m2 = _ref_model(ref_models, sd).train()
+    tr2 = _trainer(ref_te, m2)
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        ya = m2(x)
+    out["autocast/logits_train_err"] = np.array(nerr(ya.float(), y.detach()))
+    la = 0.0
+    for i in range(batch):
+        oi = torch.nn.functional.interpolate(ya[i].float().unsqueeze(0), size=(h, w), mode="bilinear",
+                                             align_corners=False).squeeze(0)
+        la = la + tr2._compute_combined_loss(oi, t[i])
+    (la / batch).backward()
+    out["autocast/loss"] = np.array(float(la / batch))
+    ref_grads = dict(m.named_parameters())
+    for k, p in m2.named_parameters():
+        a, b = p.grad.double().flatten(), ref_grads[k].grad.double().flatten()
+        out["autocast/gcos/" + k] = np.array(float((a * b).sum() / (a.norm() * b.norm() + 1e-30)))
+        out["autocast/grel/" + k] = np.array(float((a - b).norm() / (b.norm() + 1e-30)))
     np.savez_compressed(os.path.join(OUT, f"model_{name}.npz"), **out)
-    print(f"model_{name}: loss={loss.item():.6f} ysum={y.sum().item():.4f}")
+    print(f"model_{name}: loss={loss.item():.6f} ysum={y.sum().item():.4f} autocast eval/train err "
+          f"{float(out['autocast/logits_eval_err']):.3e}/{float(out['autocast/logits_train_err']):.3e}")
 
 
 def loss_case(ref_te, ref_models):

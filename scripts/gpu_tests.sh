@@ -8,7 +8,7 @@ status=0
 for f in tests/test_gpu_probe.py tests/test_gpu_kernels.py tests/test_gpu_model.py "$@"; do
   name=$(basename "$f" .py)
   echo "=== $f"
-  timeout 900 python -m pytest "$f" -q -m gpu --maxfail=25 --no-header -p no:cacheprovider > "gpurun_out/${name}.log" 2>&1
+  timeout 900 python -m pytest "$f" -q -rA -m gpu --maxfail=25 --no-header -p no:cacheprovider > "gpurun_out/${name}.log" 2>&1
   rc=$?
   tail -n 25 "gpurun_out/${name}.log"
   echo "=== $f exit $rc"

@@ -134,7 +134,7 @@ def test_bn_train_apply_pool_and_backward(k, dtn, C):
     bias = torch.randn(C, generator=g) * 0.1
     gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.2
     rm0, rv0 = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5
-    yr = rnd(dtn, y)
+    yr = y.to(k.raw_dtype(dt)).float()       # raw conv outputs are stored in the RAW dtype (fp16 in bf16 mode)
     # reference: BN sees conv output + bias
     bn = torch.nn.BatchNorm2d(C)
     with torch.no_grad():
@@ -148,7 +148,8 @@ def test_bn_train_apply_pool_and_backward(k, dtn, C):
     g_act_only = yin.grad.clone()
     # kernels
     M = B * H * W
-    yd = nhwc(y, dt)
+    raw_dt = k.raw_dtype(dt)
+    yd = nhwc(y, raw_dt)
     stats = torch.stack([yd.double().sum(0), (yd.double() ** 2).sum(0)]).reshape(-1).contiguous()
     dev = lambda t: t.clone().cuda()
     gm, bt, bs, rm, rv = dev(gamma), dev(beta), dev(bias), dev(rm0), dev(rv0)
@@ -227,7 +228,7 @@ def test_conv3x3_fwd_stats_and_epilogue(k, dtn, case):
     y = ybuf[:, 8:]
     stats = torch.zeros(2 * Cout, dtype=torch.float64, device="cuda")
     k.call("eunet_conv3x3_fwd", xd.data_ptr(), xd.stride(0), wp.data_ptr(), y.data_ptr(), y.stride(0), k.dtype_code(dt), B, H, W,
-           Cin, Cout, stats.data_ptr(), None, None, 0)
+           Cin, Cout, stats.data_ptr(), None, None, 0, 0)
     torch.cuda.synchronize()
     assert nerr(nchw(y, B, H, W), want) < TOL[dtn]
     assert torch.all(ybuf[:, :8] == 5.0)                       # neighbouring channels of the wider buffer untouched
@@ -238,7 +239,13 @@ def test_conv3x3_fwd_stats_and_epilogue(k, dtn, case):
     sc, sh = (torch.rand(Cout, generator=g) + 0.5).cuda(), torch.randn(Cout, generator=g).cuda()
     y2 = torch.empty(M, Cout, dtype=dt, device="cuda")
     k.call("eunet_conv3x3_fwd", xd.data_ptr(), xd.stride(0), wp.data_ptr(), y2.data_ptr(), Cout, k.dtype_code(dt), B, H, W,
-           Cin, Cout, None, sc.data_ptr(), sh.data_ptr(), 1)
+           Cin, Cout, None, sc.data_ptr(), sh.data_ptr(), 1, 0)
+    # raw (pre-BN) output dtype: fp16 in bf16 mode (fp32 mode: identical to the activation dtype)
+    raw_dt = k.raw_dtype(dt)
+    y3 = torch.empty(M, Cout, dtype=raw_dt, device="cuda")
+    k.call("eunet_conv3x3_fwd", xd.data_ptr(), xd.stride(0), wp.data_ptr(), y3.data_ptr(), Cout, k.dtype_code(dt), B, H, W,
+           Cin, Cout, None, None, None, 0, 1)
+    assert nerr(nchw(y3, B, H, W), want) < (1e-5 if dtn == "fp32" else 1e-3)
     want2 = F.relu(want * sc.cpu()[None, :, None, None] + sh.cpu()[None, :, None, None])
     assert nerr(nchw(y2, B, H, W), want2) < TOL[dtn]
 
@@ -260,7 +267,7 @@ def test_conv3x3_dgrad_and_wgrad(k, dtn, case):
     k.call("eunet_pack_weight3x3", w.detach().cuda().data_ptr(), wpT.data_ptr(), k.dtype_code(dt), Cout, Cin, Cout, Cin, 1)
     dx = torch.empty(M, Cin, dtype=dt, device="cuda")
     k.call("eunet_conv3x3_fwd", dyd.data_ptr(), dyd.stride(0), wpT.data_ptr(), dx.data_ptr(), Cin, k.dtype_code(dt), B, H, W,
-           Cout, Cin, None, None, None, 0)
+           Cout, Cin, None, None, None, 0, 0)
     assert nerr(nchw(dx, B, H, W), x.grad) < TOL[dtn]
     if dtn == "bf16" and Cout % 64:
         return   # the bf16 wgrad kernel takes dY in 64-channel boxes (every layer of the model has Cout >= 64)

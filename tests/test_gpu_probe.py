@@ -26,8 +26,12 @@ def _err(got, want):
 
 @pytest.fixture(scope="module")
 def pu():
-    from tests import probe_util
-    return probe_util
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("eunet_probe_util", os.path.join(here, "probe_util.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def _dummy_x():
