@@ -103,13 +103,14 @@ def synth_batch(batch: int, res: int, seed: int, device):
     cx = torch.rand(batch, n_blobs, device=device, generator=g) * res
     sig = 3 + 7 * torch.rand(batch, n_blobs, device=device, generator=g)
     amp = 0.15 + 0.30 * torch.rand(batch, n_blobs, device=device, generator=g)
-    for k in range(n_blobs):
-        d2 = (yy - cy[:, k].view(-1, 1, 1, 1)) ** 2 + (xx - cx[:, k].view(-1, 1, 1, 1)) ** 2
-        blob = amp[:, k].view(-1, 1, 1, 1) * torch.exp(-d2 / (2 * sig[:, k].view(-1, 1, 1, 1) ** 2))
-        img = img - blob
-        inside = blob[:, 0] > 0.5 * amp[:, k].view(-1, 1, 1)
-        cls = torch.where(amp[:, k] < 0.3, 1, 2).view(-1, 1, 1).expand_as(label)
-        label = torch.where(inside, cls, label)
+    for k0 in range(0, n_blobs, 16):          # 16 blobs per pass keeps the generator to a few launches
+        sl = slice(k0, min(n_blobs, k0 + 16))
+        a_ = amp[:, sl].view(batch, -1, 1, 1)
+        d2 = (yy - cy[:, sl].view(batch, -1, 1, 1)) ** 2 + (xx - cx[:, sl].view(batch, -1, 1, 1)) ** 2
+        blob = a_ * torch.exp(-d2 / (2 * sig[:, sl].view(batch, -1, 1, 1) ** 2))
+        img = img - blob.sum(1, keepdim=True)
+        cls = torch.where(a_ < 0.3, 1, 2) * (blob > 0.5 * a_)      # 0 outside, 1 live, 2 dead (dead wins overlaps)
+        label = torch.maximum(label, cls.amax(1))
     img = img.clamp_(0, 1).expand(batch, 3, res, res).contiguous()
     return img, label
 
@@ -179,7 +180,7 @@ def main_reference(args):
 # ---------------------------------------------------------------------------------------------
 def main_gpu(args):
     import torch.distributed as dist
-    from enhanced_unet_b200 import lib
+    from enhanced_unet_b200 import lib, parallel
     from enhanced_unet_b200.optim import ClippedAdamW
     from enhanced_unet_b200.models import EnhancedUNet
     from enhanced_unet_b200.ops import combined_loss
@@ -196,9 +197,8 @@ def main_gpu(args):
     torch.manual_seed(0)
     model = EnhancedUNet(3, dtype="bf16").to(dev).train()
     params = [p for p in model.parameters()]
-    if world > 1:
-        for p in params:
-            dist.broadcast(p.data, 0)
+    parallel.broadcast_parameters(list(model.parameters()) + list(model.buffers()))
+    allreduce = parallel.GradientAllReduce(params)
     opt = ClippedAdamW(params, on_update=model._packs.clear)
     x_dev, t_dev = synth_batch(BATCH, RES, 1234 + 1000 * rank, dev)
     x_host = x_dev.cpu().pin_memory()
@@ -211,14 +211,8 @@ def main_gpu(args):
         y = model(x)
         loss = combined_loss(y, t)
         loss.backward()
-        if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in params])
-            dist.all_reduce(flat)
-            off = 0
-            for p in params:
-                n = p.numel()
-                p.grad.copy_(flat[off:off + n].view_as(p))
-                off += n
+        allreduce.reduce()          # no-op at world size 1
+        allreduce.wait()
         opt.step(grad_scale=1.0 / world)
         return loss
 
@@ -263,14 +257,15 @@ def main_gpu(args):
 
     roof = None
     cpu = None
+    # roofline of the dominant kernel (the tcgen05 implicit-GEMM conv, forward + dgrad launches):
+    # algorithmic FLOPs of those launches / their CUDA-event time on the launching stream.
+    # Every rank runs the instrumented steps (they contain the collective); rank 0 reports.
+    lib.PROFILE = []
+    for _ in range(2):
+        step(x_dev, t_dev)
+    prof = lib.collect_profile()
+    lib.PROFILE = None
     if rank == 0:
-        # roofline of the dominant kernel (the tcgen05 implicit-GEMM conv, forward + dgrad launches):
-        # algorithmic FLOPs of those launches / their CUDA-event time on the launching stream
-        lib.PROFILE = []
-        for _ in range(2):
-            step(x_dev, t_dev)
-        prof = lib.collect_profile()
-        lib.PROFILE = None
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

@@ -1,0 +1,98 @@
+"""GPU parity for the callers either side of the model: the metrics drop-in (reference fixtures, bit-exact),
+the inference post-processing kernels (softmax/resize + probability->mask cascade) and the optimiser class."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_metrics_dropin_bit_exact_against_reference_fixture(golden_dir):
+    from enhanced_unet_b200 import metrics
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    keys = [str(k) for k in g["keys"]]
+    names = sorted({k.split("/")[0] for k in g.files if "/" in k})
+    for name in names:
+        pred, gt = g[f"{name}/pred"], g[f"{name}/gt"]
+        m = metrics.calculate_semantic_metrics(pred, gt)
+        assert list(m.keys()) == keys
+        assert np.array_equal(np.array([float(m[k]) for k in keys]), g[f"{name}/values"]), name   # bit-exact float64
+        m2 = metrics.calculate_semantic_metrics(torch.from_numpy(pred).cuda(), torch.from_numpy(gt).cuda().to(torch.int64))
+        assert all(float(m[k]) == float(m2[k]) for k in keys)
+    # return types of the edge rules (python float 1.0 on the empty-union branch, numpy float64 otherwise)
+    z = np.zeros((8, 8), np.int64)
+    m = metrics.calculate_semantic_metrics(z, z)
+    assert m["sem_live_iou"] == 1.0 and isinstance(m["sem_live_iou"], float)
+    assert isinstance(metrics.calculate_semantic_metrics(g["kat1/pred"], g["kat1/gt"])["sem_live_iou"], np.floating)
+    # binary helpers (metrics.py:12-26) on instance-style masks
+    import oracle
+    rng = np.random.default_rng(3)
+    a, b = (rng.random((40, 50)) < 0.3).astype(np.uint8), (rng.random((40, 50)) < 0.4).astype(np.uint8)
+    assert metrics.calculate_iou(a, b) == oracle.calculate_iou(a, b)
+    assert metrics.calculate_dice(a, b) == oracle.calculate_dice(a, b)
+    e = np.zeros((4, 4), np.uint8)
+    assert metrics.calculate_iou(e, e) == 1.0 and metrics.calculate_dice(e, e) == 1.0
+    # batched form and the 3x3 confusion matrix with ignore label
+    pb, gb = rng.integers(0, 3, (5, 33, 17)), rng.integers(0, 3, (5, 33, 17))
+    per = metrics.batch_semantic_metrics(pb, gb)
+    for i in range(5):
+        w = oracle.calculate_semantic_metrics(pb[i], gb[i])
+        assert all(float(per[i][k]) == float(w[k]) for k in w)
+    gi = gb.copy(); gi[rng.random(gi.shape) < 0.1] = 255
+    cm = metrics.confusion_matrix_3x3(pb, gi)
+    keep = gi != 255
+    want = np.bincount(gi[keep] * 3 + pb[keep], minlength=9).reshape(3, 3)
+    assert np.array_equal(cm, want)
+
+
+def test_mask_cascade_matches_reference_fixture(golden_dir):
+    from enhanced_unet_b200.lib import call
+    g = np.load(os.path.join(golden_dir, "mask.npz"))
+    names = sorted({k.split("/")[0] for k in g.files})
+    probs = torch.from_numpy(np.stack([g[f"{n}/probs"] for n in names])).cuda().contiguous()     # [N,3,H,W]
+    N, _, H, W = probs.shape
+    mask = torch.empty(N, H, W, dtype=torch.uint8, device="cuda")
+    counts = torch.empty(N, 2, dtype=torch.int32, device="cuda")
+    call("eunet_probs_to_mask", probs.data_ptr(), mask.data_ptr(), counts.data_ptr(), N, H, W)
+    for i, n in enumerate(names):
+        assert np.array_equal(mask[i].cpu().numpy().astype(np.int64), g[f"{n}/mask"]), n      # bit-exact vs the reference
+
+
+def test_softmax_probs_matches_torch():
+    from enhanced_unet_b200.lib import call
+    g = torch.Generator().manual_seed(1)
+    logits = (torch.randn(3, 3, 48, 64, generator=g) * 3).cuda()
+    want = torch.softmax(torch.nn.functional.interpolate(logits, size=(24, 32), mode="bilinear", align_corners=False), dim=1)
+    probs = torch.empty(3, 3, 24, 32, device="cuda")
+    call("eunet_softmax_probs", logits.data_ptr(), probs.data_ptr(), 3, 24, 32, 2)
+    assert float((probs - want).abs().max()) < 2e-6
+    probs1 = torch.empty_like(logits)
+    call("eunet_softmax_probs", logits.data_ptr(), probs1.data_ptr(), 3, 48, 64, 1)
+    assert float((probs1 - torch.softmax(logits, 1)).abs().max()) < 2e-6
+
+
+def test_clipped_adamw_matches_torch_adamw_with_clip():
+    from enhanced_unet_b200.optim import ClippedAdamW
+    g = torch.Generator().manual_seed(2)
+    shapes = [(64, 3, 3, 3), (64,), (128, 64, 3, 3), (3, 64, 1, 1)]
+    ref = [torch.nn.Parameter(torch.randn(s, generator=g)) for s in shapes]
+    ours = [torch.nn.Parameter(p.detach().clone().cuda()) for p in ref]
+    o_ref = torch.optim.AdamW(ref, lr=4e-3, weight_decay=1e-4, betas=(0.9, 0.999))
+    bumped = []
+    o = ClippedAdamW(ours, lr=4e-3, weight_decay=1e-4, betas=(0.9, 0.999), max_norm=1.0, on_update=lambda: bumped.append(1))
+    sched = torch.optim.lr_scheduler.LinearLR(o, start_factor=0.001, end_factor=1.0, total_iters=5)       # reference warm-up
+    sched_ref = torch.optim.lr_scheduler.LinearLR(o_ref, start_factor=0.001, end_factor=1.0, total_iters=5)
+    for it in range(4):
+        for p, q in zip(ref, ours):
+            p.grad = torch.randn(p.shape, generator=g) * (it + 1)
+            q.grad = p.grad.clone().cuda()
+        torch.nn.utils.clip_grad_norm_(ref, 1.0)
+        o_ref.step(); o.step()
+        sched.step(); sched_ref.step()
+        for p, q in zip(ref, ours):
+            assert float((q.detach().cpu() - p.detach()).abs().max() / p.detach().abs().max()) < 1e-5
+    assert len(bumped) == 4
+    sd = o.state_dict()
+    assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
