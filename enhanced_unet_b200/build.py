@@ -19,7 +19,7 @@ LIB = os.path.join(HERE, "libeunet_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 SOURCES = ["core.cu", "metrics.cu", "elementwise.cu", "loss.cu", "tail.cu", "optim.cu", "conv_direct.cu", "conv_tc.cu",
-           "mask.cu", "probe.cu"]
+           "mask.cu", "fusion.cu", "probe.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

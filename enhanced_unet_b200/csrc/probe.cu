@@ -4,6 +4,7 @@
 // memory back to global memory.  tests/test_gpu_probe.py uses it to pin the descriptor encodings
 // (K-major / MN-major, 128B / 32B swizzle, row-shifted starts) against numpy matmuls, so the conv
 // kernels' layouts are verified facts, not guesses.
+#include <string.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "../../include/eunet.h"

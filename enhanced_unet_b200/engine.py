@@ -339,3 +339,49 @@ def backward(sd: Dict[str, torch.Tensor], sv: Saved, dout: torch.Tensor, act_dty
     pool_bwd_into(dp1, cat2[:, 128:192], dcat2[:, 128:192], 0, 64)
     block_bwd("model.enc1", dcat2[:, 128:192], 0, 3, 64, False)
     return grads
+
+
+def _fold_bn_host(sd, prefix: str):
+    """Eval-mode BN -> (scale, shift) on the host (tiny vectors, used for the kernel-parameter block)."""
+    g, b = sd[prefix + ".weight"].detach().float().cpu(), sd[prefix + ".bias"].detach().float().cpu()
+    rm, rv = sd[prefix + ".running_mean"].float().cpu(), sd[prefix + ".running_var"].float().cpu()
+    sc = g / torch.sqrt(rv + BN_EPS)
+    return sc, b - rm * sc
+
+
+def fusion_forward(sd: Dict[str, torch.Tensor], out_main: torch.Tensor, out_aux: torch.Tensor, act_dtype: torch.dtype,
+                   packs: PackCache) -> torch.Tensor:
+    """Reference models.py:320-328 in eval mode.  Returns [B,3,H,W] fp32."""
+    import ctypes
+    B, _, H, W = out_main.shape
+    cx = _Ctx(out_main.device, act_dtype)
+    f32 = torch.float32
+    M = B * H * W
+    s1, h1 = _fold_bn_host(sd, "attention_gate.1")
+    s4, h4 = _fold_bn_host(sd, "attention_gate.4")
+    blob = torch.cat([sd["attention_gate.0.weight"].detach().float().cpu().reshape(-1), s1, h1,
+                      sd["attention_gate.3.weight"].detach().float().cpu().reshape(-1), s4, h4,
+                      sd["fusion_residual.weight"].detach().float().cpu().reshape(-1),
+                      sd["fusion_residual.bias"].detach().float().cpu().reshape(-1)]).contiguous()
+    assert blob.numel() == 219
+    fg16 = cx.empty(M, 16)
+    res4 = cx.empty(M, 4, dtype=f32)
+    call("eunet_fusion_gate_fwd", ptr(out_main.contiguous().float()), ptr(out_aux.contiguous().float()),
+         ctypes.c_void_p(blob.data_ptr()), ptr(fg16), cx.code, ptr(res4), B, H, W)
+    h = fg16
+    cin_p = 16
+    for conv, bn, cout in (("fusion_head.0", "fusion_head.1", 256), ("fusion_head.4", "fusion_head.5", 128),
+                           ("fusion_head.8", "fusion_head.9", 64)):
+        scale, shift = cx.empty(cout, dtype=f32), cx.empty(cout, dtype=f32)
+        call("eunet_bn_fold_eval", ptr(sd[bn + ".weight"]), ptr(sd[bn + ".bias"]), None, ptr(sd[bn + ".running_mean"]),
+             ptr(sd[bn + ".running_var"]), BN_EPS, ptr(scale), ptr(shift), cout)
+        nxt = cx.empty(M, cout)
+        conv3x3(cx, h, packs.get(cx, conv, sd[conv + ".weight"], False), nxt, B, H, W, cin_p, cout, scale=scale, shift=shift,
+                relu=True)
+        h, cin_p = nxt, cout
+    z4 = cx.empty(M, 4, dtype=f32)
+    w11 = sd["fusion_head.11.weight"].reshape(3, 64)
+    call("eunet_tail_dec1_fwd", ptr(h), _ld(h), cx.code, ptr(w11), ptr(sd["fusion_head.11.bias"]), ptr(z4), M)
+    out = torch.empty(B, 3, H, W, device=out_main.device, dtype=f32)
+    call("eunet_fusion_out_fwd", ptr(z4), ptr(res4), ptr(out), B, H, W)
+    return out

@@ -143,3 +143,49 @@ def get_model(model_name: str, num_classes: int = 3, device: str = "cuda", train
         raise ValueError(f"Unknown model: {model_name}")
     print(f"Model {model_name} initialized")
     return model
+
+
+class FusionHead(nn.Module):
+    """The in-file fusion blocks of the reference's smp body (models.py:276-302, 320-328): attention gate,
+    fusion head and residual 1x1 over ``cat([out_main, out_aux])``.  Same sub-module names / indices as the
+    reference, so the ``attention_gate.*``, ``fusion_head.*`` and ``fusion_residual.*`` entries of a reference
+    checkpoint load directly.  The two smp branches that feed it (UnetPlusPlus / DeepLabV3Plus) are third-party
+    code outside this repo's scope; this head runs standalone in EVAL mode (train mode draws Dropout2d masks from
+    torch's RNG stream and is not implemented)."""
+
+    def __init__(self, num_classes: int = 3, dtype: str = "bf16"):
+        super().__init__()
+        if num_classes != 3:
+            raise ValueError("the B200 hot path implements the reference configuration num_classes=3")
+        self.num_classes = num_classes
+        self.act_dtype = _DTYPES[dtype]
+        fc = num_classes * 2
+        self.attention_gate = nn.Sequential(
+            nn.Conv2d(fc, fc // 2, kernel_size=3, padding=1, bias=False), nn.BatchNorm2d(fc // 2), nn.GELU(),
+            nn.Conv2d(fc // 2, fc, kernel_size=1, bias=False), nn.BatchNorm2d(fc), nn.Sigmoid())
+        self.fusion_head = nn.Sequential(
+            nn.Conv2d(num_classes * 2, 256, kernel_size=3, padding=1, bias=False), nn.BatchNorm2d(256), nn.ReLU(inplace=True),
+            nn.Dropout2d(0.2),
+            nn.Conv2d(256, 128, kernel_size=3, padding=1, bias=False), nn.BatchNorm2d(128), nn.ReLU(inplace=True),
+            nn.Dropout2d(0.15),
+            nn.Conv2d(128, 64, kernel_size=3, padding=1, bias=False), nn.BatchNorm2d(64), nn.ReLU(inplace=True),
+            nn.Conv2d(64, num_classes, kernel_size=1))
+        self.fusion_residual = nn.Conv2d(num_classes * 2, num_classes, kernel_size=1)
+        self._packs = engine.PackCache()
+
+    def _apply(self, fn, *args, **kwargs):
+        r = super()._apply(fn, *args, **kwargs)
+        self._packs.clear()
+        return r
+
+    def forward(self, out_main: torch.Tensor, out_aux: torch.Tensor) -> torch.Tensor:
+        if self.training:
+            raise NotImplementedError("FusionHead runs in eval mode only (Dropout2d RNG parity is out of scope)")
+        if not (out_main.is_cuda and out_aux.is_cuda):
+            raise RuntimeError("FusionHead (B200) runs on CUDA tensors only; there is no CPU fallback")
+        if out_main.shape != out_aux.shape or out_main.dim() != 4 or out_main.shape[1] != 3:
+            raise RuntimeError(f"FusionHead expects two [B,3,H,W] tensors, got {tuple(out_main.shape)} / {tuple(out_aux.shape)}")
+        with torch.no_grad():
+            sd = dict(self.named_parameters())
+            sd.update(dict(self.named_buffers()))
+            return engine.fusion_forward(sd, out_main, out_aux, self.act_dtype, self._packs)

@@ -133,6 +133,15 @@ int eunet_softmax_probs(const float* logits, float* probs /*[B,3,H,W]*/, int B, 
  * counts int32 [B][2] = (live, dead) pixel counts after the cascade and before the ratio filters (overwritten) */
 int eunet_probs_to_mask(const float* probs, unsigned char* mask, int* counts, int B, int H, int W, void* stream);
 
+/* ---- fusion blocks of the smp body (models.py:276-302, 320-328), eval mode, standalone (secondary path a10).
+ * gate_fwd: f = cat[out_main, out_aux]; f *= sigmoid(bn(conv1x1(gelu(bn(conv3x3(f)))))); writes the gated f as
+ * NHWC16 (dtype) for the head convolutions and res4[M][4] = fusion_residual(f).  `params`: HOST pointer to 219 floats
+ * {w0[3][6][9], s1[3], h1[3], w3[6][3], s4[6], h4[6], wr[3][6], br[3]} (BN folded to scale/shift).
+ * out_fwd: out[B,3,H,W] = z4 + res4 where z4 = fusion_head.11 (1x1) of the head output (eunet_tail_dec1_fwd). */
+int eunet_fusion_gate_fwd(const float* out_main, const float* out_aux, const float* params, void* fg16, int dtype,
+                          float* res4, int B, int H, int W, void* stream);
+int eunet_fusion_out_fwd(const float* z4, const float* res4, float* out, int B, int H, int W, void* stream);
+
 /* ---- optimiser step (train_eval.py:120, 341-343): global-norm clip + AdamW over flat fp32 buffers ---- */
 int eunet_sumsq(const float* g, long long n, double* out /*scalar, accumulates; caller zeroes*/, void* stream);
 int eunet_adamw_step(float* p, const float* g, float* m, float* v, long long n, const double* gradsq /*scalar*/,

@@ -96,3 +96,60 @@ def test_clipped_adamw_matches_torch_adamw_with_clip():
     assert len(bumped) == 4
     sd = o.state_dict()
     assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+
+
+@pytest.mark.parametrize("dtype,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_fusion_head_matches_reference_fixture(golden_dir, dtype, tol):
+    """Secondary path a10: the in-file fusion blocks of the smp body, eval mode, against the fixture produced by
+    re-instantiating the reference's own nn.Sequential blocks (oracle/make_golden.py:fusion_case)."""
+    from oracle.unet_oracle import make_fusion_state_dict
+    from enhanced_unet_b200.models import FusionHead
+    g = np.load(os.path.join(golden_dir, "fusion.npz"))
+    m = FusionHead(3, dtype=dtype)
+    m.load_state_dict(make_fusion_state_dict(0), strict=True)
+    m = m.cuda().eval()
+    y = m(torch.from_numpy(g["main"]).cuda(), torch.from_numpy(g["aux"]).cuda())
+    ref = torch.from_numpy(g["out"])
+    err = float((y.cpu() - ref).abs().max() / ref.abs().max())
+    print(f"[fusion {dtype}] err {err:.3e}")
+    assert y.shape == ref.shape and err <= tol, err
+    with pytest.raises(NotImplementedError):
+        m.train()(torch.from_numpy(g["main"]).cuda(), torch.from_numpy(g["aux"]).cuda())
+
+
+def test_trainer_and_evaluator_entry_points(tmp_path, monkeypatch):
+    """The reference's training / inference entry points on reference-format batches: loss decreases over a few
+    steps on a fixed batch, ragged masks take the per-sample path, predict_semantic_mask / evaluate return the
+    reference's types, and the checkpoint round-trips (train_eval.py:66, 236, 570, 852, 1143-1151)."""
+    from enhanced_unet_b200.models import get_model
+    from enhanced_unet_b200.train_eval import Evaluator, SyntheticCellBatches, Trainer, evaluate_model, train_model
+    monkeypatch.chdir(tmp_path)
+    torch.manual_seed(0)
+    model = get_model("enhanced_unet", num_classes=3, device="cuda").to("cuda")
+    tr = Trainer(model, "cuda", "enhanced_unet", total_epochs=50)
+    assert tr.warmup_epochs == 5 and abs(tr.optimizer.param_groups[0]["lr"] - 4e-6) < 1e-12      # SURVEY KAT-5
+    batch = next(iter(SyntheticCellBatches(1, 2, 96, seed=3)))                                    # 96 -> reflect-padded to 96
+    tr.warmup_scheduler.step()
+    for g in tr.optimizer.param_groups:
+        g["lr"] = 1e-3
+    losses = [tr.train_epoch([batch]) for _ in range(6)]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+    # ragged masks (different sizes) -> per-sample loss path; 72x72 image is reflect-padded to 96
+    rb = {"images": torch.rand(2, 3, 72, 72), "batch_items": [{"semantic_mask": torch.randint(0, 3, (72, 72))},
+                                                             {"semantic_mask": torch.randint(0, 3, (72, 72))}]}
+    assert np.isfinite(tr.train_epoch([rb]))
+    ev = Evaluator(model, "cuda", "enhanced_unet")
+    mask = ev.predict_semantic_mask(batch["images"][0])
+    assert isinstance(mask, np.ndarray) and mask.dtype == np.int64 and mask.shape == (96, 96) and set(np.unique(mask)) <= {0, 1, 2}
+    probs = ev._run_model_single(torch.rand(3, 72, 80))
+    assert probs.shape == (3, 72, 80) and float((probs.sum(0) - 1).abs().max()) < 1e-5
+    res = ev.evaluate(SyntheticCellBatches(2, 2, 64, seed=5))
+    assert set(res) == {"sem_background_iou", "sem_background_dice", "sem_live_iou", "sem_live_dice", "sem_dead_iou",
+                        "sem_dead_dice", "sem_mean_iou", "sem_mean_iou_all", "sem_mean_dice"}
+    ckpt = train_model("enhanced_unet", None, "cuda", num_epochs=3, train_batches=SyntheticCellBatches(2, 2, 64, seed=1),
+                       val_batches=SyntheticCellBatches(1, 2, 64, seed=2))
+    saved = torch.load(ckpt, map_location="cpu", weights_only=False)
+    assert set(saved) >= {"epoch", "model_state_dict", "optimizer_state_dict", "scheduler_state_dict", "best_miou", "history"}
+    assert len(saved["model_state_dict"]) == 109
+    out = evaluate_model("enhanced_unet", None, "cuda", ckpt, batches=SyntheticCellBatches(1, 2, 64, seed=2))
+    assert 0.0 <= out["sem_mean_iou_all"] <= 1.0
