@@ -1,0 +1,339 @@
+// v2 forward / dgrad 3x3 convolution: persistent, halo-tile implicit GEMM on tcgen05.
+//
+// One work item = a block of (16*MT) x 8 output pixels of one image x BN output channels.  For every 64- (or 16-)
+// channel chunk ONE 4-D TMA box {KC, 10, 16*MT+2, 1} brings the block's halo tile into shared memory; all nine
+// filter taps and all MT 128-row accumulators read it through shifted UMMA descriptors:
+//     GEMM row r = (ty, tx) of tile mt, tap (dy, dx)  ->  halo row (16*mt + ty + dy) * 10 + (tx + dx)
+// i.e. descriptor start = ((16*mt + dy) * 10 + dx) rows, stride between 8-row groups (one output row of 8 pixels) =
+// 10 rows.  (The absolute-address swizzle makes any row shift legal - pinned by tests/test_gpu_probe.py.)
+// Activation bytes through L2 drop from 9x (one box per tap, v1) to 1.4x (halo overhead); filter tiles are either
+// streamed once per (tap, chunk) for all MT tiles (ring) or kept resident in shared memory for the whole kernel.
+// TMEM holds NACC = 2 accumulator sets when they fit (512 columns), so the epilogue of item i overlaps the MMAs of
+// item i+1.  BN batch statistics are accumulated in registers across items and flushed once per CTA.
+//
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..5 epilogue.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "conv.cuh"
+#include "tc_common.cuh"
+
+namespace eunet {
+
+struct ConvHaloParams {
+  void* y;           // bf16 or fp16 elements
+  int ldy;
+  int B, H, W, Cin, Cout;
+  int blocks_x, blocks_y, items;   // pixel blocks per image row / column, total pixel blocks
+  double* stats;
+  const float* scale;
+  const float* shift;
+  int relu;
+  int out_f16;
+};
+
+__device__ __forceinline__ float warp_transpose_sum32h(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float keep = upper ? v[i + s] : v[i];
+      const float send = upper ? v[i] : v[i + s];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+template <int KC, int BN, int MT, bool WRES>
+struct HaloCfg {
+  static constexpr int ROWB = KC * 2;                                   // bytes per pixel row of a tile
+  static constexpr int HALO_ROWS = (16 * MT + 2) * 10;
+  static constexpr int A_BYTES = HALO_ROWS * ROWB;                      // exact TMA transaction size
+  static constexpr int A_SLOT = (A_BYTES + 1023) / 1024 * 1024;
+  static constexpr int B_BYTES = BN * ROWB;
+  static constexpr int NACC = (2 * MT * BN <= 512) ? 2 : 1;
+  static constexpr int TMEM_NEED = NACC * MT * BN;
+  static constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
+  static constexpr int ASTAGES = (KC == 16) ? 3 : 2;
+  static constexpr int BSTAGES = WRES ? 0 : (BN >= 128 ? 4 : 6);
+  static constexpr int CH = BN >= 32 ? 32 : 16;
+  static constexpr int NCHUNK = BN / CH;
+  static int smem_bytes(int cchunks) {
+    return 1024 + ASTAGES * A_SLOT + (WRES ? 9 * cchunks * B_BYTES : BSTAGES * B_BYTES);
+  }
+};
+
+template <int KC, int BN, int MT, bool WRES>
+__global__ void __launch_bounds__(192, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const ConvHaloParams p) {
+  using C = HaloCfg<KC, BN, MT, WRES>;
+  constexpr uint32_t LAYOUT = KC == 64 ? tc::kSwizzle128 : tc::kSwizzle32;
+  constexpr int AS = C::ASTAGES, BS = WRES ? 1 : C::BSTAGES, NACC = C::NACC, CH = C::CH;
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[AS], a_empty[AS], b_full[BS], b_empty[BS], acc_full[2], acc_empty[2], w_full;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ double red[2][4][BN];
+
+  const uint32_t sbase = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = sbase, b_base = sbase + AS * C::A_SLOT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * BN;
+  const int cchunks = p.Cin / KC;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < AS; ++s) { tc::mbar_init(tc::smem_u32(&a_full[s]), 1); tc::mbar_init(tc::smem_u32(&a_empty[s]), 1); }
+    for (int s = 0; s < BS; ++s) { tc::mbar_init(tc::smem_u32(&b_full[s]), 1); tc::mbar_init(tc::smem_u32(&b_empty[s]), 1); }
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(tc::smem_u32(&acc_full[s]), 1); tc::mbar_init(tc::smem_u32(&acc_empty[s]), 4); }
+    tc::mbar_init(tc::smem_u32(&w_full), 1);
+    tc::mbar_fence_init();
+    tc::tma_prefetch_desc(&tmX);
+    tc::tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1) tc::tmem_alloc(tc::smem_u32(&tmem_base_s), C::TMEM_COLS);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (tc::elect_one()) {
+      if (WRES) {
+        const uint32_t wb = tc::smem_u32(&w_full);
+        tc::mbar_expect_tx(wb, 9u * cchunks * C::B_BYTES);
+        for (int cc = 0; cc < cchunks; ++cc)
+          for (int tap = 0; tap < 9; ++tap)
+            tc::tma_load_2d(b_base + (cc * 9 + tap) * C::B_BYTES, &tmW, wb, tap * p.Cin + cc * KC, n0);
+      }
+      uint32_t a_it = 0, b_it = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const int bx = item % p.blocks_x, by = (item / p.blocks_x) % p.blocks_y, b = item / (p.blocks_x * p.blocks_y);
+        const int x0 = bx * 8, y0 = by * (16 * MT);
+        for (int cc = 0; cc < cchunks; ++cc) {
+          const uint32_t s = a_it % AS;
+          tc::mbar_wait(tc::smem_u32(&a_empty[s]), ((a_it / AS) & 1u) ^ 1u);
+          const uint32_t fb = tc::smem_u32(&a_full[s]);
+          tc::mbar_expect_tx(fb, C::A_BYTES);
+          tc::tma_load_4d(a_base + s * C::A_SLOT, &tmX, fb, cc * KC, x0 - 1, y0 - 1, b);
+          ++a_it;
+          if (!WRES) {
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t sb = b_it % BS;
+              tc::mbar_wait(tc::smem_u32(&b_empty[sb]), ((b_it / BS) & 1u) ^ 1u);
+              const uint32_t bb = tc::smem_u32(&b_full[sb]);
+              tc::mbar_expect_tx(bb, C::B_BYTES);
+              tc::tma_load_2d(b_base + sb * C::B_BYTES, &tmW, bb, tap * p.Cin + cc * KC, n0);
+              ++b_it;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (tc::elect_one()) {
+      constexpr uint32_t idesc = tc::make_idesc_bf16(128, BN, 0, 0);
+      if (WRES) {
+        tc::mbar_wait(tc::smem_u32(&w_full), 0);
+        tc::tc_fence_after();
+      }
+      uint32_t a_it = 0, b_it = 0, li = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++li) {
+        const uint32_t ab = li % NACC;
+        tc::mbar_wait(tc::smem_u32(&acc_empty[ab]), ((li / NACC) & 1u) ^ 1u);
+        tc::tc_fence_after();
+        for (int cc = 0; cc < cchunks; ++cc) {
+          const uint32_t s = a_it % AS;
+          tc::mbar_wait(tc::smem_u32(&a_full[s]), (a_it / AS) & 1u);
+          tc::tc_fence_after();
+          const uint32_t a_addr = a_base + s * C::A_SLOT;
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            uint32_t b_addr, sb = 0;
+            if (WRES) {
+              b_addr = b_base + (cc * 9 + tap) * C::B_BYTES;
+            } else {
+              sb = b_it % BS;
+              tc::mbar_wait(tc::smem_u32(&b_full[sb]), (b_it / BS) & 1u);
+              tc::tc_fence_after();
+              b_addr = b_base + sb * C::B_BYTES;
+            }
+            const int dy = tap / 3, dx = tap - dy * 3;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              const uint32_t a_tap = a_addr + (uint32_t)(((16 * mt + dy) * 10 + dx) * C::ROWB);
+#pragma unroll
+              for (int j = 0; j < KC / 16; ++j) {
+                const uint64_t adesc = tc::make_smem_desc(a_tap + j * 32, 16, 10 * C::ROWB, LAYOUT);
+                const uint64_t bdesc = tc::make_smem_desc(b_addr + j * 32, 16, 8 * C::ROWB, LAYOUT);
+                tc::umma_bf16(tmem_base + (ab * MT + mt) * BN, adesc, bdesc, idesc, (cc | tap | j) != 0 ? 1u : 0u);
+              }
+            }
+            if (!WRES) {
+              tc::umma_commit(tc::smem_u32(&b_empty[sb]));
+              ++b_it;
+            }
+          }
+          tc::umma_commit(tc::smem_u32(&a_empty[s]));
+          ++a_it;
+        }
+        tc::umma_commit(tc::smem_u32(&acc_full[ab]));
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                 // GEMM row inside a 128-row tile: (ty, tx) = (r / 8, r % 8)
+    const int ty = r >> 3, tx = r & 7;
+    // fp64 running sums: a CTA folds hundreds of items, and var = E[x^2] - mean^2 cancels badly in fp32
+    double st1[C::NCHUNK], st2[C::NCHUNK];
+#pragma unroll
+    for (int c = 0; c < C::NCHUNK; ++c) st1[c] = st2[c] = 0.0;
+    uint32_t li = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++li) {
+      const int bx = item % p.blocks_x, by = (item / p.blocks_x) % p.blocks_y, b = item / (p.blocks_x * p.blocks_y);
+      const uint32_t ab = li % NACC;
+      tc::mbar_wait(tc::smem_u32(&acc_full[ab]), (li / NACC) & 1u);
+      tc::tc_fence_after();
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+        const int gx = bx * 8 + tx, gy = by * (16 * MT) + 16 * mt + ty;
+        const bool valid = gx < p.W && gy < p.H;
+        const long long pix = ((long long)b * p.H + gy) * p.W + gx;
+        uint16_t* yrow = reinterpret_cast<uint16_t*>(p.y) + pix * p.ldy + n0;
+#pragma unroll
+        for (int c = 0; c < C::NCHUNK; ++c) {
+          const int c0 = c * CH;
+          uint32_t raw[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((ab * MT + mt) * BN + c0);
+          if (CH == 32) tc::tmem_ld32(taddr, raw);
+          else {
+            tc::tmem_ld16(taddr, raw);
+#pragma unroll
+            for (int i = 16; i < 32; ++i) raw[i] = 0u;
+          }
+          tc::tmem_ld_wait();
+          if (p.stats != nullptr) {
+            float s1[32], s2[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float f = valid ? __uint_as_float(raw[i]) : 0.f;
+              s1[i] = f;
+              s2[i] = f * f;
+            }
+            st1[c] += (double)warp_transpose_sum32h(s1, lane);
+            st2[c] += (double)warp_transpose_sum32h(s2, lane);
+          }
+          if (valid) {
+#pragma unroll
+            for (int g8 = 0; g8 < CH / 8; ++g8) {
+              float o[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float f = __uint_as_float(raw[g8 * 8 + e]);
+                if (p.scale != nullptr) f = fmaf(f, __ldg(p.scale + n0 + c0 + g8 * 8 + e), __ldg(p.shift + n0 + c0 + g8 * 8 + e));
+                if (p.relu) f = fmaxf(f, 0.f);
+                o[e] = f;
+              }
+              uint4 u;
+              if (p.out_f16) {
+                u.x = pack_f16x2(o[0], o[1]); u.y = pack_f16x2(o[2], o[3]); u.z = pack_f16x2(o[4], o[5]); u.w = pack_f16x2(o[6], o[7]);
+              } else {
+                u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]); u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+              }
+              *reinterpret_cast<uint4*>(yrow + c0 + g8 * 8) = u;
+            }
+          }
+        }
+      }
+      // this accumulator set may be overwritten by the MMA warp once all four epilogue warps have drained it
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[ab]));
+    }
+    if (p.stats != nullptr) {
+#pragma unroll
+      for (int c = 0; c < C::NCHUNK; ++c)
+        if (lane < CH) {
+          red[0][q][c * CH + lane] = st1[c];
+          red[1][q][c * CH + lane] = st2[c];
+        }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int c = threadIdx.x - 64; c < BN; c += 128) {
+        const double t1 = red[0][0][c] + red[0][1][c] + red[0][2][c] + red[0][3][c];
+        const double t2 = red[1][0][c] + red[1][1][c] + red[1][2][c] + red[1][3][c];
+        atomicAdd(p.stats + n0 + c, t1);
+        atomicAdd(p.stats + p.Cout + n0 + c, t2);
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+template <int KC, int BN, int MT, bool WRES>
+static int launch_halo(const void* x, int ldx, const void* w, ConvHaloParams p, cudaStream_t st) {
+  using C = HaloCfg<KC, BN, MT, WRES>;
+  const int cchunks = p.Cin / KC;
+  const int smem = C::smem_bytes(cchunks);
+  if (smem > 227 * 1024) return 1;   // does not fit: caller falls back to the per-tap kernel
+  p.blocks_x = (p.W + 7) / 8;
+  p.blocks_y = (p.H + 16 * MT - 1) / (16 * MT);
+  const long long items = (long long)p.blocks_x * p.blocks_y * p.B;
+  if (items > 0x7fffffffLL) return 1;
+  p.items = (int)items;
+  CUtensorMap tmX, tmW;
+  {
+    uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.B};
+    uint64_t str[3] = {(uint64_t)ldx * 2, (uint64_t)ldx * 2 * p.W, (uint64_t)ldx * 2 * p.W * p.H};
+    uint32_t box[4] = {(uint32_t)KC, 10u, (uint32_t)(16 * MT + 2), 1u};
+    if (tc::encode_tensor_map_bf16(&tmX, x, 4, dims, str, box, KC == 64 ? 128 : 32)) return -1;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)9 * p.Cin, (uint64_t)p.Cout}, str[1] = {(uint64_t)9 * p.Cin * 2};
+    uint32_t box[2] = {(uint32_t)KC, (uint32_t)BN};
+    if (tc::encode_tensor_map_bf16(&tmW, w, 2, dims, str, box, KC == 64 ? 128 : 32)) return -1;
+  }
+  auto kern = conv3x3_halo_kernel<KC, BN, MT, WRES>;
+  static int configured = 0;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    EUNET_REQUIRE(e == cudaSuccess, "conv3x3_halo: cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e));
+    configured = smem;
+  }
+  const int ntiles = p.Cout / BN;
+  int per = kNumSMs / ntiles;
+  if (per < 1) per = 1;
+  if (per > p.items) per = p.items;
+  dim3 grid((unsigned)per, (unsigned)ntiles);
+  kern<<<grid, 192, smem, st>>>(tmX, tmW, p);
+  return check_launch("conv3x3_halo");
+}
+
+// returns 0 = launched, 1 = shape not covered (caller uses the per-tap kernel), < 0 = error
+int conv3x3_fwd_halo_bf16(const void* x, int ldx, const void* w, void* y, int ldy, int B, int H, int W, int Cin, int Cout,
+                          double* stats, const float* scale, const float* shift, int relu, int out_raw, cudaStream_t st) {
+  ConvHaloParams p;
+  p.y = y; p.ldy = ldy; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.blocks_x = p.blocks_y = p.items = 0;
+  p.stats = stats; p.scale = scale; p.shift = shift; p.relu = relu; p.out_f16 = out_raw ? 1 : 0;
+  if (H < 8 || W < 8) return 1;           // tiny images: the batch-folding per-tap kernel wastes less
+  if (Cin % 64 == 0) {
+    if (Cout % 256 == 0) return 1;        // BN=256 layers stay on the per-tap kernel (already ~0.8 of peak)
+    if (Cout % 128 == 0) return launch_halo<64, 128, 2, false>(x, ldx, w, p, st);
+    if (Cout % 64 == 0) {
+      if (Cin == 64) return launch_halo<64, 64, 2, true>(x, ldx, w, p, st);
+      return launch_halo<64, 64, 2, false>(x, ldx, w, p, st);
+    }
+    if (Cout == 16 && Cin == 64) return launch_halo<64, 16, 4, true>(x, ldx, w, p, st);
+    return 1;
+  }
+  if (Cin == 16 && Cout % 64 == 0 && Cout % 128 != 0) return launch_halo<16, 64, 4, true>(x, ldx, w, p, st);
+  return 1;
+}
+
+}  // namespace eunet

@@ -12,6 +12,7 @@
 // issuer, warps 2..5 = epilogue (TMEM -> registers -> BN statistics / affine / ReLU -> global).
 // smem ring of STAGES {A,B} tiles with full/empty mbarriers; tcgen05.commit releases ring slots.
 #include <cuda_bf16.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "conv.cuh"
@@ -19,6 +20,8 @@
 #include "../../include/eunet.h"
 
 namespace eunet {
+
+int g_opt_conv_halo = 1;
 
 PixelTile choose_pixel_tile(int B, int H, int W, int pixels) {
   PixelTile best{};
@@ -379,6 +382,10 @@ static int conv3x3_fwd_bf16(const void* x, int ldx, const void* w, void* y, int 
   EUNET_REQUIRE(Cin % 16 == 0 && Cout % 16 == 0, "conv3x3_fwd(bf16): Cin=%d and Cout=%d must be multiples of 16", Cin, Cout);
   EUNET_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && ldx >= Cin && ldy >= Cout, "conv3x3_fwd(bf16): bad ld (%d, %d)", ldx, ldy);
   EUNET_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0, "conv3x3_fwd(bf16): y not 16-byte aligned");
+  if (g_opt_conv_halo) {
+    const int rc = conv3x3_fwd_halo_bf16(x, ldx, w, y, ldy, B, H, W, Cin, Cout, stats, scale, shift, relu, out_raw, st);
+    if (rc <= 0) return rc;   // launched (0) or failed (< 0); 1 = not covered, fall through to the per-tap kernel
+  }
   const int KC = (Cin % 64 == 0) ? 64 : 16;
   const int BN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0) ? 128 : (Cout % 64 == 0) ? 64 : 16;
   const PixelTile t = choose_pixel_tile(B, H, W, 128);
@@ -458,6 +465,15 @@ static int conv3x3_wgrad_bf16(const void* x, int ldx, const void* dy, int lddy, 
 }  // namespace eunet
 
 using namespace eunet;
+
+extern "C" int eunet_set_option(const char* name, int value) {
+  if (strcmp(name, "conv_halo") == 0) {
+    g_opt_conv_halo = value;
+    return 0;
+  }
+  set_error("unknown option '%s'", name);
+  return -1;
+}
 
 extern "C" int eunet_conv3x3_fwd(const void* x, int ldx, const void* w_packed, void* y, int ldy, int dtype, int B, int H, int W,
                                  int Cin, int Cout, double* stats, const float* scale, const float* shift, int relu,

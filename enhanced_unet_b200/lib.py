@@ -26,6 +26,7 @@ _f = C.c_float
 SIGNATURES = {
     "eunet_abi_version": [],
     "eunet_device_info": [_p, _p, _p, _p],
+    "eunet_set_option": [C.c_char_p, _i],
     "eunet_confusion4x4": [_p, _p, _i, _ll, _ll, _p, _p],
     "eunet_pack_input_nchw": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
     "eunet_pack_weight3x3": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
@@ -139,6 +140,12 @@ def collect_profile() -> dict:
 def raw_dtype(act: torch.dtype) -> torch.dtype:
     """Storage dtype of RAW (pre-BatchNorm) conv outputs for a given activation dtype."""
     return torch.float16 if act == torch.bfloat16 else torch.float32
+
+
+def set_option(name: str, value: int) -> None:
+    rc = load().eunet_set_option(name.encode(), int(value))
+    if rc != 0:
+        raise RuntimeError(f"eunet_set_option failed: {last_error()}")
 
 
 def dtype_code(dt: torch.dtype) -> int:

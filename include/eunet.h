@@ -34,6 +34,9 @@ extern "C" {
 const char* eunet_last_error(void);
 int eunet_abi_version(void);
 int eunet_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin);
+/* tuning / A-B switches for benchmarking (process-global).  "conv_halo": 1 (default) = halo-tile persistent conv
+ * kernel where it applies, 0 = always the per-tap kernel. */
+int eunet_set_option(const char* name, int value);
 
 /* ---- metrics.py:12-58 (calculate_iou / calculate_dice / calculate_semantic_metrics) and the confusion
  * counts of visualization.py:294-311, 1484-1492.  Per image i: counts[i][g][p] = #pixels with gt class g

@@ -203,6 +203,12 @@ CONV_CASES = [
     (1, 16, 16, 64, 16),      # dgrad of enhance.0 (N = 16)
     (3, 2, 2, 64, 128),       # tiny spatial extent: batch folded into the pixel tile
     (1, 40, 24, 64, 64),      # overhanging tiles
+    (4, 128, 128, 64, 64),    # > 148 work items: persistent loop + double-buffered TMEM of the halo kernel
+    (2, 48, 40, 192, 64),     # halo kernel, streamed filters, 3 channel chunks
+    (1, 64, 64, 128, 128),    # halo kernel BN = 128
+    (2, 80, 72, 16, 64),      # halo kernel, 16-channel chunks, MT = 4
+    (1, 72, 64, 64, 16),      # halo kernel, N = 16 (dgrad of enhance.0)
+    (2, 32, 32, 64, 192),     # three N tiles sharing the pixel blocks (dgrad of dec2.0)
 ]
 
 
@@ -210,10 +216,12 @@ def _conv_ref(x, w):
     return F.conv2d(x, w, None, padding=1)
 
 
-@pytest.mark.parametrize("dtn", ["fp32", "bf16"])
+@pytest.mark.parametrize("dtn", ["fp32", "bf16", "bf16-pertap"])
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv3x3_fwd_stats_and_epilogue(k, dtn, case):
     B, H, W, Cin, Cout = case
+    k.set_option("conv_halo", 0 if dtn == "bf16-pertap" else 1)     # both tensor-core kernels are covered
+    dtn = dtn.split("-")[0]
     dt = DT[dtn]
     g = torch.Generator().manual_seed(hash(case) % 1000)
     x = torch.randn(B, Cin, H, W, generator=g)
@@ -246,6 +254,7 @@ def test_conv3x3_fwd_stats_and_epilogue(k, dtn, case):
     k.call("eunet_conv3x3_fwd", xd.data_ptr(), xd.stride(0), wp.data_ptr(), y3.data_ptr(), Cout, k.dtype_code(dt), B, H, W,
            Cin, Cout, None, None, None, 0, 1)
     assert nerr(nchw(y3, B, H, W), want) < (1e-5 if dtn == "fp32" else 1e-3)
+    k.set_option("conv_halo", 1)
     want2 = F.relu(want * sc.cpu()[None, :, None, None] + sh.cpu()[None, :, None, None])
     assert nerr(nchw(y2, B, H, W), want2) < TOL[dtn]
 

@@ -153,6 +153,19 @@ def test_state_dict_round_trip_and_error_paths():
         get_model("nope")
 
 
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_train_logits_do_not_depend_on_batch_replication(dtype):
+    """Duplicating a sample leaves every batch statistic unchanged, so train-mode logits must not move.  Guards the
+    cross-CTA statistics accumulation (fp64): fp32 running sums in a persistent CTA once cost 1.6e-2 here."""
+    import oracle
+    m = _model(dtype, oracle.make_state_dict(2)).train()
+    x1 = oracle.make_input(1, 256, 256, 3).cuda()
+    with torch.no_grad():
+        y1 = m(x1)
+        y4 = m(x1.expand(4, 3, 256, 256).contiguous())
+    assert nerr(y4[0], y1[0]) <= 1e-5 and nerr(y4[3], y1[0]) <= 1e-5, (nerr(y4[0], y1[0]), nerr(y4[3], y1[0]))
+
+
 def test_bf16_full_size_properties():
     """BASELINE config-2 shape on one GPU (batch 16, 512x512, bf16 train step): size-independent properties -
     finite logits, per-channel BN statistics consistency, gradient of a batch-replicated input equals the

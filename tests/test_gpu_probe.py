@@ -162,3 +162,56 @@ def test_row_shifted_descriptor_start(pu):
     REPORT["row_shift"] = res
     _save()
     assert res["shift8_bo0"] < 1e-5 and res["shift16_bo0"] < 1e-5, res   # whole swizzle atoms must work
+
+
+def _halo_rows(dy, dx, bw_halo=10, th=16, tw=8):
+    """row index inside an (th+2) x bw_halo halo tile of GEMM row r = ty*tw + tx for tap (dy, dx)"""
+    return [(ty + dy) * bw_halo + (tx + dx) for ty in range(th) for tx in range(tw)]
+
+
+@pytest.mark.parametrize("swz,kc", [(128, 64), (32, 16)])
+def test_halo_tile_taps_by_descriptor_shift_kmajor(pu, swz, kc):
+    """Halo-reuse scheme of the v2 forward kernel: ONE 18x10-pixel halo tile in smem serves all nine taps of a
+    16x8 output tile.  GEMM row r = (ty, tx) reads halo row (ty+dy)*10 + (tx+dx): the eight pixels of an output
+    row are one 8-row group, consecutive output rows are 10 halo rows apart -> SBO = 10 rows, start = (dy*10+dx) rows."""
+    row_b = kc * 2
+    a = pu.rand_bf16(180, kc, seed=20).cuda()
+    b = pu.rand_bf16(64, kc, seed=21).cuda()
+    layout = pu.SW128 if swz == 128 else pu.SW32
+    a_bytes = ((180 * row_b + 1023) // 1024) * 1024
+    loads = [(0, (0, 0), 0), (1, (0, 0), a_bytes)]
+    res = {}
+    for dy in range(3):
+        for dx in range(3):
+            want = pu.f32(a)[_halo_rows(dy, dx)] @ pu.f32(b).T
+            mmas = [(pu.smem_desc((dy * 10 + dx) * row_b + 32 * j, 16, 10 * row_b, layout),
+                     pu.smem_desc(a_bytes + 32 * j, 16, 8 * row_b, layout), pu.idesc_bf16(128, 64, 0, 0), int(j > 0), 0)
+                    for j in range(kc // 16)]
+            t, _ = pu.run_probe(a, (180, kc), swz, b, (64, kc), swz, _dummy_x(), (64, 8, 8, 1), 128, loads,
+                                180 * row_b + 64 * row_b, mmas, 64, 65536, 16)
+            res[f"dy{dy}dx{dx}"] = _err(t[:, :64], want)
+    REPORT[f"halo_kmajor_sw{swz}"] = res
+    _save()
+    assert max(res.values()) < 1e-5, res
+
+
+def test_halo_tile_taps_by_descriptor_shift_mnmajor(pu):
+    """Same scheme for wgrad's B' operand (MN-major: K = pixels): K=16 per MMA = two output rows of 8 pixels =
+    two 8-row groups 10 halo rows apart (SBO = 1280 B); K advance per MMA = 2 output rows = 20 halo rows."""
+    xh = pu.rand_bf16(180, 64, seed=22).cuda()        # halo tile [180 px][64 ci]
+    dyt = pu.rand_bf16(128, 128, seed=23).cuda()      # dY tile [128 px (16x8)][128 co]
+    a_off, b_off = 0, 32768
+    loads = [(0, (0, 0), a_off), (0, (64, 0), a_off + 16384), (1, (0, 0), b_off)]
+    res = {}
+    for dy in range(3):
+        for dx in range(3):
+            want = pu.f32(dyt).T @ pu.f32(xh)[_halo_rows(dy, dx)]          # [128 co, 64 ci]
+            mmas = [(pu.smem_desc(a_off + 2048 * j, 16384, 1024, pu.SW128),
+                     pu.smem_desc(b_off + ((dy + 2 * j) * 10 + dx) * 128, 0, 1280, pu.SW128),
+                     pu.idesc_bf16(128, 64, 1, 1), int(j > 0), 0) for j in range(8)]
+            t, _ = pu.run_probe(dyt, (128, 64), 128, xh, (180, 64), 128, _dummy_x(), (64, 8, 8, 1), 128, loads,
+                                2 * 16384 + 180 * 128, mmas, 64, 65536, 16)
+            res[f"dy{dy}dx{dx}"] = _err(t[:, :64], want)
+    REPORT["halo_mnmajor_sw128"] = res
+    _save()
+    assert max(res.values()) < 1e-5, res
