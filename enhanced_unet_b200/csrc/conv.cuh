@@ -13,6 +13,8 @@ int conv3x3_wgrad_f32(const float* x, int ldx, const float* dy, int lddy, float*
 // v2 halo-tile kernel (conv_halo.cu): 0 = launched, 1 = shape not covered (use the per-tap kernel), < 0 = error
 int conv3x3_fwd_halo_bf16(const void* x, int ldx, const void* w, void* y, int ldy, int B, int H, int W, int Cin, int Cout,
                           double* stats, const float* scale, const float* shift, int relu, int out_raw, cudaStream_t st);
+int conv3x3_wgrad_halo_bf16(const void* x, int ldx, const void* dy, int lddy, float* dw, int B, int H, int W, int Cin, int Cout,
+                            cudaStream_t st);
 extern int g_opt_conv_halo;   // 1 (default): use the halo kernel where it applies
 
 // Power-of-two (bw, bh, bb) with bw*bh*bb == pixels minimising the number of tiles over a [B,H,W] image batch.

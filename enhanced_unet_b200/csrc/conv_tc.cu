@@ -446,6 +446,10 @@ static int conv3x3_wgrad_bf16(const void* x, int ldx, const void* dy, int lddy, 
                               cudaStream_t st) {
   EUNET_REQUIRE(Cin % 16 == 0 && Cout % 64 == 0, "conv3x3_wgrad(bf16): Cin=%d must be a multiple of 16 and Cout=%d of 64", Cin, Cout);
   EUNET_REQUIRE(ldx % 8 == 0 && lddy % 8 == 0 && ldx >= Cin && lddy >= Cout, "conv3x3_wgrad(bf16): bad ld (%d, %d)", ldx, lddy);
+  if (g_opt_conv_halo) {
+    const int rc = conv3x3_wgrad_halo_bf16(x, ldx, dy, lddy, dw, B, H, W, Cin, Cout, st);
+    if (rc <= 0) return rc;
+  }
   const int KC = (Cin % 64 == 0) ? 64 : 16;
   const PixelTile t = choose_pixel_tile(B, H, W, 64);
   CUtensorMap tmX, tmDY;

@@ -259,10 +259,12 @@ def test_conv3x3_fwd_stats_and_epilogue(k, dtn, case):
     assert nerr(nchw(y2, B, H, W), want2) < TOL[dtn]
 
 
-@pytest.mark.parametrize("dtn", ["fp32", "bf16"])
+@pytest.mark.parametrize("dtn", ["fp32", "bf16", "bf16-pertap"])
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv3x3_dgrad_and_wgrad(k, dtn, case):
     B, H, W, Cin, Cout = case
+    k.set_option("conv_halo", 0 if dtn == "bf16-pertap" else 1)
+    dtn = dtn.split("-")[0]
     dt = DT[dtn]
     g = torch.Generator().manual_seed(hash(case) % 1000 + 1)
     x = rnd(dtn, torch.randn(B, Cin, H, W, generator=g)).requires_grad_(True)
@@ -285,6 +287,7 @@ def test_conv3x3_dgrad_and_wgrad(k, dtn, case):
            Cin, Cout)
     dw = torch.empty(Cout, Cin, 3, 3, device="cuda")
     k.call("eunet_unpack_wgrad3x3", dwp.data_ptr(), dw.data_ptr(), Cout, Cin, Cin)
+    k.set_option("conv_halo", 1)
     assert nerr(dw.cpu(), w.grad) < 2e-5     # fp32 accumulation in both modes (inputs are identical)
 
 

@@ -215,3 +215,26 @@ def test_halo_tile_taps_by_descriptor_shift_mnmajor(pu):
     REPORT["halo_mnmajor_sw128"] = res
     _save()
     assert max(res.values()) < 1e-5, res
+
+
+def test_wgrad_v2_tap_pair_stacked_in_m(pu):
+    """wgrad v2 operand scheme: A' = the X halo tile consumed MN-major with M = 128 = TWO taps x 64 input channels,
+    the second "64-channel block" being the same tile at another tap shift (LBO = byte distance between the two tap
+    origins, e.g. 128 B); B' = the dense dY tile [128 px][64 co]; K = 16 pixels per MMA = two output rows."""
+    xh = pu.rand_bf16(180, 64, seed=30).cuda()
+    dyt = pu.rand_bf16(128, 64, seed=31).cuda()
+    x_off, d_off = 0, 24576
+    loads = [(0, (0, 0), x_off), (1, (0, 0), d_off)]
+    res = {}
+    pairs = [((0, 0), (0, 1)), ((0, 2), (1, 0)), ((1, 1), (1, 2)), ((2, 0), (2, 1)), ((2, 2), (2, 2))]
+    for (t1, t2) in pairs:
+        off1, off2 = (t1[0] * 10 + t1[1]) * 128, (t2[0] * 10 + t2[1]) * 128
+        want = np.concatenate([pu.f32(xh)[_halo_rows(*t1)].T @ pu.f32(dyt), pu.f32(xh)[_halo_rows(*t2)].T @ pu.f32(dyt)])
+        mmas = [(pu.smem_desc(x_off + off1 + 2 * j * 10 * 128, off2 - off1, 1280, pu.SW128),
+                 pu.smem_desc(d_off + 2048 * j, 0, 1024, pu.SW128), pu.idesc_bf16(128, 64, 1, 1), int(j > 0), 0) for j in range(8)]
+        t, _ = pu.run_probe(xh, (180, 64), 128, dyt, (128, 64), 128, _dummy_x(), (64, 8, 8, 1), 128, loads, 180 * 128 + 16384, mmas,
+                            64, 65536, 16)
+        res[f"{t1}{t2}"] = _err(t[:, :64], want)
+    REPORT["wgrad_v2_pairs"] = res
+    _save()
+    assert max(res.values()) < 1e-5, res
