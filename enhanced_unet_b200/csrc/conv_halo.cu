@@ -11,7 +11,7 @@
 // TMEM holds NACC = 2 accumulator sets when they fit (512 columns), so the epilogue of item i overlaps the MMAs of
 // item i+1.  BN batch statistics are accumulated in registers across items and flushed once per CTA.
 //
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..5 epilogue.
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..9 epilogue.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -66,7 +66,7 @@ struct HaloCfg {
 };
 
 template <int KC, int BN, int MT, bool WRES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const ConvHaloParams p) {
   using C = HaloCfg<KC, BN, MT, WRES>;
   constexpr uint32_t LAYOUT = KC == 64 ? tc::kSwizzle128 : tc::kSwizzle32;
@@ -75,7 +75,6 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[AS], a_empty[AS], b_full[BS], b_empty[BS], acc_full[2], acc_empty[2], w_full;
   __shared__ uint32_t tmem_base_s;
-  __shared__ double red[2][4][BN];
 
   const uint32_t sbase = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = sbase, b_base = sbase + AS * C::A_SLOT;
@@ -86,7 +85,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < AS; ++s) { tc::mbar_init(tc::smem_u32(&a_full[s]), 1); tc::mbar_init(tc::smem_u32(&a_empty[s]), 1); }
     for (int s = 0; s < BS; ++s) { tc::mbar_init(tc::smem_u32(&b_full[s]), 1); tc::mbar_init(tc::smem_u32(&b_empty[s]), 1); }
-    for (int s = 0; s < 2; ++s) { tc::mbar_init(tc::smem_u32(&acc_full[s]), 1); tc::mbar_init(tc::smem_u32(&acc_empty[s]), 4); }
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(tc::smem_u32(&acc_full[s]), 1); tc::mbar_init(tc::smem_u32(&acc_empty[s]), (C::NCHUNK >= 2) ? 8 : 4); }
     tc::mbar_init(tc::smem_u32(&w_full), 1);
     tc::mbar_fence_init();
     tc::tma_prefetch_desc(&tmX);
@@ -184,89 +183,95 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       }
     }
   } else {
-    // ===================== epilogue =====================
-    const int q = warp & 3;
-    const int r = q * 32 + lane;                 // GEMM row inside a 128-row tile: (ty, tx) = (r / 8, r % 8)
-    const int ty = r >> 3, tx = r & 7;
-    // fp64 running sums: a CTA folds hundreds of items, and var = E[x^2] - mean^2 cancels badly in fp32
-    double st1[C::NCHUNK], st2[C::NCHUNK];
+    // ===================== epilogue: 8 warps =====================
+    // warp w owns TMEM lanes [32 (w%4), +32); the two warps of a lane quarter split the column chunks (even / odd).
+    // BN statistics: per-thread fp32 sums over its rows of the MT tiles, ONE 31-shuffle transpose-reduce per chunk and
+    // item into fp64 per-lane column totals, flushed with fp64 atomics when the CTA is done.
+    const int e = warp - 2, q = warp & 3, half = e >> 2;
+    constexpr int NCW = (C::NCHUNK >= 2) ? C::NCHUNK / 2 : 1;
+    const bool active = (C::NCHUNK >= 2) || half == 0;
+    if (active) {
+      const int r = q * 32 + lane;                 // GEMM row inside a 128-row tile: (ty, tx) = (r / 8, r % 8)
+      const int ty = r >> 3, tx = r & 7;
+      double tot1[NCW], tot2[NCW];
 #pragma unroll
-    for (int c = 0; c < C::NCHUNK; ++c) st1[c] = st2[c] = 0.0;
-    uint32_t li = 0;
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++li) {
-      const int bx = item % p.blocks_x, by = (item / p.blocks_x) % p.blocks_y, b = item / (p.blocks_x * p.blocks_y);
-      const uint32_t ab = li % NACC;
-      tc::mbar_wait(tc::smem_u32(&acc_full[ab]), (li / NACC) & 1u);
-      tc::tc_fence_after();
+      for (int cw = 0; cw < NCW; ++cw) tot1[cw] = tot2[cw] = 0.0;
+      uint32_t li = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++li) {
+        const int bx = item % p.blocks_x, by = (item / p.blocks_x) % p.blocks_y, b = item / (p.blocks_x * p.blocks_y);
+        const uint32_t ab = li % NACC;
+        tc::mbar_wait(tc::smem_u32(&acc_full[ab]), (li / NACC) & 1u);
+        tc::tc_fence_after();
+        const int gx = bx * 8 + tx;
+#pragma unroll
+        for (int cw = 0; cw < NCW; ++cw) {
+          const int c0 = ((C::NCHUNK >= 2) ? 2 * cw + half : 0) * CH;
+          float run1[32], run2[32];            // this thread's rows of the MT tiles, one column chunk
+#pragma unroll
+          for (int i = 0; i < 32; ++i) run1[i] = run2[i] = 0.f;
 #pragma unroll 1
-      for (int mt = 0; mt < MT; ++mt) {
-        const int gx = bx * 8 + tx, gy = by * (16 * MT) + 16 * mt + ty;
-        const bool valid = gx < p.W && gy < p.H;
-        const long long pix = ((long long)b * p.H + gy) * p.W + gx;
-        uint16_t* yrow = reinterpret_cast<uint16_t*>(p.y) + pix * p.ldy + n0;
+          for (int mt = 0; mt < MT; ++mt) {
+            const int gy = by * (16 * MT) + 16 * mt + ty;
+            const bool valid = gx < p.W && gy < p.H;
+            const long long pix = ((long long)b * p.H + gy) * p.W + gx;
+            uint16_t* yrow = reinterpret_cast<uint16_t*>(p.y) + pix * p.ldy + n0;
+            uint32_t raw[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((ab * MT + mt) * BN + c0);
+            if (CH == 32) tc::tmem_ld32(taddr, raw);
+            else {
+              tc::tmem_ld16(taddr, raw);
 #pragma unroll
-        for (int c = 0; c < C::NCHUNK; ++c) {
-          const int c0 = c * CH;
-          uint32_t raw[32];
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((ab * MT + mt) * BN + c0);
-          if (CH == 32) tc::tmem_ld32(taddr, raw);
-          else {
-            tc::tmem_ld16(taddr, raw);
+              for (int i = 16; i < 32; ++i) raw[i] = 0u;
+            }
+            tc::tmem_ld_wait();
+            if (p.stats != nullptr && valid) {
 #pragma unroll
-            for (int i = 16; i < 32; ++i) raw[i] = 0u;
+              for (int i = 0; i < 32; ++i) {
+                const float f = __uint_as_float(raw[i]);
+                run1[i] += f;
+                run2[i] = fmaf(f, f, run2[i]);
+              }
+            }
+            if (valid) {
+#pragma unroll
+              for (int g8 = 0; g8 < CH / 8; ++g8) {
+                float o[8];
+#pragma unroll
+                for (int ee = 0; ee < 8; ++ee) {
+                  float f = __uint_as_float(raw[g8 * 8 + ee]);
+                  if (p.scale != nullptr) f = fmaf(f, __ldg(p.scale + n0 + c0 + g8 * 8 + ee), __ldg(p.shift + n0 + c0 + g8 * 8 + ee));
+                  if (p.relu) f = fmaxf(f, 0.f);
+                  o[ee] = f;
+                }
+                uint4 u;
+                if (p.out_f16) {
+                  u.x = pack_f16x2(o[0], o[1]); u.y = pack_f16x2(o[2], o[3]); u.z = pack_f16x2(o[4], o[5]); u.w = pack_f16x2(o[6], o[7]);
+                } else {
+                  u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]); u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+                }
+                *reinterpret_cast<uint4*>(yrow + c0 + g8 * 8) = u;
+              }
+            }
           }
-          tc::tmem_ld_wait();
           if (p.stats != nullptr) {
-            float s1[32], s2[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float f = valid ? __uint_as_float(raw[i]) : 0.f;
-              s1[i] = f;
-              s2[i] = f * f;
-            }
-            st1[c] += (double)warp_transpose_sum32h(s1, lane);
-            st2[c] += (double)warp_transpose_sum32h(s2, lane);
-          }
-          if (valid) {
-#pragma unroll
-            for (int g8 = 0; g8 < CH / 8; ++g8) {
-              float o[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                float f = __uint_as_float(raw[g8 * 8 + e]);
-                if (p.scale != nullptr) f = fmaf(f, __ldg(p.scale + n0 + c0 + g8 * 8 + e), __ldg(p.shift + n0 + c0 + g8 * 8 + e));
-                if (p.relu) f = fmaxf(f, 0.f);
-                o[e] = f;
-              }
-              uint4 u;
-              if (p.out_f16) {
-                u.x = pack_f16x2(o[0], o[1]); u.y = pack_f16x2(o[2], o[3]); u.z = pack_f16x2(o[4], o[5]); u.w = pack_f16x2(o[6], o[7]);
-              } else {
-                u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]); u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
-              }
-              *reinterpret_cast<uint4*>(yrow + c0 + g8 * 8) = u;
-            }
+            tot1[cw] += (double)warp_transpose_sum32h(run1, lane);
+            tot2[cw] += (double)warp_transpose_sum32h(run2, lane);
           }
         }
+        // this accumulator set may be overwritten once every participating epilogue warp has drained it
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[ab]));
       }
-      // this accumulator set may be overwritten by the MMA warp once all four epilogue warps have drained it
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[ab]));
-    }
-    if (p.stats != nullptr) {
+      if (p.stats != nullptr) {
 #pragma unroll
-      for (int c = 0; c < C::NCHUNK; ++c)
-        if (lane < CH) {
-          red[0][q][c * CH + lane] = st1[c];
-          red[1][q][c * CH + lane] = st2[c];
+        for (int cw = 0; cw < NCW; ++cw) {
+          const int c0 = ((C::NCHUNK >= 2) ? 2 * cw + half : 0) * CH;
+          if (lane < CH) {
+            atomicAdd(p.stats + n0 + c0 + lane, tot1[cw]);
+            atomicAdd(p.stats + p.Cout + n0 + c0 + lane, tot2[cw]);
+          }
         }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int c = threadIdx.x - 64; c < BN; c += 128) {
-        const double t1 = red[0][0][c] + red[0][1][c] + red[0][2][c] + red[0][3][c];
-        const double t2 = red[1][0][c] + red[1][1][c] + red[1][2][c] + red[1][3][c];
-        atomicAdd(p.stats + n0 + c, t1);
-        atomicAdd(p.stats + p.Cout + n0 + c, t2);
       }
     }
   }
@@ -310,7 +315,7 @@ static int launch_halo(const void* x, int ldx, const void* w, ConvHaloParams p, 
   if (per < 1) per = 1;
   if (per > p.items) per = p.items;
   dim3 grid((unsigned)per, (unsigned)ntiles);
-  kern<<<grid, 192, smem, st>>>(tmX, tmW, p);
+  kern<<<grid, 320, smem, st>>>(tmX, tmW, p);
   return check_launch("conv3x3_halo");
 }
 
@@ -323,11 +328,15 @@ int conv3x3_fwd_halo_bf16(const void* x, int ldx, const void* w, void* y, int ld
   p.stats = stats; p.scale = scale; p.shift = shift; p.relu = relu; p.out_f16 = out_raw ? 1 : 0;
   if (H < 8 || W < 8) return 1;           // tiny images: the batch-folding per-tap kernel wastes less
   if (Cin % 64 == 0) {
-    if (Cout % 256 == 0) return 1;        // BN=256 layers stay on the per-tap kernel (already ~0.8 of peak)
+    if (Cout % 256 == 0) {
+      // BN = 256: one 128-row tile per item leaves room for two accumulator sets (2 x 256 columns), so the statistics
+      // epilogue overlaps the next item's MMAs; without statistics (dgrad) the per-tap kernel is already at ~0.85 of peak
+      return launch_halo<64, 256, 1, false>(x, ldx, w, p, st);
+    }
     if (Cout % 128 == 0) return launch_halo<64, 128, 2, false>(x, ldx, w, p, st);
     if (Cout % 64 == 0) {
       if (Cin == 64) return launch_halo<64, 64, 2, true>(x, ldx, w, p, st);
-      return launch_halo<64, 64, 2, false>(x, ldx, w, p, st);
+      return launch_halo<64, 64, 4, false>(x, ldx, w, p, st);
     }
     if (Cout == 16 && Cin == 64) return launch_halo<64, 16, 4, true>(x, ldx, w, p, st);
     return 1;

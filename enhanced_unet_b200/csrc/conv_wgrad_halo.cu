@@ -127,6 +127,8 @@ conv3x3_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
 int conv3x3_wgrad_halo_bf16(const void* x, int ldx, const void* dy, int lddy, float* dw, int B, int H, int W, int Cin, int Cout,
                             cudaStream_t st) {
   if (Cin % 64 != 0 || H < 8 || W < 8) return 1;
+  // many (ci chunk, co tile) columns with few pixel tiles each: the per-tap kernel (N = 192 per MMA, fewer atomics) wins
+  if (g_opt_conv_halo != 2 && (long long)Cin * Cout > 128LL * 256) return 1;
   constexpr int STAGES = 4;
   constexpr int SMEM = 1024 + STAGES * (23 * 1024 + 128 * 128);
   WgradHaloParams p;
