@@ -104,6 +104,40 @@ template <> __device__ __forceinline__ __half from_f32<__half>(float x) { return
 // fp32 accumulators agree with what later kernels read back)
 template <typename T> __device__ __forceinline__ float round_to(float x) { return to_f32(from_f32<T>(x)); }
 
+// ---- per-thread cp.async rings: keep several 8-element vectors per thread in flight without holding registers.
+// Each thread only ever reads the slots it filled itself, so cp.async.wait_group is the only synchronisation.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename T, int STAGES>
+struct Stream8 {
+  char* base;
+  int stride;
+  // smem region of STAGES * nthreads * 8 * sizeof(T) bytes
+  __device__ __forceinline__ Stream8(char* smem, int nthreads)
+      : base(smem + threadIdx.x * 8 * (int)sizeof(T)), stride(nthreads * 8 * (int)sizeof(T)) {}
+  __device__ __forceinline__ void issue(int stage, const T* src) {
+    cp_async16(base + stage * stride, src);
+    if (sizeof(T) == 4) cp_async16(base + stage * stride + 16, reinterpret_cast<const char*>(src) + 16);
+  }
+  __device__ __forceinline__ F8 get(int stage) const { return load8(reinterpret_cast<const T*>(base + stage * stride)); }
+  static constexpr int bytes(int nthreads) { return STAGES * nthreads * 8 * (int)sizeof(T); }
+};
+
+// per-thread ring of float4 values (e.g. a 3-channel fp32 pixel padded to 4)
+template <int STAGES>
+struct Stream4f {
+  char* base;
+  int stride;
+  __device__ __forceinline__ Stream4f(char* smem, int nthreads) : base(smem + threadIdx.x * 16), stride(nthreads * 16) {}
+  __device__ __forceinline__ void issue(int stage, const float* src) { cp_async16(base + stage * stride, src); }
+  __device__ __forceinline__ float4 get(int stage) const { return *reinterpret_cast<const float4*>(base + stage * stride); }
+  static constexpr int bytes(int nthreads) { return STAGES * nthreads * 16; }
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

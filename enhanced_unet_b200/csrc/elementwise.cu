@@ -22,6 +22,10 @@ namespace eunet {
     }                                                       \
   } while (0)
 
+static void bn_ring_smem_attr(const void* kernel, int bytes) {
+  if (bytes > 48 * 1024) (void)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
 static inline int ew_grid(long long items, int threads = 256) {
   long long blocks = (items + threads - 1) / threads;
   long long cap = (long long)kNumSMs * 16;
@@ -75,19 +79,33 @@ __global__ void bn_fold_eval_kernel(const float* __restrict__ gamma, const float
 // BN apply + ReLU (+ fused 2x2 max-pool)
 // ------------------------------------------------------------------------------------------------
 template <typename T, typename TY>
-__global__ void bn_apply_relu_kernel(const TY* __restrict__ y, int ldy, T* __restrict__ out, int ldo, long long M, int C,
-                                     const float* __restrict__ scale, const float* __restrict__ shift) {
-  const int G = C >> 3;
-  const long long items = M * G;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % G);
-    const long long p = i / G;
-    F8 v = load8(y + p * ldy + cg * 8);
-    const F8 sc = load8(scale + cg * 8), sh = load8(shift + cg * 8);
+__global__ void __launch_bounds__(256)
+bn_apply_relu_kernel(const TY* __restrict__ y, int ldy, T* __restrict__ out, int ldo, long long M, int C,
+                     const float* __restrict__ scale, const float* __restrict__ shift) {
+  // block = 256 threads = G channel groups x R pixel lanes (G = C/8 divides 256); y streamed through a per-thread ring
+  extern __shared__ __align__(16) char dyn_smem[];
+  Stream8<TY, 6> sy(dyn_smem, 256);
+  const int G = C >> 3, R = 256 / G;
+  const int cg = threadIdx.x % G, r = threadIdx.x / G;
+  const F8 sc = load8(scale + cg * 8), sh = load8(shift + cg * 8);
+  const long long p0 = (long long)blockIdx.x * R + r, step = (long long)gridDim.x * R;
+  const long long n = p0 < M ? (M - p0 + step - 1) / step : 0;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    if (i < n) sy.issue(i, y + (p0 + i * step) * ldy + cg * 8);
+    cp_async_commit();
+  }
+  for (long long i = 0; i < n; ++i) {
+    const long long j = i + 5;
+    if (j < n) sy.issue((int)(j % 6), y + (p0 + j * step) * ldy + cg * 8);
+    cp_async_commit();
+    cp_async_wait<5>();
+    F8 v = sy.get((int)(i % 6));
 #pragma unroll
     for (int k = 0; k < 8; ++k) v.v[k] = fmaxf(fmaf(v.v[k], sc.v[k], sh.v[k]), 0.f);
-    store8(out + p * ldo + cg * 8, v);
+    store8(out + (p0 + i * step) * ldo + cg * 8, v);
   }
+  cp_async_wait<0>();
 }
 
 template <typename T, typename TY>
@@ -290,20 +308,44 @@ __global__ void upsample2_bwd_kernel(const T* __restrict__ dout, int ldo, T* __r
 // BatchNorm + ReLU backward
 // ------------------------------------------------------------------------------------------------
 // Block = 256 threads = G channel groups x R pixel lanes (G = C/8 divides 256).
+constexpr int kBnStages = 4;   // 8-element vectors in flight per thread and stream
+
 template <typename T, typename TY>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const T* __restrict__ dact, int ldd, const TY* __restrict__ y, int ldy, long long M, int C,
                      const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                      const float* __restrict__ invstd, double* __restrict__ sums) {
+  extern __shared__ __align__(16) char dyn_smem[];
   __shared__ float red[2][256 * 8];
+  Stream8<T, kBnStages> sd(dyn_smem, 256);
+  Stream8<TY, kBnStages> sy(dyn_smem + Stream8<T, kBnStages>::bytes(256), 256);
   const int G = C >> 3, R = 256 / G;
   const int cg = threadIdx.x % G, r = threadIdx.x / G;
   const F8 sc = load8(scale + cg * 8), sh = load8(shift + cg * 8), mu = load8(mean + cg * 8), is = load8(invstd + cg * 8);
   float sg[8], sgx[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) sg[e] = sgx[e] = 0.f;
-  for (long long p = (long long)blockIdx.x * R + r; p < M; p += (long long)gridDim.x * R) {
-    const F8 d = load8(dact + p * ldd + cg * 8), v = load8(y + p * ldy + cg * 8);
+  const long long p0 = (long long)blockIdx.x * R + r, step = (long long)gridDim.x * R;
+  const long long n = p0 < M ? (M - p0 + step - 1) / step : 0;   // this thread's pixel count
+#pragma unroll
+  for (int i = 0; i < kBnStages - 1; ++i) {
+    if (i < n) {
+      const long long p = p0 + i * step;
+      sd.issue(i, dact + p * ldd + cg * 8);
+      sy.issue(i, y + p * ldy + cg * 8);
+    }
+    cp_async_commit();
+  }
+  for (long long i = 0; i < n; ++i) {
+    const long long j = i + kBnStages - 1;
+    if (j < n) {
+      const long long p = p0 + j * step;
+      sd.issue((int)(j % kBnStages), dact + p * ldd + cg * 8);
+      sy.issue((int)(j % kBnStages), y + p * ldy + cg * 8);
+    }
+    cp_async_commit();
+    cp_async_wait<kBnStages - 1>();
+    const F8 d = sd.get((int)(i % kBnStages)), v = sy.get((int)(i % kBnStages));
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float g = fmaf(v.v[e], sc.v[e], sh.v[e]) > 0.f ? d.v[e] : 0.f;
@@ -311,6 +353,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dact, int ldd, const TY* __restrict__
       sgx[e] += g * ((v.v[e] - mu.v[e]) * is.v[e]);
     }
   }
+  cp_async_wait<0>();
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     red[0][r * C + cg * 8 + e] = sg[e];
@@ -349,8 +392,30 @@ bn_bwd_apply_kernel(const T* __restrict__ dact, int ldd, const TY* __restrict__ 
     k1[e] = (float)(sums[cg * 8 + e] * invM);
     k2[e] = (float)(sums[C + cg * 8 + e] * invM);
   }
-  for (long long p = (long long)blockIdx.x * R + r; p < M; p += (long long)gridDim.x * R) {
-    const F8 d = load8(dact + p * ldd + cg * 8), v = load8(y + p * ldy + cg * 8);
+  extern __shared__ __align__(16) char dyn_smem[];
+  Stream8<T, kBnStages> sd(dyn_smem, 256);
+  Stream8<TY, kBnStages> sy(dyn_smem + Stream8<T, kBnStages>::bytes(256), 256);
+  const long long p0 = (long long)blockIdx.x * R + r, step = (long long)gridDim.x * R;
+  const long long n = p0 < M ? (M - p0 + step - 1) / step : 0;
+#pragma unroll
+  for (int i = 0; i < kBnStages - 1; ++i) {
+    if (i < n) {
+      const long long p = p0 + i * step;
+      sd.issue(i, dact + p * ldd + cg * 8);
+      sy.issue(i, y + p * ldy + cg * 8);
+    }
+    cp_async_commit();
+  }
+  for (long long i = 0; i < n; ++i) {
+    const long long j = i + kBnStages - 1;
+    if (j < n) {
+      const long long p = p0 + j * step;
+      sd.issue((int)(j % kBnStages), dact + p * ldd + cg * 8);
+      sy.issue((int)(j % kBnStages), y + p * ldy + cg * 8);
+    }
+    cp_async_commit();
+    cp_async_wait<kBnStages - 1>();
+    const F8 d = sd.get((int)(i % kBnStages)), v = sy.get((int)(i % kBnStages));
     F8 o;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -358,8 +423,9 @@ bn_bwd_apply_kernel(const T* __restrict__ dact, int ldd, const TY* __restrict__ 
       const float xhat = (v.v[e] - mu.v[e]) * is.v[e];
       o.v[e] = sc.v[e] * (g - k1[e] - xhat * k2[e]);
     }
-    store8(dy + p * lddy + cg * 8, o);
+    store8(dy + (p0 + i * step) * lddy + cg * 8, o);
   }
+  cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -461,7 +527,9 @@ int eunet_bn_apply_relu(const void* y, int ldy, void* out, int ldo, void* pooled
     DISPATCH_DTYPE(dtype, bn_apply_relu_pool_kernel<T, TY><<<ew_grid(M / 4 * (C / 8)), 256, 0, st>>>(
                               (const TY*)y, ldy, (T*)out, ldo, (T*)pooled, ldp, B, H, W, C, scale, shift));
   } else {
-    DISPATCH_DTYPE(dtype, bn_apply_relu_kernel<T, TY><<<ew_grid(M * (C / 8)), 256, 0, st>>>((const TY*)y, ldy, (T*)out, ldo, M, C,
+    EUNET_REQUIRE(C <= 2048 && 256 % (C / 8) == 0, "bn_apply_relu: C/8=%d must divide 256", C / 8);
+    DISPATCH_DTYPE(dtype, bn_ring_smem_attr((const void*)bn_apply_relu_kernel<T, TY>, Stream8<TY, 6>::bytes(256));
+                   bn_apply_relu_kernel<T, TY><<<clamp_grid((M + 256 / (C / 8) - 1) / (256 / (C / 8)), 8), 256, Stream8<TY, 6>::bytes(256), st>>>((const TY*)y, ldy, (T*)out, ldo, M, C,
                                                                                          scale, shift));
   }
   return check_launch("bn_apply_relu");
@@ -474,7 +542,8 @@ int eunet_bn_bwd_reduce(const void* dact, int ldd, const void* y, int ldy, int d
   EUNET_REQUIRE(M > 0, "bn_bwd_reduce: empty tensor");
   const int R = 256 / (C / 8);
   const int grid = clamp_grid((M + R - 1) / R, 8);
-  DISPATCH_DTYPE(dtype, bn_bwd_reduce_kernel<T, TY><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)dact, ldd, (const TY*)y, ldy,
+  DISPATCH_DTYPE(dtype, bn_ring_smem_attr((const void*)bn_bwd_reduce_kernel<T, TY>, (int)(8 * 256 * kBnStages * (sizeof(T) + sizeof(TY))));
+                 bn_bwd_reduce_kernel<T, TY><<<grid, 256, 8 * 256 * kBnStages * (sizeof(T) + sizeof(TY)), (cudaStream_t)stream>>>((const T*)dact, ldd, (const TY*)y, ldy,
                                                                                          M, C, scale, shift, mean, invstd,
                                                                                          sums));
   return check_launch("bn_bwd_reduce");
@@ -488,7 +557,8 @@ int eunet_bn_bwd_apply(const void* dact, int ldd, const void* y, int ldy, void* 
     return -1;
   EUNET_REQUIRE(M > 0, "bn_bwd_apply: empty tensor");
   EUNET_REQUIRE(C <= 2048 && 256 % (C / 8) == 0, "bn_bwd_apply: C/8=%d must divide 256", C / 8);
-  DISPATCH_DTYPE(dtype, bn_bwd_apply_kernel<T, TY><<<clamp_grid((M + 256 / (C / 8) - 1) / (256 / (C / 8)), 16), 256, 0, (cudaStream_t)stream>>>(
+  DISPATCH_DTYPE(dtype, bn_ring_smem_attr((const void*)bn_bwd_apply_kernel<T, TY>, (int)(8 * 256 * kBnStages * (sizeof(T) + sizeof(TY))));
+                 bn_bwd_apply_kernel<T, TY><<<clamp_grid((M + 256 / (C / 8) - 1) / (256 / (C / 8)), 8), 256, 8 * 256 * kBnStages * (sizeof(T) + sizeof(TY)), (cudaStream_t)stream>>>(
                             (const T*)dact, ldd, (const TY*)y, ldy, (T*)dy, lddy, M, C, scale, shift, mean, invstd, sums, dgamma,
                             dbeta));
   return check_launch("bn_bwd_apply");

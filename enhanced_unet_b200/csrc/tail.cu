@@ -85,7 +85,7 @@ tail_dec1_fwd_kernel(const T* __restrict__ d2, int ld, const float* __restrict__
 
 // ---- d1p = up(z) padded to 16 channels: one thread per output pixel ----
 template <typename T>
-__global__ void tail_up_fwd_kernel(const float* __restrict__ z4, T* __restrict__ d1p, int B, int H, int W) {
+__global__ void tail_up_fwd_kernel(const float* __restrict__ z4, T* __restrict__ d1p, float* __restrict__ d14, int B, int H, int W) {
   const long long items = 4LL * B * H * W;
   const int Wo = 2 * W, Ho = 2 * H;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
@@ -100,16 +100,33 @@ __global__ void tail_up_fwd_kernel(const float* __restrict__ z4, T* __restrict__
     lo.v[0] = d[0]; lo.v[1] = d[1]; lo.v[2] = d[2];
     store8(d1p + i * 16, lo);
     store8(d1p + i * 16 + 8, hi);
+    if (d14 != nullptr) reinterpret_cast<float4*>(d14)[i] = make_float4(d[0], d[1], d[2], 0.f);   // fp32 copy for the residual
   }
 }
 
-// ---- out = up(z) + b3 + W3 . relu(mid*scale+shift): 8 lanes per output pixel ----
+// NCHW fp32 [B,3,Ho,Wo] -> pixel-major float4 (3 channels + pad): one 16-byte load per pixel for the tail kernels
+__global__ void tail_pack3_kernel(const float* __restrict__ src, float* __restrict__ dst4, int B, long long HW) {
+  const long long M = (long long)B * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / HW, hw = i % HW;
+    const float* p = src + b * 3 * HW + hw;
+    reinterpret_cast<float4*>(dst4)[i] = make_float4(__ldg(p), __ldg(p + HW), __ldg(p + 2 * HW), 0.f);
+  }
+}
+
+constexpr int kTailStages = 4;   // 64-channel pixels (16 B per lane) in flight per thread
+
+// ---- out = up(z) + b3 + W3 . relu(mid*scale+shift): 8 lanes per output pixel, mid streamed through a per-thread
+// cp.async ring (kTailStages loads in flight) ----
 template <typename TY>
 __global__ void __launch_bounds__(256)
-tail_out_fwd_kernel(const float* __restrict__ z4, const TY* __restrict__ mid, const float* __restrict__ scale,
+tail_out_fwd_kernel(const float* __restrict__ d14, const TY* __restrict__ mid, const float* __restrict__ scale,
                     const float* __restrict__ shift, const float* __restrict__ w3, const float* __restrict__ b3,
                     float* __restrict__ out, int B, int H, int W) {
-  const int cg = threadIdx.x & 7;
+  extern __shared__ __align__(16) char dyn_smem[];
+  Stream8<TY, kTailStages> sm(dyn_smem, 256);
+  Stream4f<kTailStages> sd(dyn_smem + Stream8<TY, kTailStages>::bytes(256), 256);
+  const int cg = threadIdx.x & 7, slot = threadIdx.x >> 3;
   const int Wo = 2 * W, Ho = 2 * H;
   const long long M = (long long)B * Ho * Wo;
   const F8 sc = load8(scale + cg * 8), sh = load8(shift + cg * 8);
@@ -120,33 +137,50 @@ tail_out_fwd_kernel(const float* __restrict__ z4, const TY* __restrict__ mid, co
 #pragma unroll
     for (int e = 0; e < 8; ++e) w[k][e] = t.v[e];
   }
-  const float bb[3] = {b3[0], b3[1], b3[2]};
-  const long long stride = (long long)gridDim.x * 32;
-  const long long Mr = (M + stride - 1) / stride * stride;
-  for (long long p = (long long)blockIdx.x * 32 + (threadIdx.x >> 3); p < Mr; p += stride) {
-    float s[3] = {0.f, 0.f, 0.f};
+  const float bias = cg < 3 ? b3[cg] : 0.f;
+  const long long p0 = (long long)blockIdx.x * 32 + slot, step = (long long)gridDim.x * 32;
+  const long long n = (M + step - 1) / step;       // same trip count for every thread (shuffles below)
+#pragma unroll
+  for (int i = 0; i < kTailStages - 1; ++i) {
+    const long long p = p0 + i * step;
+    if (i < n && p < M) {
+      sm.issue(i, mid + p * 64 + cg * 8);
+      if (cg < 3) sd.issue(i, d14 + p * 4);
+    }
+    cp_async_commit();
+  }
+  for (long long i = 0; i < n; ++i) {
+    const long long j = i + kTailStages - 1, pj = p0 + j * step;
+    if (j < n && pj < M) {
+      sm.issue((int)(j % kTailStages), mid + pj * 64 + cg * 8);
+      if (cg < 3) sd.issue((int)(j % kTailStages), d14 + pj * 4);
+    }
+    cp_async_commit();
+    cp_async_wait<kTailStages - 1>();
+    const long long p = p0 + i * step;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
     if (p < M) {
-      const F8 v = load8(mid + p * 64 + cg * 8);
+      const F8 v = sm.get((int)(i % kTailStages));
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float a = fmaxf(fmaf(v.v[e], sc.v[e], sh.v[e]), 0.f);
-        s[0] = fmaf(a, w[0][e], s[0]);
-        s[1] = fmaf(a, w[1][e], s[1]);
-        s[2] = fmaf(a, w[2][e], s[2]);
+        s0 = fmaf(a, w[0][e], s0);
+        s1 = fmaf(a, w[1][e], s1);
+        s2 = fmaf(a, w[2][e], s2);
       }
     }
-    s[0] = group8_sum(s[0]); s[1] = group8_sum(s[1]); s[2] = group8_sum(s[2]);
+    s0 = group8_sum(s0); s1 = group8_sum(s1); s2 = group8_sum(s2);
     if (cg < 3 && p < M) {   // lanes 0..2 of the group write one class plane each
       const int ox = (int)(p % Wo);
       const int oy = (int)((p / Wo) % Ho);
       const int b = (int)(p / ((long long)Wo * Ho));
-      float d[3];
-      up_sample3(z4, b, oy, ox, H, W, d);
-      const float sv = cg == 0 ? s[0] : (cg == 1 ? s[1] : s[2]);
-      const float dv = cg == 0 ? d[0] : (cg == 1 ? d[1] : d[2]);
-      out[((long long)b * 3 + cg) * Ho * Wo + (long long)oy * Wo + ox] = dv + bb[cg] + sv;
+      const float4 d = sd.get((int)(i % kTailStages));
+      const float sv = cg == 0 ? s0 : (cg == 1 ? s1 : s2);
+      const float dv = cg == 0 ? d.x : (cg == 1 ? d.y : d.z);
+      out[((long long)b * 3 + cg) * Ho * Wo + (long long)oy * Wo + ox] = dv + bias + sv;
     }
   }
+  cp_async_wait<0>();
 }
 
 // Shared helper: reduce per-thread arrays (thread = 8 channels of group cg, 32 pixel rows per block)
@@ -186,11 +220,31 @@ tail_bwd_reduce_kernel(const float* __restrict__ dout, const TY* __restrict__ mi
   float sg[8], sgx[8], dw[3][8], db[3] = {0.f, 0.f, 0.f};
 #pragma unroll
   for (int e = 0; e < 8; ++e) { sg[e] = sgx[e] = 0.f; dw[0][e] = dw[1][e] = dw[2][e] = 0.f; }
-  for (long long p = (long long)blockIdx.x * 32 + row; p < M; p += (long long)gridDim.x * 32) {
-    const long long b = p / HWo, hw = p % HWo;
-    const float* dp = dout + b * 3 * HWo + hw;
-    const float g0 = __ldg(dp), g1 = __ldg(dp + HWo), g2 = __ldg(dp + 2 * HWo);
-    const F8 v = load8(mid + p * 64 + cg * 8);
+  extern __shared__ __align__(16) char dyn_smem[];
+  Stream8<TY, kTailStages> sm(dyn_smem, 256);
+  Stream4f<kTailStages> sdo(dyn_smem + Stream8<TY, kTailStages>::bytes(256), 256);
+  const long long p0 = (long long)blockIdx.x * 32 + row, step = (long long)gridDim.x * 32;
+  const long long n = p0 < M ? (M - p0 + step - 1) / step : 0;
+#pragma unroll
+  for (int i = 0; i < kTailStages - 1; ++i) {
+    if (i < n) {
+      sm.issue(i, mid + (p0 + i * step) * 64 + cg * 8);
+      sdo.issue(i, dout + (p0 + i * step) * 4);
+    }
+    cp_async_commit();
+  }
+  for (long long i = 0; i < n; ++i) {
+    const long long j = i + kTailStages - 1;
+    if (j < n) {
+      sm.issue((int)(j % kTailStages), mid + (p0 + j * step) * 64 + cg * 8);
+      sdo.issue((int)(j % kTailStages), dout + (p0 + j * step) * 4);
+    }
+    cp_async_commit();
+    const long long p = p0 + i * step;
+    cp_async_wait<kTailStages - 1>();
+    const float4 gq = sdo.get((int)(i % kTailStages));
+    const float g0 = gq.x, g1 = gq.y, g2 = gq.z;
+    const F8 v = sm.get((int)(i % kTailStages));
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float pre = fmaf(v.v[e], sc.v[e], sh.v[e]);
@@ -205,6 +259,7 @@ tail_bwd_reduce_kernel(const float* __restrict__ dout, const TY* __restrict__ mi
     }
     if (cg == 0) { db[0] += g0; db[1] += g1; db[2] += g2; }
   }
+  cp_async_wait<0>();
   block_reduce64(sg, red, cg, row, acc);
   block_reduce64(sgx, red, cg, row, acc + 64);
   block_reduce64(dw[0], red, cg, row, acc + 128);
@@ -244,11 +299,31 @@ tail_bwd_dmid_kernel(const float* __restrict__ dout, const TY* __restrict__ mid,
     k1[e] = (float)(acc[cg * 8 + e] / (double)M);
     k2[e] = (float)(acc[64 + cg * 8 + e] / (double)M);
   }
-  for (long long p = (long long)blockIdx.x * 32 + row; p < M; p += (long long)gridDim.x * 32) {
-    const long long b = p / HWo, hw = p % HWo;
-    const float* dp = dout + b * 3 * HWo + hw;
-    const float g0 = __ldg(dp), g1 = __ldg(dp + HWo), g2 = __ldg(dp + 2 * HWo);
-    const F8 v = load8(mid + p * 64 + cg * 8);
+  extern __shared__ __align__(16) char dyn_smem[];
+  Stream8<TY, kTailStages> sm(dyn_smem, 256);
+  Stream4f<kTailStages> sdo(dyn_smem + Stream8<TY, kTailStages>::bytes(256), 256);
+  const long long p0 = (long long)blockIdx.x * 32 + row, step = (long long)gridDim.x * 32;
+  const long long n = p0 < M ? (M - p0 + step - 1) / step : 0;
+#pragma unroll
+  for (int i = 0; i < kTailStages - 1; ++i) {
+    if (i < n) {
+      sm.issue(i, mid + (p0 + i * step) * 64 + cg * 8);
+      sdo.issue(i, dout + (p0 + i * step) * 4);
+    }
+    cp_async_commit();
+  }
+  for (long long i = 0; i < n; ++i) {
+    const long long j = i + kTailStages - 1;
+    if (j < n) {
+      sm.issue((int)(j % kTailStages), mid + (p0 + j * step) * 64 + cg * 8);
+      sdo.issue((int)(j % kTailStages), dout + (p0 + j * step) * 4);
+    }
+    cp_async_commit();
+    const long long p = p0 + i * step;
+    cp_async_wait<kTailStages - 1>();
+    const float4 gq = sdo.get((int)(i % kTailStages));
+    const float g0 = gq.x, g1 = gq.y, g2 = gq.z;
+    const F8 v = sm.get((int)(i % kTailStages));
     F8 o;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -260,6 +335,7 @@ tail_bwd_dmid_kernel(const float* __restrict__ dout, const TY* __restrict__ mid,
     }
     store8(dmid + p * 64 + cg * 8, o);
   }
+  cp_async_wait<0>();
 }
 
 // ---- dz = up^T(dd1[:3] + dout): one thread per HxW pixel gathers the 4x4 output neighbourhood ----
@@ -354,7 +430,11 @@ tail_dec1_bwd_kernel(const float* __restrict__ dz4, const T* __restrict__ d2, in
   }
 }
 
+static void tail_ring_attr(const void* kernel, int bytes) {
+  if (bytes > 32 * 1024) (void)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
 static inline int rows_grid(long long M) { return clamp_grid((M + 31) / 32, 8); }
+static inline int rows_grid4(long long M) { return clamp_grid((M + 127) / 128, 8); }
 static inline int ew_grid(long long items) { return clamp_grid((items + 255) / 256, 16); }
 
 }  // namespace eunet
@@ -370,17 +450,24 @@ int eunet_tail_dec1_fwd(const void* d2, int ldd2, int dtype, const float* w1, co
   return check_launch("tail_dec1_fwd");
 }
 
-int eunet_tail_up_fwd(const float* z4, void* d1p, int dtype, int B, int H, int W, void* stream) {
+int eunet_tail_pack3(const float* src, float* dst4, int B, int H, int W, void* stream) {
+  EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "tail_pack3: bad shape");
+  tail_pack3_kernel<<<ew_grid((long long)B * H * W), 256, 0, (cudaStream_t)stream>>>(src, dst4, B, (long long)H * W);
+  return check_launch("tail_pack3");
+}
+
+int eunet_tail_up_fwd(const float* z4, void* d1p, float* d14, int dtype, int B, int H, int W, void* stream) {
   EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "tail_up_fwd: bad shape");
-  DISPATCH_DTYPE(dtype, tail_up_fwd_kernel<T><<<ew_grid(4LL * B * H * W), 256, 0, (cudaStream_t)stream>>>(z4, (T*)d1p, B, H, W));
+  DISPATCH_DTYPE(dtype, tail_up_fwd_kernel<T><<<ew_grid(4LL * B * H * W), 256, 0, (cudaStream_t)stream>>>(z4, (T*)d1p, d14, B, H, W));
   return check_launch("tail_up_fwd");
 }
 
-int eunet_tail_out_fwd(const float* z4, const void* mid, int dtype, const float* scale, const float* shift, const float* w3,
+int eunet_tail_out_fwd(const float* d14, const void* mid, int dtype, const float* scale, const float* shift, const float* w3,
                        const float* b3, float* out, int B, int H, int W, void* stream) {
   EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "tail_out_fwd: bad shape");
-  DISPATCH_DTYPE(dtype, tail_out_fwd_kernel<TY><<<rows_grid(4LL * B * H * W), 256, 0, (cudaStream_t)stream>>>(
-                            z4, (const TY*)mid, scale, shift, w3, b3, out, B, H, W));
+  DISPATCH_DTYPE(dtype, tail_ring_attr((const void*)tail_out_fwd_kernel<TY>, Stream8<TY, kTailStages>::bytes(256) + Stream4f<kTailStages>::bytes(256));
+                 tail_out_fwd_kernel<TY><<<rows_grid(4LL * B * H * W), 256, Stream8<TY, kTailStages>::bytes(256) + Stream4f<kTailStages>::bytes(256), (cudaStream_t)stream>>>(
+                            d14, (const TY*)mid, scale, shift, w3, b3, out, B, H, W));
   return check_launch("tail_out_fwd");
 }
 
@@ -388,7 +475,8 @@ int eunet_tail_bwd_reduce(const float* dout, const void* mid, int dtype, const f
                           const float* mean, const float* invstd, const float* w3, double* acc, int B, int H, int W,
                           void* stream) {
   EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "tail_bwd_reduce: bad shape");
-  DISPATCH_DTYPE(dtype, tail_bwd_reduce_kernel<TY><<<rows_grid(4LL * B * H * W), 256, 0, (cudaStream_t)stream>>>(
+  DISPATCH_DTYPE(dtype, tail_ring_attr((const void*)tail_bwd_reduce_kernel<TY>, Stream8<TY, kTailStages>::bytes(256) + Stream4f<kTailStages>::bytes(256));
+                 tail_bwd_reduce_kernel<TY><<<rows_grid(4LL * B * H * W), 256, Stream8<TY, kTailStages>::bytes(256) + Stream4f<kTailStages>::bytes(256), (cudaStream_t)stream>>>(
                             dout, (const TY*)mid, scale, shift, mean, invstd, w3, acc, B, H, W));
   return check_launch("tail_bwd_reduce");
 }
@@ -397,7 +485,8 @@ int eunet_tail_bwd_dmid(const float* dout, const void* mid, void* dmid, int dtyp
                         const float* mean, const float* invstd, const float* w3, const double* acc, int B, int H, int W,
                         void* stream) {
   EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "tail_bwd_dmid: bad shape");
-  DISPATCH_DTYPE(dtype, tail_bwd_dmid_kernel<T, TY><<<rows_grid(4LL * B * H * W), 256, 0, (cudaStream_t)stream>>>(
+  DISPATCH_DTYPE(dtype, tail_ring_attr((const void*)tail_bwd_dmid_kernel<T, TY>, Stream8<TY, kTailStages>::bytes(256) + Stream4f<kTailStages>::bytes(256));
+                 tail_bwd_dmid_kernel<T, TY><<<rows_grid(4LL * B * H * W), 256, Stream8<TY, kTailStages>::bytes(256) + Stream4f<kTailStages>::bytes(256), (cudaStream_t)stream>>>(
                             dout, (const TY*)mid, (T*)dmid, scale, shift, mean, invstd, w3, acc, B, H, W));
   return check_launch("tail_bwd_dmid");
 }

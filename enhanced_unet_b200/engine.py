@@ -214,7 +214,8 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, train: bool, act_dtype
     z4 = cx.empty(M1, 4, dtype=f32)
     call("eunet_tail_dec1_fwd", ptr(d2), _ld(d2), cx.code, ptr(w1), ptr(sd["model.dec1.bias"]), ptr(z4), M1)
     d1p = cx.empty(M2x, 16)
-    call("eunet_tail_up_fwd", ptr(z4), ptr(d1p), cx.code, B, H, W)
+    d14 = cx.empty(M2x, 4, dtype=f32)
+    call("eunet_tail_up_fwd", ptr(z4), ptr(d1p), ptr(d14), cx.code, B, H, W)
     out = torch.empty(B, 3, 2 * H, 2 * W, device=x.device, dtype=f32)
     midt = cx.empty(M2x, 64, dtype=cx.raw)
     if train:
@@ -228,7 +229,7 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, train: bool, act_dtype
     else:
         _conv_bn_eval(cx, packs, sd, "enhance.0", "enhance.1", d1p, B, 2 * H, 2 * W, 16, 64, midt)
         scale, shift = torch.ones(64, device=x.device, dtype=f32), torch.zeros(64, device=x.device, dtype=f32)
-    call("eunet_tail_out_fwd", ptr(z4), ptr(midt), cx.code, ptr(scale), ptr(shift), ptr(w3), ptr(sd["enhance.3.bias"]), ptr(out),
+    call("eunet_tail_out_fwd", ptr(d14), ptr(midt), cx.code, ptr(scale), ptr(shift), ptr(w3), ptr(sd["enhance.3.bias"]), ptr(out),
          B, H, W)
     if train and want_saved:
         sv.act.update(dict(cat2=cat2, cat3=cat3, cat4=cat4, d2=d2, d1p=d1p, z4=z4))
@@ -258,10 +259,12 @@ def backward(sd: Dict[str, torch.Tensor], sv: Saved, dout: torch.Tensor, act_dty
     w1 = sd["model.dec1.weight"].reshape(3, 64)
     w3 = sd["enhance.3.weight"].reshape(3, 64)
     acc = cx.zeros(328, dtype=f64)
-    call("eunet_tail_bwd_reduce", ptr(dout), ptr(bn.y), cx.code, ptr(bn.scale), ptr(bn.shift), ptr(bn.mean), ptr(bn.invstd),
+    dout4 = cx.empty(M2x, 4, dtype=f32)
+    call("eunet_tail_pack3", ptr(dout), ptr(dout4), B, 2 * H, 2 * W)
+    call("eunet_tail_bwd_reduce", ptr(dout4), ptr(bn.y), cx.code, ptr(bn.scale), ptr(bn.shift), ptr(bn.mean), ptr(bn.invstd),
          ptr(w3), ptr(acc), B, H, W)
     dmid = cx.empty(M2x, 64)
-    call("eunet_tail_bwd_dmid", ptr(dout), ptr(bn.y), ptr(dmid), cx.code, ptr(bn.scale), ptr(bn.shift), ptr(bn.mean),
+    call("eunet_tail_bwd_dmid", ptr(dout4), ptr(bn.y), ptr(dmid), cx.code, ptr(bn.scale), ptr(bn.shift), ptr(bn.mean),
          ptr(bn.invstd), ptr(w3), ptr(acc), B, H, W)
     grads["enhance.1.bias"] = cast64(acc[0:64], (64,))
     grads["enhance.1.weight"] = cast64(acc[64:128], (64,))

@@ -43,7 +43,8 @@ SIGNATURES = {
     "eunet_upsample2_fwd": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p],
     "eunet_upsample2_bwd": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p],
     "eunet_tail_dec1_fwd": [_p, _i, _i, _p, _p, _p, _ll, _p],
-    "eunet_tail_up_fwd": [_p, _p, _i, _i, _i, _i, _p],
+    "eunet_tail_up_fwd": [_p, _p, _p, _i, _i, _i, _i, _p],
+    "eunet_tail_pack3": [_p, _p, _i, _i, _i, _p],
     "eunet_tail_out_fwd": [_p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "eunet_tail_bwd_reduce": [_p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "eunet_tail_bwd_dmid": [_p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],

@@ -103,14 +103,18 @@ int eunet_upsample2_bwd(const void* dout, int ldo, void* dx, int ldx, int dtype,
  * z = dec1(d2) is computed at HxW (a 1x1 conv commutes with bilinear interpolation), d1 = up(z). ---- */
 int eunet_tail_dec1_fwd(const void* d2, int ldd2, int dtype, const float* w1 /*[3][64]*/, const float* b1, float* z4 /*[M][4]*/,
                         long long M, void* stream);
-int eunet_tail_up_fwd(const float* z4, void* d1p /*[B,2H,2W,16]*/, int dtype, int B, int H, int W, void* stream);
-int eunet_tail_out_fwd(const float* z4, const void* mid /*[B,2H,2W,64]*/, int dtype, const float* scale, const float* shift,
+/* d1 = up(z): d1p = activation-dtype copy padded to 16 channels (conv input), d14 = fp32 [4M][4] copy (residual; may be NULL) */
+int eunet_tail_up_fwd(const float* z4, void* d1p /*[B,2H,2W,16]*/, float* d14, int dtype, int B, int H, int W, void* stream);
+/* NCHW fp32 [B,3,H,W] -> pixel-major [B*H*W][4] fp32 (the gradient of the logits as the tail backward kernels read it) */
+int eunet_tail_pack3(const float* src, float* dst4, int B, int H, int W, void* stream);
+int eunet_tail_out_fwd(const float* d14, const void* mid /*[B,2H,2W,64]*/, int dtype, const float* scale, const float* shift,
                        const float* w3 /*[3][64]*/, const float* b3, float* out /*[B,3,2H,2W]*/, int B, int H, int W,
                        void* stream);
-int eunet_tail_bwd_reduce(const float* dout, const void* mid, int dtype, const float* scale, const float* shift,
+/* dout4: pixel-major [4M][4] fp32 gradient of the logits (eunet_tail_pack3) */
+int eunet_tail_bwd_reduce(const float* dout4, const void* mid, int dtype, const float* scale, const float* shift,
                           const float* mean, const float* invstd, const float* w3, double* acc /*[128 + 192 + 3]*/, int B,
                           int H, int W, void* stream);
-int eunet_tail_bwd_dmid(const float* dout, const void* mid, void* dmid, int dtype, const float* scale, const float* shift,
+int eunet_tail_bwd_dmid(const float* dout4, const void* mid, void* dmid, int dtype, const float* scale, const float* shift,
                         const float* mean, const float* invstd, const float* w3, const double* acc, int B, int H, int W,
                         void* stream);
 int eunet_tail_up_bwd(const void* dd1p /*[B,2H,2W,16]*/, int dtype, const float* dout, float* dz4, int B, int H, int W,
