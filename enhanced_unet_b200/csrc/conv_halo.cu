@@ -79,7 +79,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   const uint32_t sbase = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = sbase, b_base = sbase + AS * C::A_SLOT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.y * BN;
+  // blockIdx.x = N tile (fastest in launch order: the CTAs that read the same halo tiles run together and share them
+  // through L2), blockIdx.y = persistent CTA index over the pixel blocks
+  const int n0 = blockIdx.x * BN;
   const int cchunks = p.Cin / KC;
 
   if (warp == 0 && lane == 0) {
@@ -108,7 +110,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             tc::tma_load_2d(b_base + (cc * 9 + tap) * C::B_BYTES, &tmW, wb, tap * p.Cin + cc * KC, n0);
       }
       uint32_t a_it = 0, b_it = 0;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      for (int item = blockIdx.y; item < p.items; item += gridDim.y) {
         const int bx = item % p.blocks_x, by = (item / p.blocks_x) % p.blocks_y, b = item / (p.blocks_x * p.blocks_y);
         const int x0 = bx * 8, y0 = by * (16 * MT);
         for (int cc = 0; cc < cchunks; ++cc) {
@@ -140,7 +142,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         tc::tc_fence_after();
       }
       uint32_t a_it = 0, b_it = 0, li = 0;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++li) {
+      for (int item = blockIdx.y; item < p.items; item += gridDim.y, ++li) {
         const uint32_t ab = li % NACC;
         tc::mbar_wait(tc::smem_u32(&acc_empty[ab]), ((li / NACC) & 1u) ^ 1u);
         tc::tc_fence_after();
@@ -197,7 +199,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 #pragma unroll
       for (int cw = 0; cw < NCW; ++cw) tot1[cw] = tot2[cw] = 0.0;
       uint32_t li = 0;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++li) {
+      for (int item = blockIdx.y; item < p.items; item += gridDim.y, ++li) {
         const int bx = item % p.blocks_x, by = (item / p.blocks_x) % p.blocks_y, b = item / (p.blocks_x * p.blocks_y);
         const uint32_t ab = li % NACC;
         tc::mbar_wait(tc::smem_u32(&acc_full[ab]), (li / NACC) & 1u);
@@ -314,7 +316,7 @@ static int launch_halo(const void* x, int ldx, const void* w, ConvHaloParams p, 
   int per = kNumSMs / ntiles;
   if (per < 1) per = 1;
   if (per > p.items) per = p.items;
-  dim3 grid((unsigned)per, (unsigned)ntiles);
+  dim3 grid((unsigned)ntiles, (unsigned)per);
   kern<<<grid, 320, smem, st>>>(tmX, tmW, p);
   return check_launch("conv3x3_halo");
 }

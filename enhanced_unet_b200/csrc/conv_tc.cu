@@ -432,7 +432,7 @@ static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDY, ConvWgr
   const int co_tiles = (p.Cout + 127) / 128;
   const int zdim = (p.Cin / KC) * (9 / TAPS);
   const int cols = co_tiles * zdim;
-  int splits = (2 * kNumSMs + cols - 1) / cols;          // ~2 CTAs of work per SM
+  int splits = (2 * kNumSMs) / cols;                     // <= 2 CTAs of work per SM (no third, nearly empty wave)
   if (splits > p.tiles) splits = p.tiles;
   if (splits < 1) splits = 1;
   p.tiles_per_split = (p.tiles + splits - 1) / splits;

@@ -21,6 +21,7 @@ struct WgradHaloParams {
   float* dw;
   int B, H, W, Cin, Cout;
   int blocks_x, blocks_y, tiles, tiles_per_split, ci_chunks;
+  int debug_skip_store;
 };
 
 template <int STAGES>
@@ -33,14 +34,16 @@ conv3x3_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
   __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
   __shared__ uint32_t tmem_base_s;
 
-  const int t_begin = blockIdx.x * p.tiles_per_split;
+  // blockIdx.x = (ci chunk, co tile) column, blockIdx.y = pixel split: CTAs that share a pixel range are adjacent in
+  // launch order, so the X / dY tiles they all read are fetched from HBM once and hit in L2 afterwards
+  const int t_begin = blockIdx.y * p.tiles_per_split;
   const int t_end = min(p.tiles, t_begin + p.tiles_per_split);
   const int kiters = t_end - t_begin;
   if (kiters <= 0) return;
 
   const uint32_t sbase = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ci0 = (blockIdx.y % p.ci_chunks) * 64, co0 = (blockIdx.y / p.ci_chunks) * 64;
+  const int ci0 = (blockIdx.x % p.ci_chunks) * 64, co0 = (blockIdx.x / p.ci_chunks) * 64;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { tc::mbar_init(tc::smem_u32(&full_bar[s]), 1); tc::mbar_init(tc::smem_u32(&empty_bar[s]), 1); }
@@ -108,7 +111,7 @@ conv3x3_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
         uint32_t raw[32];
         tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(pr * 64 + c0), raw);
         tc::tmem_ld_wait();
-        if (live) {
+        if (live && !p.debug_skip_store) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int co = co0 + c0 + i;
@@ -128,7 +131,7 @@ int conv3x3_wgrad_halo_bf16(const void* x, int ldx, const void* dy, int lddy, fl
                             cudaStream_t st) {
   if (Cin % 64 != 0 || H < 8 || W < 8) return 1;
   // many (ci chunk, co tile) columns with few pixel tiles each: the per-tap kernel (N = 192 per MMA, fewer atomics) wins
-  if (g_opt_conv_halo != 2 && (long long)Cin * Cout > 128LL * 256) return 1;
+  if (g_opt_conv_halo < 2 && (long long)Cin * Cout > 128LL * 256) return 1;
   constexpr int STAGES = 4;
   constexpr int SMEM = 1024 + STAGES * (23 * 1024 + 128 * 128);
   WgradHaloParams p;
@@ -139,9 +142,10 @@ int conv3x3_wgrad_halo_bf16(const void* x, int ldx, const void* dy, int lddy, fl
   if (tiles > 0x7fffffffLL) return 1;
   p.tiles = (int)tiles;
   p.ci_chunks = Cin / 64;
+  p.debug_skip_store = (g_opt_conv_halo == 3);
   const int co_tiles = (Cout + 63) / 64;
   const int cols = p.ci_chunks * co_tiles;
-  int splits = (2 * kNumSMs + cols - 1) / cols;
+  int splits = (2 * kNumSMs) / cols;   // cols * splits <= 2 CTAs per SM: never spill into a third, nearly empty wave
   if (splits > p.tiles) splits = p.tiles;
   if (splits < 1) splits = 1;
   p.tiles_per_split = (p.tiles + splits - 1) / splits;
@@ -166,7 +170,7 @@ int conv3x3_wgrad_halo_bf16(const void* x, int ldx, const void* dy, int lddy, fl
     EUNET_REQUIRE(e == cudaSuccess, "conv3x3_wgrad_halo: cudaFuncSetAttribute(%d): %s", SMEM, cudaGetErrorString(e));
     configured = true;
   }
-  dim3 grid((unsigned)splits, (unsigned)cols);
+  dim3 grid((unsigned)cols, (unsigned)splits);
   kern<<<grid, 192, SMEM, st>>>(tmX, tmDY, p);
   return check_launch("conv3x3_wgrad_halo");
 }

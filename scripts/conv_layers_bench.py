@@ -14,6 +14,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--res", type=int, default=512)
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--halo", type=int, default=1, help="value of the conv_halo option for the first column")
 args = ap.parse_args()
 B, R = args.batch, args.res
 LAYERS = [("enc1.0", 16, 64, 0), ("enc1.3", 64, 64, 0), ("enc2.0", 64, 128, 1), ("enc2.3", 128, 128, 1), ("enc3.0", 128, 256, 2),
@@ -59,7 +60,7 @@ for name, cin, cout, lvl in LAYERS:
                                              cin, cout)))
     for pname, fn in passes:
         res = []
-        for halo in (1, 0):
+        for halo in (args.halo, 0):
             lib.set_option("conv_halo", halo)
             res.append(timeit(fn))
         lib.set_option("conv_halo", 1)
