@@ -116,69 +116,82 @@ __global__ void tail_pack3_kernel(const float* __restrict__ src, float* __restri
 
 constexpr int kTailStages = 4;   // 64-channel pixels (16 B per lane) in flight per thread
 
-// ---- out = up(z) + b3 + W3 . relu(mid*scale+shift): 8 lanes per output pixel, mid streamed through a per-thread
-// cp.async ring (kTailStages loads in flight) ----
+// ---- out = d1 + b3 + W3 . relu(mid*scale+shift) ----
+// One thread per output pixel (no shuffles, coalesced NCHW stores); the 64-channel rows are staged block-wide
+// through shared memory with cp.async (coalesced 16-byte chunks, 3 tiles of 128 pixels in flight) and read back
+// with a padded pitch so every thread reads its own row conflict-free.  ~50 instructions per 16 bytes moved,
+// i.e. below the ~80 at which a B200 SM stops being HBM-bound.
 template <typename TY>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 tail_out_fwd_kernel(const float* __restrict__ d14, const TY* __restrict__ mid, const float* __restrict__ scale,
                     const float* __restrict__ shift, const float* __restrict__ w3, const float* __restrict__ b3,
                     float* __restrict__ out, int B, int H, int W) {
+  constexpr int STAGES = 3, TP = 128;
+  constexpr int ROWB = 64 * (int)sizeof(TY), PITCH = ROWB + 16, CPR = ROWB / 16;   // 16-byte chunks per row
+  constexpr int STAGE_BYTES = TP * PITCH;
   extern __shared__ __align__(16) char dyn_smem[];
-  Stream8<TY, kTailStages> sm(dyn_smem, 256);
-  Stream4f<kTailStages> sd(dyn_smem + Stream8<TY, kTailStages>::bytes(256), 256);
-  const int cg = threadIdx.x & 7, slot = threadIdx.x >> 3;
+  __shared__ __align__(16) float cst[5][64];          // scale, shift, w3[0..2]
+  __shared__ __align__(16) float4 dres[STAGES][TP];   // the residual d1 pixel of every thread
+  const int tid = threadIdx.x;
   const int Wo = 2 * W, Ho = 2 * H;
-  const long long M = (long long)B * Ho * Wo;
-  const F8 sc = load8(scale + cg * 8), sh = load8(shift + cg * 8);
-  float w[3][8];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const F8 t = load8(w3 + k * 64 + cg * 8);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) w[k][e] = t.v[e];
+  const long long HWo = (long long)Ho * Wo, M = (long long)B * HWo;
+  const long long ntiles = (M + TP - 1) / TP;
+  if (tid < 64) {
+    cst[0][tid] = scale[tid]; cst[1][tid] = shift[tid];
+    cst[2][tid] = w3[tid]; cst[3][tid] = w3[64 + tid]; cst[4][tid] = w3[128 + tid];
   }
-  const float bias = cg < 3 ? b3[cg] : 0.f;
-  const long long p0 = (long long)blockIdx.x * 32 + slot, step = (long long)gridDim.x * 32;
-  const long long n = (M + step - 1) / step;       // same trip count for every thread (shuffles below)
+  const float bb0 = b3[0], bb1 = b3[1], bb2 = b3[2];
+  auto issue = [&](int stage, long long tile) {
+    char* dst = dyn_smem + stage * STAGE_BYTES;
+    const long long pbase = tile * TP;
 #pragma unroll
-  for (int i = 0; i < kTailStages - 1; ++i) {
-    const long long p = p0 + i * step;
-    if (i < n && p < M) {
-      sm.issue(i, mid + p * 64 + cg * 8);
-      if (cg < 3) sd.issue(i, d14 + p * 4);
+    for (int k = 0; k < CPR; ++k) {
+      const int id = k * TP + tid, px = id / CPR, c = id % CPR;
+      if (pbase + px < M) cp_async16(dst + px * PITCH + c * 16, reinterpret_cast<const char*>(mid + (pbase + px) * 64) + c * 16);
     }
+    if (pbase + tid < M) cp_async16(&dres[stage][tid], d14 + (pbase + tid) * 4);
+  };
+  long long t = blockIdx.x;
+#pragma unroll
+  for (int i = 0; i < STAGES - 1; ++i) {
+    if (t + (long long)i * gridDim.x < ntiles) issue(i, t + (long long)i * gridDim.x);
     cp_async_commit();
   }
-  for (long long i = 0; i < n; ++i) {
-    const long long j = i + kTailStages - 1, pj = p0 + j * step;
-    if (j < n && pj < M) {
-      sm.issue((int)(j % kTailStages), mid + pj * 64 + cg * 8);
-      if (cg < 3) sd.issue((int)(j % kTailStages), d14 + pj * 4);
-    }
+  int it = 0;
+  for (; t < ntiles; t += gridDim.x, ++it) {
+    const long long tn = t + (long long)(STAGES - 1) * gridDim.x;
+    if (tn < ntiles) issue((it + STAGES - 1) % STAGES, tn);
     cp_async_commit();
-    cp_async_wait<kTailStages - 1>();
-    const long long p = p0 + i * step;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    cp_async_wait<STAGES - 1>();
+    __syncthreads();                                  // tile `it` has landed for every thread (also publishes cst)
+    const int stage = it % STAGES;
+    const long long p = t * TP + tid;
     if (p < M) {
-      const F8 v = sm.get((int)(i % kTailStages));
+      const char* row = dyn_smem + stage * STAGE_BYTES + tid * PITCH;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float a = fmaxf(fmaf(v.v[e], sc.v[e], sh.v[e]), 0.f);
-        s0 = fmaf(a, w[0][e], s0);
-        s1 = fmaf(a, w[1][e], s1);
-        s2 = fmaf(a, w[2][e], s2);
+      for (int g = 0; g < 8; ++g) {
+        const F8 v = load8(reinterpret_cast<const TY*>(row) + g * 8);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float4 sc = *reinterpret_cast<const float4*>(&cst[0][g * 8 + h * 4]), sh = *reinterpret_cast<const float4*>(&cst[1][g * 8 + h * 4]);
+          const float4 w0 = *reinterpret_cast<const float4*>(&cst[2][g * 8 + h * 4]), w1 = *reinterpret_cast<const float4*>(&cst[3][g * 8 + h * 4]);
+          const float4 w2 = *reinterpret_cast<const float4*>(&cst[4][g * 8 + h * 4]);
+          const float a0 = fmaxf(fmaf(v.v[h * 4 + 0], sc.x, sh.x), 0.f), a1 = fmaxf(fmaf(v.v[h * 4 + 1], sc.y, sh.y), 0.f);
+          const float a2 = fmaxf(fmaf(v.v[h * 4 + 2], sc.z, sh.z), 0.f), a3 = fmaxf(fmaf(v.v[h * 4 + 3], sc.w, sh.w), 0.f);
+          s0 = fmaf(a0, w0.x, s0); s0 = fmaf(a1, w0.y, s0); s0 = fmaf(a2, w0.z, s0); s0 = fmaf(a3, w0.w, s0);
+          s1 = fmaf(a0, w1.x, s1); s1 = fmaf(a1, w1.y, s1); s1 = fmaf(a2, w1.z, s1); s1 = fmaf(a3, w1.w, s1);
+          s2 = fmaf(a0, w2.x, s2); s2 = fmaf(a1, w2.y, s2); s2 = fmaf(a2, w2.z, s2); s2 = fmaf(a3, w2.w, s2);
+        }
       }
+      const float4 d = dres[stage][tid];
+      const long long b = p / HWo, hw = p - b * HWo;
+      float* o = out + b * 3 * HWo + hw;
+      o[0] = d.x + bb0 + s0;
+      o[HWo] = d.y + bb1 + s1;
+      o[2 * HWo] = d.z + bb2 + s2;
     }
-    s0 = group8_sum(s0); s1 = group8_sum(s1); s2 = group8_sum(s2);
-    if (cg < 3 && p < M) {   // lanes 0..2 of the group write one class plane each
-      const int ox = (int)(p % Wo);
-      const int oy = (int)((p / Wo) % Ho);
-      const int b = (int)(p / ((long long)Wo * Ho));
-      const float4 d = sd.get((int)(i % kTailStages));
-      const float sv = cg == 0 ? s0 : (cg == 1 ? s1 : s2);
-      const float dv = cg == 0 ? d.x : (cg == 1 ? d.y : d.z);
-      out[((long long)b * 3 + cg) * Ho * Wo + (long long)oy * Wo + ox] = dv + bias + sv;
-    }
+    __syncthreads();                                  // everyone is done with this stage before it is refilled
   }
   cp_async_wait<0>();
 }
@@ -465,8 +478,8 @@ int eunet_tail_up_fwd(const float* z4, void* d1p, float* d14, int dtype, int B, 
 int eunet_tail_out_fwd(const float* d14, const void* mid, int dtype, const float* scale, const float* shift, const float* w3,
                        const float* b3, float* out, int B, int H, int W, void* stream) {
   EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "tail_out_fwd: bad shape");
-  DISPATCH_DTYPE(dtype, tail_ring_attr((const void*)tail_out_fwd_kernel<TY>, Stream8<TY, kTailStages>::bytes(256) + Stream4f<kTailStages>::bytes(256));
-                 tail_out_fwd_kernel<TY><<<rows_grid(4LL * B * H * W), 256, Stream8<TY, kTailStages>::bytes(256) + Stream4f<kTailStages>::bytes(256), (cudaStream_t)stream>>>(
+  DISPATCH_DTYPE(dtype, tail_ring_attr((const void*)tail_out_fwd_kernel<TY>, 3 * 128 * (64 * (int)sizeof(TY) + 16));
+                 tail_out_fwd_kernel<TY><<<clamp_grid((4LL * B * H * W + 127) / 128, 4), 128, 3 * 128 * (64 * (int)sizeof(TY) + 16), (cudaStream_t)stream>>>(
                             d14, (const TY*)mid, scale, shift, w3, b3, out, B, H, W));
   return check_launch("tail_out_fwd");
 }
