@@ -58,6 +58,8 @@ SIGNATURES = {
     "eunet_fusion_gate_fwd": [_p, _p, _p, _p, _i, _p, _i, _i, _i, _p],
     "eunet_fusion_out_fwd": [_p, _p, _p, _i, _i, _i, _p],
     "eunet_sumsq": [_p, _ll, _p, _p],
+    "eunet_sumsq_multi": [_p, _p, _i, _p, _p],
+    "eunet_adamw_multi": [_p, _p, _p, _p, _p, _i, _p, _f, _f, _f, _f, _f, _f, _i, _f, _p],
     "eunet_adamw_step": [_p, _p, _p, _p, _ll, _p, _f, _f, _f, _f, _f, _f, _i, _f, _p],
     "eunet_probe_umma": [_p, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p, _p, _i, _p],
 }

@@ -8,6 +8,7 @@ train_eval.py:122-132) and checkpoint code (train_eval.py:1143-1151) work on it 
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Callable, Iterable, Optional
 
 import torch
@@ -44,21 +45,35 @@ class ClippedAdamW(torch.optim.Optimizer):
         if self._sq is None or self._sq.device != dev:
             self._sq = torch.zeros((), dtype=torch.float64, device=dev)
         self._sq.zero_()
-        for _, p in items:
-            g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-            call("eunet_sumsq", g.data_ptr(), g.numel(), self._sq.data_ptr())
-        for grp, p in items:
+        grads = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for _, p in items]
+        n = len(items)
+        VP, LL = ctypes.c_void_p * n, ctypes.c_longlong * n
+        g_arr = VP(*[g.data_ptr() for g in grads])
+        n_arr = LL(*[g.numel() for g in grads])
+        call("eunet_sumsq_multi", g_arr, n_arr, n, self._sq.data_ptr())        # global norm over ALL gradients
+        # one fused clip+AdamW launch per run of parameters that share hyper-parameters and step count
+        runs = []
+        for i, (grp, p) in enumerate(items):
             st = self.state[p]
             if len(st) == 0:
                 st["step"] = 0
                 st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
             st["step"] = int(st["step"]) + 1
-            g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-            b1, b2 = grp["betas"]
-            call("eunet_adamw_step", p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
-                 p.numel(), self._sq.data_ptr(), float(grp["max_norm"]), float(grp["lr"]), float(b1), float(b2),
-                 float(grp["eps"]), float(grp["weight_decay"]), st["step"], float(grad_scale))
+            key = (float(grp["max_norm"]), float(grp["lr"]), float(grp["betas"][0]), float(grp["betas"][1]), float(grp["eps"]),
+                   float(grp["weight_decay"]), st["step"])
+            if runs and runs[-1][0] == key:
+                runs[-1][1].append(i)
+            else:
+                runs.append((key, [i]))
+        for key, idxs in runs:
+            k = len(idxs)
+            VPk, LLk = ctypes.c_void_p * k, ctypes.c_longlong * k
+            ps = [items[i][1] for i in idxs]
+            call("eunet_adamw_multi", VPk(*[p.data_ptr() for p in ps]), VPk(*[grads[i].data_ptr() for i in idxs]),
+                 VPk(*[self.state[p]["exp_avg"].data_ptr() for p in ps]), VPk(*[self.state[p]["exp_avg_sq"].data_ptr() for p in ps]),
+                 LLk(*[p.numel() for p in ps]), k, self._sq.data_ptr(), key[0], key[1], key[2], key[3], key[4], key[5], key[6],
+                 float(grad_scale))
         if self.on_update is not None:
             self.on_update()   # parameters changed behind autograd's back: drop packed-filter caches
         return None

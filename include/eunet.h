@@ -155,6 +155,13 @@ int eunet_adamw_step(float* p, const float* g, float* m, float* v, long long n, 
                      float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                      float grad_scale, void* stream);
 
+/* multi-tensor forms (one launch for up to 64 tensors): HOST arrays of `count` device pointers and element counts;
+ * every parameter group shares the hyper-parameters and step count. */
+int eunet_sumsq_multi(const void* const* g, const long long* n, int count, double* out, void* stream);
+int eunet_adamw_multi(void* const* p, const void* const* g, void* const* m, void* const* v, const long long* n, int count,
+                      const double* gradsq, float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay,
+                      int step, float grad_scale, void* stream);
+
 /* ---- bring-up / verification: UMMA + TMA probe (tests/test_gpu_probe.py) ---- */
 int eunet_probe_umma(const void* a, int a_rows, int a_cols, int a_box_rows, int a_box_cols, int a_swizzle, const void* b,
                      int b_rows, int b_cols, int b_box_rows, int b_box_cols, int b_swizzle, const void* x, const int* x_dims,
