@@ -48,6 +48,33 @@ def conv_flops_train(batch: int, res: int) -> float:
     return total
 
 
+def hbm_bytes_per_step(batch: int, res: int) -> dict:
+    """Algorithmic HBM bytes per training step of the bandwidth-bound kernels (every logical input read
+    once + every logical output written once at its storage dtype; bf16/fp16 = 2 B, fp32 = 4 B)."""
+    bn_layers = [(0, 64)] * 2 + [(1, 128)] * 2 + [(2, 256)] * 2 + [(3, 512)] * 2 + [(2, 256)] * 2 + [(1, 128)] * 2 + [(0, 64)] * 2
+    elems = sum(batch * (res >> l) ** 2 * c for l, c in bn_layers)
+    pooled = sum(batch * (res >> l) ** 2 * c // 4 for l, c in ((0, 64), (1, 128), (2, 256)))
+    ups = [(3, 512), (2, 256), (1, 128)]          # (input level, channels)
+    up_bytes = sum(batch * (res >> l) ** 2 * c * 2 * 5 for l, c in ups)        # read in (2 B) + write 4x out (8 B)
+    m1, m2 = batch * res * res, 4 * batch * res * res
+    return {
+        "eunet_bn_apply_relu": elems * 4 + pooled * 2,
+        "eunet_bn_bwd_reduce": elems * 4,
+        "eunet_bn_bwd_apply": elems * 6,
+        "eunet_upsample2_fwd": up_bytes,
+        "eunet_upsample2_bwd": up_bytes,
+        "eunet_maxpool2_bwd": sum(batch * (res >> l) ** 2 * c * (2 + 4) + batch * (res >> l) ** 2 * c // 4 * 2
+                                  for l, c in ((0, 64), (1, 128), (2, 256))),
+        "eunet_tail_out_fwd": m2 * (128 + 16 + 12),
+        "eunet_tail_bwd_reduce": m2 * (128 + 16),
+        "eunet_tail_bwd_dmid": m2 * (128 + 16 + 128),
+        "eunet_tail_dec1_fwd": m1 * (128 + 16),
+        "eunet_tail_dec1_bwd": m1 * (16 + 128 + 128),
+        "eunet_loss_fwd": m1 * (48 + 8),
+        "eunet_loss_bwd": m1 * (48 + 8 + 48),
+    }
+
+
 class ClockSampler:
     """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
 
@@ -276,10 +303,20 @@ def main_gpu(args):
         if "eunet_conv3x3_fwd" in prof:
             fl, msk, n = prof["eunet_conv3x3_fwd"]
             ach = fl / (msk / 1e3) / 1e12
-            roof = {"bound": "tensor", "kernel": "conv3x3_fwd_tc_kernel (fwd + dgrad launches)", "achieved": ach, "peak": peak,
-                    "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": which,
+            hbm_peak = peaks.get("hbm_gbs") or 6650.0
+            hb = hbm_bytes_per_step(BATCH, RES)
+            hbm = {k: {"GB/s": round(hb[k] / (prof[k][1] / 2 / 1e3) / 1e9, 1), "frac": round(hb[k] / (prof[k][1] / 2 / 1e3) / 1e9 / hbm_peak, 3)}
+                   for k in hb if k in prof and prof[k][1] > 0}
+            wg = prof.get("eunet_conv3x3_wgrad")
+            roof = {"bound": "tensor", "kernel": "conv3x3 implicit-GEMM tcgen05 kernels, forward + dgrad launches "
+                                                 "(conv3x3_halo_kernel / conv3x3_fwd_tc_kernel)",
+                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    # dram__bytes_read+write per launch, ncu --set full, mean of the 4 launches in profiles/conv_fwd_tc_r1_ncu_summary.txt
+                    "traffic": 3.04e8, "peak_source": which,
                     "launches_per_step": n // 2, "kernel_ms_per_step": msk / 2,
-                    "all_kernels_ms_per_step": {k: v[1] / 2 for k, v in prof.items()}}
+                    "wgrad_tflops": (wg[0] / (wg[1] / 1e3) / 1e12) if wg else None,
+                    "hbm_kernels": hbm, "hbm_peak_gbs": hbm_peak,
+                    "all_kernels_ms_per_step": {k: round(v[1] / 2, 4) for k, v in prof.items()}}
         if world == 1 and not args.no_cpu:
             r = run_cpu(2, 1)
             cpu = {"value": r["img512_per_s"], "unit": "images/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
@@ -303,8 +340,8 @@ def main_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the bounded CPU baseline leg")
     args = ap.parse_args()

@@ -14,6 +14,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--res", type=int, default=512)
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--only", default="", help="comma-separated layer names")
 ap.add_argument("--halo", type=int, default=1, help="value of the conv_halo option for the first column")
 args = ap.parse_args()
 B, R = args.batch, args.res
@@ -39,6 +40,8 @@ def timeit(fn):
 tot = {}
 print(f"{'layer':8} {'pass':6} {'GFLOP':>8} | {'halo ms':>8} {'TF/s':>7} | {'pertap ms':>9} {'TF/s':>7}")
 for name, cin, cout, lvl in LAYERS:
+    if args.only and name not in args.only.split(","):
+        continue
     h = (R >> lvl) if lvl >= 0 else 2 * R
     M = B * h * h
     real_cin = 3 if cin == 16 else cin
