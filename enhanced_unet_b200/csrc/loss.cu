@@ -58,8 +58,8 @@ loss_fwd_kernel(const float* __restrict__ logits, const long long* __restrict__ 
   float acc[10];
 #pragma unroll
   for (int i = 0; i < 10; ++i) acc[i] = 0.f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
-    const int h = (int)(i / W), w = (int)(i % W);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (int)HW; i += gridDim.x * blockDim.x) {   // HW < 2^31 (checked on the host)
+    const int h = i / W, w = i % W;
     float z[3], lp[3], p[3];
     load_logits<SCALE>(logits, b, h, w, H, W, z);
     softmax3(z, lp, p);
@@ -147,8 +147,8 @@ loss_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ 
     cSp[c] = (float)coef[b * 8 + 3 + c];
   }
   const float cF = (float)coef[b * 8 + 6];
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
-    const int h = (int)(i / W), w = (int)(i % W);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (int)HW; i += gridDim.x * blockDim.x) {   // HW < 2^31 (checked on the host)
+    const int h = i / W, w = i % W;
     float z[3], lp[3], p[3];
     load_logits<SCALE>(logits, b, h, w, H, W, z);
     softmax3(z, lp, p);
@@ -192,7 +192,7 @@ using namespace eunet;
 
 extern "C" int eunet_loss_fwd(const float* logits, const long long* target, int B, int H, int W, int logits_scale,
                               double* partial, float* loss, float* per_sample, double* coef, void* stream) {
-  EUNET_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, "loss_fwd: bad shape B=%d H=%d W=%d", B, H, W);
+  EUNET_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0 && (long long)H * W < (1LL << 30), "loss_fwd: bad shape B=%d H=%d W=%d", B, H, W);
   EUNET_REQUIRE(logits_scale == 1 || logits_scale == 2, "loss_fwd: logits_scale must be 1 or 2");
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(partial, 0, sizeof(double) * 10 * B, st);
@@ -210,7 +210,7 @@ extern "C" int eunet_loss_fwd(const float* logits, const long long* target, int 
 
 extern "C" int eunet_loss_bwd(const float* logits, const long long* target, int B, int H, int W, int logits_scale,
                               const double* coef, const float* grad_out, float* dlogits, void* stream) {
-  EUNET_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, "loss_bwd: bad shape B=%d H=%d W=%d", B, H, W);
+  EUNET_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0 && (long long)H * W < (1LL << 30), "loss_bwd: bad shape B=%d H=%d W=%d", B, H, W);
   EUNET_REQUIRE(logits_scale == 1 || logits_scale == 2, "loss_bwd: logits_scale must be 1 or 2");
   const long long HW = (long long)H * W;
   long long bx_want = (HW + 255) / 256, bx_cap = ((long long)kNumSMs * 8 + B - 1) / B;

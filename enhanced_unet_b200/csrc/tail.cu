@@ -86,12 +86,11 @@ tail_dec1_fwd_kernel(const T* __restrict__ d2, int ld, const float* __restrict__
 // ---- d1p = up(z) padded to 16 channels: one thread per output pixel ----
 template <typename T>
 __global__ void tail_up_fwd_kernel(const float* __restrict__ z4, T* __restrict__ d1p, float* __restrict__ d14, int B, int H, int W) {
-  const long long items = 4LL * B * H * W;
   const int Wo = 2 * W, Ho = 2 * H;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
-    const int ox = (int)(i % Wo);
-    const int oy = (int)((i / Wo) % Ho);
-    const int b = (int)(i / ((long long)Wo * Ho));
+  for (int row = blockIdx.x; row < B * Ho; row += gridDim.x)      // one output row per block iteration (32-bit indexing)
+  for (int ox = threadIdx.x; ox < Wo; ox += blockDim.x) {
+    const int oy = row % Ho, b = row / Ho;
+    const long long i = (long long)row * Wo + ox;
     float d[3];
     up_sample3(z4, b, oy, ox, H, W, d);
     F8 lo, hi;
@@ -106,12 +105,11 @@ __global__ void tail_up_fwd_kernel(const float* __restrict__ z4, T* __restrict__
 
 // NCHW fp32 [B,3,Ho,Wo] -> pixel-major float4 (3 channels + pad): one 16-byte load per pixel for the tail kernels
 __global__ void tail_pack3_kernel(const float* __restrict__ src, float* __restrict__ dst4, int B, long long HW) {
-  const long long M = (long long)B * HW;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (long long)gridDim.x * blockDim.x) {
-    const long long b = i / HW, hw = i % HW;
-    const float* p = src + b * 3 * HW + hw;
-    reinterpret_cast<float4*>(dst4)[i] = make_float4(__ldg(p), __ldg(p + HW), __ldg(p + 2 * HW), 0.f);
-  }
+  for (int b = blockIdx.y; b < B; b += gridDim.y)
+    for (long long hw = (long long)blockIdx.x * blockDim.x + threadIdx.x; hw < HW; hw += (long long)gridDim.x * blockDim.x) {
+      const float* p = src + (long long)b * 3 * HW + hw;
+      reinterpret_cast<float4*>(dst4)[(long long)b * HW + hw] = make_float4(__ldg(p), __ldg(p + HW), __ldg(p + 2 * HW), 0.f);
+    }
 }
 
 constexpr int kTailStages = 4;   // 64-channel pixels (16 B per lane) in flight per thread
@@ -370,13 +368,12 @@ __device__ __forceinline__ void load3<__nv_bfloat16>(const __nv_bfloat16* p, flo
 template <typename T>
 __global__ void tail_up_bwd_kernel(const T* __restrict__ dd1p, const float* __restrict__ dout, float* __restrict__ dz4, int B,
                                    int H, int W) {
-  const long long items = (long long)B * H * W;
   const int Wo = 2 * W, Ho = 2 * H;
   const long long HWo = (long long)Ho * Wo;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
-    const int j = (int)(i % W);
-    const int k = (int)((i / W) % H);
-    const int b = (int)(i / ((long long)W * H));
+  for (int row = blockIdx.x; row < B * H; row += gridDim.x)
+  for (int j = threadIdx.x; j < W; j += blockDim.x) {
+    const int k = row % H, b = row / H;
+    const long long i = (long long)row * W + j;
     const float wy[4] = {k > 0 ? 0.25f : 0.f, k > 0 ? 0.75f : 1.f, k < H - 1 ? 0.75f : 1.f, k < H - 1 ? 0.25f : 0.f};
     const float wx[4] = {j > 0 ? 0.25f : 0.f, j > 0 ? 0.75f : 1.f, j < W - 1 ? 0.75f : 1.f, j < W - 1 ? 0.25f : 0.f};
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
@@ -465,13 +462,18 @@ int eunet_tail_dec1_fwd(const void* d2, int ldd2, int dtype, const float* w1, co
 
 int eunet_tail_pack3(const float* src, float* dst4, int B, int H, int W, void* stream) {
   EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "tail_pack3: bad shape");
-  tail_pack3_kernel<<<ew_grid((long long)B * H * W), 256, 0, (cudaStream_t)stream>>>(src, dst4, B, (long long)H * W);
+  {
+    const long long HW = (long long)H * W;
+    long long bx = (HW + 255) / 256, cap = ((long long)kNumSMs * 8 + B - 1) / B;
+    dim3 grid((unsigned)(bx < cap ? bx : cap), (unsigned)(B < 65535 ? B : 65535));
+    tail_pack3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst4, B, HW);
+  }
   return check_launch("tail_pack3");
 }
 
 int eunet_tail_up_fwd(const float* z4, void* d1p, float* d14, int dtype, int B, int H, int W, void* stream) {
   EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "tail_up_fwd: bad shape");
-  DISPATCH_DTYPE(dtype, tail_up_fwd_kernel<T><<<ew_grid(4LL * B * H * W), 256, 0, (cudaStream_t)stream>>>(z4, (T*)d1p, d14, B, H, W));
+  DISPATCH_DTYPE(dtype, tail_up_fwd_kernel<T><<<clamp_grid(2LL * B * H, 16), 256, 0, (cudaStream_t)stream>>>(z4, (T*)d1p, d14, B, H, W));
   return check_launch("tail_up_fwd");
 }
 
@@ -506,7 +508,7 @@ int eunet_tail_bwd_dmid(const float* dout, const void* mid, void* dmid, int dtyp
 
 int eunet_tail_up_bwd(const void* dd1p, int dtype, const float* dout, float* dz4, int B, int H, int W, void* stream) {
   EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "tail_up_bwd: bad shape");
-  DISPATCH_DTYPE(dtype, tail_up_bwd_kernel<T><<<ew_grid((long long)B * H * W), 256, 0, (cudaStream_t)stream>>>(
+  DISPATCH_DTYPE(dtype, tail_up_bwd_kernel<T><<<clamp_grid((long long)B * H, 16), 256, 0, (cudaStream_t)stream>>>(
                             (const T*)dd1p, dout, dz4, B, H, W));
   return check_launch("tail_up_bwd");
 }
