@@ -195,3 +195,37 @@ def test_bf16_full_size_properties():
             continue
         assert torch.isfinite(p.grad).all(), n
         assert nerr(p.grad, g1[n]) < 0.2, (n, nerr(p.grad, g1[n]))
+
+
+@pytest.mark.parametrize("shape", [(4, 1024, 1024), (1, 2048, 2048)])
+def test_inference_configs_masks_and_counts(shape):
+    """BASELINE configs 4 / 5 (high-res and whole-slide inference, reduced batch): eval-mode bf16 logits stay within
+    2e-2 of the fp32-mode path (itself pinned to the reference at 1e-6), thresholded masks agree on >= 99.9 % of the
+    pixels, and the integer metric pipeline (logits -> probabilities -> mask cascade -> confusion counts) is
+    bit-identical between a batched device run and the per-image CPU oracle."""
+    import oracle
+    from enhanced_unet_b200.train_eval import Evaluator
+    from enhanced_unet_b200.ops import confusion_counts
+    b, h, w = shape
+    sd = oracle.make_state_dict(4)
+    x = oracle.make_input(b, h, w, 5).cuda()
+    m16, m32 = _model("bf16", sd).eval(), _model("fp32", sd).eval()
+    with torch.no_grad():
+        y16 = m16(x)
+        y32 = m32(x)
+    assert y16.shape == (b, 3, 2 * h, 2 * w)
+    err = nerr(y16, y32)
+    agree = (torch.nn.functional.avg_pool2d(y16, 2).argmax(1) == torch.nn.functional.avg_pool2d(y32, 2).argmax(1)).float().mean().item()
+    print(f"[infer {shape}] bf16 vs fp32-mode logits err {err:.3e}, mask agreement {agree:.5f}")
+    assert err <= 2e-2 and agree >= 0.999
+    del y32, m32
+    ev = Evaluator(m16, "cuda", "enhanced_unet")
+    probs = ev._probs(x)
+    masks = ev._convert_probs_to_mask_device(probs)                      # uint8 [B,h,w]
+    gt = oracle.make_target(b, h, w, 6).to(torch.uint8).cuda()
+    cm = confusion_counts(masks, gt)
+    assert torch.equal(cm.sum((1, 2)), torch.full((b,), h * w, device="cuda"))
+    # per-image CPU oracle on the first image: cascade and counts must be bit-identical
+    want_mask = oracle.convert_probs_to_mask(probs[0].cpu().numpy())
+    assert np.array_equal(masks[0].cpu().numpy().astype(np.int64), want_mask)
+    assert np.array_equal(cm[0].cpu().numpy(), oracle.confusion_counts(want_mask[None], gt[0].cpu().numpy()[None])[0])
