@@ -431,18 +431,28 @@ bn_bwd_apply_kernel(const T* __restrict__ dact, int ldd, const TY* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 // packing
 // ------------------------------------------------------------------------------------------------
+// x [B,C,H,W] fp32 -> NHWC, Cpad channels.  split (C == 3, Cpad >= 9): channels [0,3) = hi = T(x), [3,6) = lo = T(x - hi),
+// [6,9) = hi again - with filters packed as {w_hi, w_hi, w_lo} the first convolution evaluates x*w to ~16 mantissa
+// bits on the bf16 tensor cores using channels that would otherwise be zero padding.
 template <typename T>
-__global__ void pack_input_kernel(const float* __restrict__ x, T* __restrict__ out, int B, int C, int H, int W, int Cpad) {
-  const long long items = (long long)B * H * W;
+__global__ void pack_input_kernel(const float* __restrict__ x, T* __restrict__ out, int B, int C, int H, int W, int Cpad, int split) {
+  const long long HW = (long long)H * W, items = (long long)B * HW;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < items; p += (long long)gridDim.x * blockDim.x) {
-    const long long hw = p % ((long long)H * W);
-    const long long b = p / ((long long)H * W);
+    const long long hw = p % HW, b = p / HW;
     for (int c0 = 0; c0 < Cpad; c0 += 8) {
       F8 v;
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int c = c0 + e;
-        v.v[e] = c < C ? x[(b * C + c) * (long long)H * W + hw] : 0.f;
+        float val = 0.f;
+        if (!split) {
+          if (c < C) val = x[(b * C + c) * HW + hw];
+        } else if (c < 9) {
+          const float xv = x[(b * C + c % 3) * HW + hw];
+          const float hi = round_to<T>(xv);
+          val = (c >= 3 && c < 6) ? xv - hi : hi;
+        }
+        v.v[e] = val;
       }
       store8(out + p * Cpad + c0, v);
     }
@@ -453,29 +463,34 @@ template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int Co, int Ci, int CoPad, int CiPad,
                                    int transpose_flip) {
   // output rows R = transpose_flip ? CiPad : CoPad, inner K = transpose_flip ? CoPad : CiPad
-  const int rows = transpose_flip ? CiPad : CoPad, inner = transpose_flip ? CoPad : CiPad;
+  const int rows = transpose_flip == 1 ? CiPad : CoPad, inner = transpose_flip == 1 ? CoPad : CiPad;
   const long long items = (long long)rows * 9 * inner;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(i % inner);
     const int tap = (int)((i / inner) % 9);
     const int r = (int)(i / ((long long)inner * 9));
     float v = 0.f;
-    if (!transpose_flip) {
+    if (transpose_flip == 0) {
       if (r < Co && k < Ci) v = w[((long long)r * Ci + k) * 9 + tap];
-    } else {
+    } else if (transpose_flip == 1) {
       if (k < Co && r < Ci) v = w[((long long)k * Ci + r) * 9 + (8 - tap)];
+    } else if (r < Co && k < 9) {   // mode 2 (Ci == 3): {w_hi, w_hi, w_lo} for the {x_hi, x_lo, x_hi} input split
+      const float wv = w[((long long)r * Ci + k % 3) * 9 + tap];
+      const float hi = round_to<T>(wv);
+      v = k < 6 ? hi : wv - hi;
     }
     out[i] = from_f32<T>(v);
   }
 }
 
-__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Co, int Ci, int CiPad) {
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Co, int Ci, int CiPad, int hilo) {
   const long long items = (long long)Co * Ci * 9;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
     const int tap = (int)(i % 9);
     const int ci = (int)((i / 9) % Ci);
     const int co = (int)(i / (9LL * Ci));
-    dw[i] = dwp[((long long)co * 9 + tap) * CiPad + ci];
+    const float* row = dwp + ((long long)co * 9 + tap) * CiPad;
+    dw[i] = hilo ? row[ci] + row[3 + ci] : row[ci];   // hi/lo input split: d/dw sums the x_hi and x_lo channels
   }
 }
 
@@ -608,25 +623,29 @@ int eunet_upsample2_bwd(const void* dout, int ldo, void* dx, int ldx, int dtype,
   return check_launch("upsample2_bwd");
 }
 
-int eunet_pack_input_nchw(const float* x, void* out, int dtype, int B, int C, int H, int W, int Cpad, void* stream) {
+int eunet_pack_input_nchw(const float* x, void* out, int dtype, int B, int C, int H, int W, int Cpad, int split_hilo,
+                          void* stream) {
   EUNET_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && Cpad >= C && (Cpad & 7) == 0, "pack_input: bad shape");
+  EUNET_REQUIRE(!split_hilo || (C == 3 && Cpad >= 9), "pack_input: the hi/lo split needs C == 3 and Cpad >= 9");
   DISPATCH_DTYPE(dtype, pack_input_kernel<T><<<ew_grid((long long)B * H * W), 256, 0, (cudaStream_t)stream>>>(x, (T*)out, B, C,
-                                                                                                               H, W, Cpad));
+                                                                                                               H, W, Cpad, split_hilo));
   return check_launch("pack_input_nchw");
 }
 
 int eunet_pack_weight3x3(const float* w, void* out, int dtype, int Co, int Ci, int CoPad, int CiPad, int transpose_flip,
                          void* stream) {
   EUNET_REQUIRE(Co > 0 && Ci > 0 && CoPad >= Co && CiPad >= Ci, "pack_weight3x3: bad shape");
+  EUNET_REQUIRE(transpose_flip >= 0 && transpose_flip <= 2 && (transpose_flip != 2 || (Ci == 3 && CiPad >= 9)),
+                "pack_weight3x3: bad mode %d", transpose_flip);
   const long long items = (long long)CoPad * 9 * CiPad;
   DISPATCH_DTYPE(dtype, pack_weight_kernel<T><<<ew_grid(items), 256, 0, (cudaStream_t)stream>>>(w, (T*)out, Co, Ci, CoPad,
                                                                                                  CiPad, transpose_flip));
   return check_launch("pack_weight3x3");
 }
 
-int eunet_unpack_wgrad3x3(const float* dw_packed, float* dw, int Co, int Ci, int CiPad, void* stream) {
-  EUNET_REQUIRE(Co > 0 && Ci > 0 && CiPad >= Ci, "unpack_wgrad3x3: bad shape");
-  unpack_wgrad_kernel<<<ew_grid((long long)Co * Ci * 9), 256, 0, (cudaStream_t)stream>>>(dw_packed, dw, Co, Ci, CiPad);
+int eunet_unpack_wgrad3x3(const float* dw_packed, float* dw, int Co, int Ci, int CiPad, int hilo, void* stream) {
+  EUNET_REQUIRE(Co > 0 && Ci > 0 && CiPad >= Ci && (!hilo || (Ci == 3 && CiPad >= 6)), "unpack_wgrad3x3: bad shape");
+  unpack_wgrad_kernel<<<ew_grid((long long)Co * Ci * 9), 256, 0, (cudaStream_t)stream>>>(dw_packed, dw, Co, Ci, CiPad, hilo);
   return check_launch("unpack_wgrad3x3");
 }
 

@@ -62,8 +62,8 @@ class PackCache:
     def __init__(self):
         self._c: Dict[Tuple[str, int, int], Tuple[int, int, torch.Tensor]] = {}
 
-    def get(self, cx: _Ctx, name: str, w: torch.Tensor, flip: bool) -> torch.Tensor:
-        key = (name, int(flip), cx.code)
+    def get(self, cx: _Ctx, name: str, w: torch.Tensor, flip: bool, hilo: bool = False) -> torch.Tensor:
+        key = (name, 2 if hilo else int(flip), cx.code)
         ver = (w._version, w.data_ptr())
         hit = self._c.get(key)
         if hit is not None and hit[0] == ver and hit[2].device == w.device:
@@ -72,7 +72,7 @@ class PackCache:
         cop, cip = _pad16(co), _pad16(ci)
         rows, inner = (cip, cop) if flip else (cop, cip)
         out = cx.empty(rows, 9, inner)
-        call("eunet_pack_weight3x3", ptr(w), ptr(out), cx.code, co, ci, cop, cip, int(flip))
+        call("eunet_pack_weight3x3", ptr(w), ptr(out), cx.code, co, ci, cop, cip, 2 if hilo else int(flip))
         self._c[key] = (ver, 0, out)
         return out
 
@@ -96,10 +96,16 @@ def conv3x3_wgrad(cx: _Ctx, x: torch.Tensor, dy: torch.Tensor, B: int, H: int, W
     return dwp
 
 
-def unpack_wgrad(dwp: torch.Tensor, co: int, ci: int) -> torch.Tensor:
+def unpack_wgrad(dwp: torch.Tensor, co: int, ci: int, hilo: bool = False) -> torch.Tensor:
     dw = torch.empty(co, ci, 3, 3, device=dwp.device, dtype=torch.float32)
-    call("eunet_unpack_wgrad3x3", ptr(dwp), ptr(dw), co, ci, dwp.shape[2])
+    call("eunet_unpack_wgrad3x3", ptr(dwp), ptr(dw), co, ci, dwp.shape[2], int(hilo))
     return dw
+
+
+def _first_layer_split(cx: _Ctx) -> bool:
+    """bf16 mode: the 3-channel network input and the first filters are split into hi + lo bf16 parts that ride in the
+    otherwise zero padding channels (free: K stays 16), removing the largest single source of train-mode logit error."""
+    return cx.dt == torch.bfloat16
 
 
 class _BNSaved:
@@ -110,11 +116,11 @@ class _BNSaved:
 
 
 def _conv_bn_train(cx: _Ctx, packs: PackCache, sd: Dict[str, torch.Tensor], conv: str, bn: str, x: torch.Tensor, B, H, W, cin_p,
-                   cout, out: torch.Tensor, pooled: Optional[torch.Tensor]) -> _BNSaved:
+                   cout, out: torch.Tensor, pooled: Optional[torch.Tensor], hilo: bool = False) -> _BNSaved:
     M = B * H * W
     y = cx.empty(M, cout, dtype=cx.raw)
     stats = cx.zeros(2 * cout, dtype=torch.float64)
-    conv3x3(cx, x, packs.get(cx, conv, sd[conv + ".weight"], False), y, B, H, W, cin_p, cout, stats=stats)
+    conv3x3(cx, x, packs.get(cx, conv, sd[conv + ".weight"], False, hilo), y, B, H, W, cin_p, cout, stats=stats)
     f32 = torch.float32
     scale, shift, mean, invstd = (cx.empty(cout, dtype=f32) for _ in range(4))
     call("eunet_bn_finalize", ptr(stats), M, ptr(sd[bn + ".weight"]), ptr(sd[bn + ".bias"]), ptr(sd[conv + ".bias"]),
@@ -125,12 +131,13 @@ def _conv_bn_train(cx: _Ctx, packs: PackCache, sd: Dict[str, torch.Tensor], conv
     return _BNSaved(y, scale, shift, mean, invstd)
 
 
-def _conv_bn_eval(cx: _Ctx, packs: PackCache, sd, conv: str, bn: str, x, B, H, W, cin_p, cout, out) -> None:
+def _conv_bn_eval(cx: _Ctx, packs: PackCache, sd, conv: str, bn: str, x, B, H, W, cin_p, cout, out, hilo: bool = False) -> None:
     f32 = torch.float32
     scale, shift = cx.empty(cout, dtype=f32), cx.empty(cout, dtype=f32)
     call("eunet_bn_fold_eval", ptr(sd[bn + ".weight"]), ptr(sd[bn + ".bias"]), ptr(sd[conv + ".bias"]),
          ptr(sd[bn + ".running_mean"]), ptr(sd[bn + ".running_var"]), BN_EPS, ptr(scale), ptr(shift), cout)
-    conv3x3(cx, x, packs.get(cx, conv, sd[conv + ".weight"], False), out, B, H, W, cin_p, cout, scale=scale, shift=shift, relu=True)
+    conv3x3(cx, x, packs.get(cx, conv, sd[conv + ".weight"], False, hilo), out, B, H, W, cin_p, cout, scale=scale, shift=shift,
+            relu=True)
 
 
 class Saved:
@@ -166,7 +173,8 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, train: bool, act_dtype
     Ms = [B * h * w for h, w in dims]
 
     x16 = cx.empty(Ms[0], 16)
-    call("eunet_pack_input_nchw", ptr(x), ptr(x16), cx.code, B, 3, H, W, 16)
+    hilo = _first_layer_split(cx)
+    call("eunet_pack_input_nchw", ptr(x), ptr(x16), cx.code, B, 3, H, W, 16, int(hilo))
     sv.x16 = x16
 
     cat2 = cx.empty(Ms[0], 192)   # [up(d3) | e1]
@@ -180,13 +188,15 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, train: bool, act_dtype
     def block(prefix, xin, lvl, cin_p, cout, out, pooled=None):
         h, w = dims[lvl]
         mid = cx.empty(Ms[lvl], cout)
+        first = hilo and prefix == "model.enc1"
         if train:
-            sv.bn[prefix + ".1"] = _conv_bn_train(cx, packs, sd, prefix + ".0", prefix + ".1", xin, B, h, w, cin_p, cout, mid, None)
+            sv.bn[prefix + ".1"] = _conv_bn_train(cx, packs, sd, prefix + ".0", prefix + ".1", xin, B, h, w, cin_p, cout, mid, None,
+                                                  hilo=first)
             sv.bn[prefix + ".4"] = _conv_bn_train(cx, packs, sd, prefix + ".3", prefix + ".4", mid, B, h, w, cout, cout, out, pooled)
             sv.act[prefix + ".in"] = xin
             sv.act[prefix + ".mid"] = mid
         else:
-            _conv_bn_eval(cx, packs, sd, prefix + ".0", prefix + ".1", xin, B, h, w, cin_p, cout, mid)
+            _conv_bn_eval(cx, packs, sd, prefix + ".0", prefix + ".1", xin, B, h, w, cin_p, cout, mid, hilo=first)
             _conv_bn_eval(cx, packs, sd, prefix + ".3", prefix + ".4", mid, B, h, w, cout, cout, out)
             if pooled is not None:
                 call("eunet_maxpool2_fwd", ptr(out), _ld(out), ptr(pooled), _ld(pooled), cx.code, B, h, w, cout)
@@ -309,7 +319,8 @@ def backward(sd: Dict[str, torch.Tensor], sv: Saved, dout: torch.Tensor, act_dty
         dmid_act = cx.empty(M, cout)
         conv3x3(cx, dy_b, packs.get(cx, prefix + ".3", sd[prefix + ".3.weight"], True), dmid_act, B, h, w, cout, cout)
         dy_a = bn_bwd(prefix + ".1", dmid_act, M, cout)
-        grads[prefix + ".0.weight"] = unpack_wgrad(conv3x3_wgrad(cx, xin, dy_a, B, h, w, cin_p, cout), cout, cin)
+        grads[prefix + ".0.weight"] = unpack_wgrad(conv3x3_wgrad(cx, xin, dy_a, B, h, w, cin_p, cout), cout, cin,
+                                                   hilo=(prefix == "model.enc1" and _first_layer_split(cx)))
         grads[prefix + ".0.bias"] = torch.zeros(cout, device=dout.device, dtype=f32)
         if not need_dx:
             return None

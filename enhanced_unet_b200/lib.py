@@ -28,9 +28,9 @@ SIGNATURES = {
     "eunet_device_info": [_p, _p, _p, _p],
     "eunet_set_option": [C.c_char_p, _i],
     "eunet_confusion4x4": [_p, _p, _i, _ll, _ll, _p, _p],
-    "eunet_pack_input_nchw": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "eunet_pack_input_nchw": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "eunet_pack_weight3x3": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
-    "eunet_unpack_wgrad3x3": [_p, _p, _i, _i, _i, _p],
+    "eunet_unpack_wgrad3x3": [_p, _p, _i, _i, _i, _i, _p],
     "eunet_conv3x3_fwd": [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _i, _p],
     "eunet_conv3x3_wgrad": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p],
     "eunet_bn_finalize": [_p, _ll, _p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _i, _p],

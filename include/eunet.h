@@ -46,15 +46,19 @@ int eunet_confusion4x4(const void* pred, const void* gt, int elem_bytes, long lo
                        long long* counts /* [n_images][4][4], overwritten */, void* stream);
 
 /* ---- layout / parameter packing (host glue of models.py:227-238: NCHW fp32 tensors at the boundary) ---- */
-/* x [B,C,H,W] fp32 -> NHWC with Cpad channels (zero padded), dtype */
-int eunet_pack_input_nchw(const float* x, void* out, int dtype, int B, int C, int H, int W, int Cpad, void* stream);
+/* x [B,C,H,W] fp32 -> NHWC with Cpad channels (zero padded), dtype.
+ * split_hilo (C == 3): channels {0-2, 3-5, 6-8} = {hi, lo, hi} with hi = dtype(x), lo = dtype(x - hi); together with
+ * filters packed in mode 2 the first convolution then sees ~16 mantissa bits of the input and of its weights. */
+int eunet_pack_input_nchw(const float* x, void* out, int dtype, int B, int C, int H, int W, int Cpad, int split_hilo,
+                          void* stream);
 /* w [Co,Ci,3,3] fp32 (nn.Conv2d.weight) -> packed [CoPad][9][CiPad] dtype.
  * transpose_flip = 0: forward form out[co][tap][ci] = w[co][ci][tap];
- * transpose_flip = 1: dgrad form   out[ci][8-tap][co] = w[co][ci][tap] (so dgrad is a forward conv over dY). */
+ * transpose_flip = 1: dgrad form   out[ci][8-tap][co] = w[co][ci][tap] (so dgrad is a forward conv over dY);
+ * transpose_flip = 2: forward form for a hi/lo split 3-channel input: input channels {0-2, 3-5, 6-8} = {w_hi, w_hi, w_lo}. */
 int eunet_pack_weight3x3(const float* w, void* out, int dtype, int Co, int Ci, int CoPad, int CiPad, int transpose_flip,
                          void* stream);
-/* dw_packed [Co][9][CiPad] fp32 -> dw [Co,Ci,3,3] fp32 (layout of nn.Conv2d.weight.grad) */
-int eunet_unpack_wgrad3x3(const float* dw_packed, float* dw, int Co, int Ci, int CiPad, void* stream);
+/* dw_packed [Co][9][CiPad] fp32 -> dw [Co,Ci,3,3] fp32 (layout of nn.Conv2d.weight.grad); hilo: sum the x_hi / x_lo channels */
+int eunet_unpack_wgrad3x3(const float* dw_packed, float* dw, int Co, int Ci, int CiPad, int hilo, void* stream);
 
 /* ---- nn.Conv2d(k=3, padding=1) forward (models.py:219,222,309) and its autograd dgrad/wgrad
  * (loss.backward(), train_eval.py:338).  bf16: tcgen05/TMEM implicit GEMM with TMA-staged tiles;

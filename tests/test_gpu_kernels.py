@@ -286,7 +286,7 @@ def test_conv3x3_dgrad_and_wgrad(k, dtn, case):
     k.call("eunet_conv3x3_wgrad", xd.data_ptr(), Cin, dyd.data_ptr(), dyd.stride(0), dwp.data_ptr(), k.dtype_code(dt), B, H, W,
            Cin, Cout)
     dw = torch.empty(Cout, Cin, 3, 3, device="cuda")
-    k.call("eunet_unpack_wgrad3x3", dwp.data_ptr(), dw.data_ptr(), Cout, Cin, Cin)
+    k.call("eunet_unpack_wgrad3x3", dwp.data_ptr(), dw.data_ptr(), Cout, Cin, Cin, 0)
     k.set_option("conv_halo", 1)
     assert nerr(dw.cpu(), w.grad) < 2e-5     # fp32 accumulation in both modes (inputs are identical)
 
@@ -295,9 +295,32 @@ def test_pack_input_and_padded_weights(k):
     g = torch.Generator().manual_seed(4)
     x = torch.rand(2, 3, 8, 8, generator=g)
     out = torch.empty(2 * 64, 16, dtype=torch.bfloat16, device="cuda")
-    k.call("eunet_pack_input_nchw", x.cuda().data_ptr(), out.data_ptr(), k.BF16, 2, 3, 8, 8, 16)
+    k.call("eunet_pack_input_nchw", x.cuda().data_ptr(), out.data_ptr(), k.BF16, 2, 3, 8, 8, 16, 0)
     want = torch.zeros(2, 16, 8, 8); want[:, :3] = x.to(torch.bfloat16).float()
     assert torch.equal(nchw(out, 2, 8, 8), want)
+    # hi/lo split of the 3-channel input + {w_hi, w_hi, w_lo} filters: the bf16 conv then reproduces the fp32 conv to ~2^-16
+    k.call("eunet_pack_input_nchw", x.cuda().data_ptr(), out.data_ptr(), k.BF16, 2, 3, 8, 8, 16, 1)
+    hi = x.to(torch.bfloat16).float()
+    got = nchw(out, 2, 8, 8)
+    assert torch.equal(got[:, 0:3], hi) and torch.equal(got[:, 6:9], hi) and torch.equal(got[:, 3:6], (x - hi).to(torch.bfloat16).float())
+    assert float(got[:, 9:].abs().max()) == 0.0
+    w1 = torch.randn(64, 3, 3, 3, generator=g) / 5
+    wp2 = torch.empty(64, 9, 16, dtype=torch.bfloat16, device="cuda")
+    k.call("eunet_pack_weight3x3", w1.cuda().data_ptr(), wp2.data_ptr(), k.BF16, 64, 3, 64, 16, 2)
+    y = torch.empty(2 * 64, 64, dtype=torch.float16, device="cuda")
+    k.call("eunet_conv3x3_fwd", out.data_ptr(), 16, wp2.data_ptr(), y.data_ptr(), 64, k.BF16, 2, 8, 8, 16, 64, None, None, None, 0, 1)
+    ref = F.conv2d(x, w1, None, padding=1)
+    assert nerr(nchw(y, 2, 8, 8), ref) < 1e-3            # fp16 output rounding only (plain bf16 operands: ~4e-3)
+    dy = torch.randn(2, 64, 8, 8, generator=g).to(torch.bfloat16)
+    dyd = nhwc(dy.float(), torch.bfloat16)
+    dwp = torch.zeros(64, 9, 16, dtype=torch.float32, device="cuda")
+    k.call("eunet_conv3x3_wgrad", out.data_ptr(), 16, dyd.data_ptr(), 64, dwp.data_ptr(), k.BF16, 2, 8, 8, 16, 64)
+    dw = torch.empty(64, 3, 3, 3, device="cuda")
+    k.call("eunet_unpack_wgrad3x3", dwp.data_ptr(), dw.data_ptr(), 64, 3, 16, 1)
+    xr = x.clone().requires_grad_(False)
+    wr = w1.clone().requires_grad_(True)
+    F.conv2d(xr, wr, None, padding=1).backward(dy.float())
+    assert nerr(dw.cpu(), wr.grad) < 1e-4                  # x_hi + x_lo carries ~16 bits of the input
     w = torch.randn(64, 3, 3, 3, generator=g)
     wp = torch.empty(64, 9, 16, dtype=torch.float32, device="cuda")
     k.call("eunet_pack_weight3x3", w.cuda().data_ptr(), wp.data_ptr(), k.F32, 64, 3, 64, 16, 0)
