@@ -238,3 +238,4 @@ def test_wgrad_v2_tap_pair_stacked_in_m(pu):
     REPORT["wgrad_v2_pairs"] = res
     _save()
     assert max(res.values()) < 1e-5, res
+
