@@ -225,7 +225,7 @@ def main_gpu(args):
     model = EnhancedUNet(3, dtype="bf16").to(dev).train()
     params = [p for p in model.parameters()]
     parallel.broadcast_parameters(list(model.parameters()) + list(model.buffers()))
-    allreduce = parallel.GradientAllReduce(params)
+    allreduce = parallel.GradientAllReduce(model)   # gradients land in one flat buffer; buckets are exchanged DURING backward
     opt = ClippedAdamW(params, on_update=model._packs.clear)
     x_dev, t_dev = synth_batch(BATCH, RES, 1234 + 1000 * rank, dev)
     x_host = x_dev.cpu().pin_memory()
@@ -237,8 +237,7 @@ def main_gpu(args):
             p.grad = None
         y = model(x)
         loss = combined_loss(y, t)
-        loss.backward()
-        allreduce.reduce()          # no-op at world size 1
+        loss.backward()             # launches the bucketed gradient all-reduce as gradients are finished (N > 1)
         allreduce.wait()
         opt.step(grad_scale=1.0 / world)
         return loss

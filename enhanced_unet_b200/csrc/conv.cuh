@@ -16,6 +16,7 @@ int conv3x3_fwd_halo_bf16(const void* x, int ldx, const void* w, void* y, int ld
 int conv3x3_wgrad_halo_bf16(const void* x, int ldx, const void* dy, int lddy, float* dw, int B, int H, int W, int Cin, int Cout,
                             cudaStream_t st);
 extern int g_opt_conv_halo;   // 1 (default): use the halo kernel where it applies
+extern int g_opt_tma_store;   // 1 (default): Cout = 64 halo kernels write their output tile with a TMA tensor store
 
 // Power-of-two (bw, bh, bb) with bw*bh*bb == pixels minimising the number of tiles over a [B,H,W] image batch.
 struct PixelTile {

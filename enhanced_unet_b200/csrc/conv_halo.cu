@@ -13,6 +13,7 @@
 //
 // Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..9 epilogue.
 #include <cuda_bf16.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "conv.cuh"
@@ -46,7 +47,7 @@ __device__ __forceinline__ float warp_transpose_sum32h(float (&v)[32], int lane)
   return v[0];
 }
 
-template <int KC, int BN, int MT, bool WRES>
+template <int KC, int BN, int MT, bool WRES, bool TST = false>
 struct HaloCfg {
   static constexpr int ROWB = KC * 2;                                   // bytes per pixel row of a tile
   static constexpr int HALO_ROWS = (16 * MT + 2) * 10;
@@ -60,25 +61,37 @@ struct HaloCfg {
   static constexpr int BSTAGES = WRES ? 0 : (BN >= 128 ? 4 : 6);
   static constexpr int CH = BN >= 32 ? 32 : 16;
   static constexpr int NCHUNK = BN / CH;
+  // TST: the epilogue stages an item's output tile in shared memory (128-byte swizzled rows = one pixel's BN = 64
+  // channels) and ONE thread writes it with a TMA tensor store.  Per-thread 16-byte global stores touch 32 different
+  // 128-byte lines per warp instruction and made the store-bound layers (3->64 at 2Hx2W) L1/LSU-bound.
+  static constexpr int STG_BYTES = TST ? MT * 128 * BN * 2 : 0;
+  static_assert(!TST || (BN == 64 && WRES), "TMA-store epilogue: BN = 64 (one 128-byte row per pixel), resident filters");
   static int smem_bytes(int cchunks) {
-    return 1024 + ASTAGES * A_SLOT + (WRES ? 9 * cchunks * B_BYTES : BSTAGES * B_BYTES);
+    return 1024 + ASTAGES * A_SLOT + (WRES ? 9 * cchunks * B_BYTES : BSTAGES * B_BYTES) + 2 * STG_BYTES;
   }
 };
 
-template <int KC, int BN, int MT, bool WRES>
+template <int KC, int BN, int MT, bool WRES, bool TST>
 __global__ void __launch_bounds__(320, 1)
-conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const ConvHaloParams p) {
-  using C = HaloCfg<KC, BN, MT, WRES>;
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                    const __grid_constant__ CUtensorMap tmY, const ConvHaloParams p) {
+  using C = HaloCfg<KC, BN, MT, WRES, TST>;
   constexpr uint32_t LAYOUT = KC == 64 ? tc::kSwizzle128 : tc::kSwizzle32;
   constexpr int AS = C::ASTAGES, BS = WRES ? 1 : C::BSTAGES, NACC = C::NACC, CH = C::CH;
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[AS], a_empty[AS], b_full[BS], b_empty[BS], acc_full[2], acc_empty[2], w_full;
   __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float s_scale[BN], s_shift[BN];   // folded-BN affine of this CTA's channel tile (eval epilogue)
 
   const uint32_t sbase = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = sbase, b_base = sbase + AS * C::A_SLOT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p.scale != nullptr)
+    for (int i = threadIdx.x; i < BN; i += blockDim.x) {
+      s_scale[i] = p.scale[blockIdx.x * BN + i];
+      s_shift[i] = p.shift[blockIdx.x * BN + i];
+    }
   // blockIdx.x = N tile (fastest in launch order: the CTAs that read the same halo tiles run together and share them
   // through L2), blockIdx.y = persistent CTA index over the pixel blocks
   const int n0 = blockIdx.x * BN;
@@ -92,6 +105,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     tc::mbar_fence_init();
     tc::tma_prefetch_desc(&tmX);
     tc::tma_prefetch_desc(&tmW);
+    if (TST) tc::tma_prefetch_desc(&tmY);
   }
   if (warp == 1) tc::tmem_alloc(tc::smem_u32(&tmem_base_s), C::TMEM_COLS);
   tc::tc_fence_before();
@@ -187,18 +201,40 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   } else {
     // ===================== epilogue: 8 warps =====================
     // warp w owns TMEM lanes [32 (w%4), +32); the two warps of a lane quarter split the column chunks (even / odd).
-    // BN statistics: per-thread fp32 sums over its rows of the MT tiles, ONE 31-shuffle transpose-reduce per chunk and
-    // item into fp64 per-lane column totals, flushed with fp64 atomics when the CTA is done.
+    // BN statistics: per-thread fp32 partial sums (packed f32x2 adds / fmas) over its rows, reduced over the warp's 32
+    // rows by ONE 31-shuffle transpose-reduce per flush into fp64 per-lane column totals, which go out with fp64
+    // atomics when the CTA is done.  With one column chunk per warp (BN <= 64) the partials stay in registers across
+    // kFlush items (<= 32 addends per fp32 partial); otherwise they are flushed per chunk and item.
+    // With two epilogue warps per scheduler the epilogue is issue-latency bound, so instruction count is what matters.
     const int e = warp - 2, q = warp & 3, half = e >> 2;
+    // TMA-store staging (2 buffers, 1024-byte aligned: the filters / B ring in front are multiples of 1 KB)
+    const uint32_t stg_base = b_base + (WRES ? 9u * cchunks * C::B_BYTES : (uint32_t)(C::BSTAGES * C::B_BYTES));
     constexpr int NCW = (C::NCHUNK >= 2) ? C::NCHUNK / 2 : 1;
+    constexpr int kFlush = 8;
     const bool active = (C::NCHUNK >= 2) || half == 0;
     if (active) {
       const int r = q * 32 + lane;                 // GEMM row inside a 128-row tile: (ty, tx) = (r / 8, r % 8)
       const int ty = r >> 3, tx = r & 7;
+      const bool want_stats = p.stats != nullptr, affine = p.scale != nullptr;
       double tot1[NCW], tot2[NCW];
 #pragma unroll
       for (int cw = 0; cw < NCW; ++cw) tot1[cw] = tot2[cw] = 0.0;
+      uint64_t run1[16], run2[16];             // f32x2 pairs: columns (2i, 2i+1) of the current chunk
+#pragma unroll
+      for (int i = 0; i < 16; ++i) run1[i] = run2[i] = 0ull;
+      auto flush = [&](int cw) {
+        float a[32], c[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          tc::unpack_f32x2(run1[i], a[2 * i], a[2 * i + 1]);
+          tc::unpack_f32x2(run2[i], c[2 * i], c[2 * i + 1]);
+          run1[i] = run2[i] = 0ull;
+        }
+        tot1[cw] += (double)warp_transpose_sum32h(a, lane);
+        tot2[cw] += (double)warp_transpose_sum32h(c, lane);
+      };
       uint32_t li = 0;
+      int pending = 0;
       for (int item = blockIdx.y; item < p.items; item += gridDim.y, ++li) {
         const int bx = item % p.blocks_x, by = (item / p.blocks_x) % p.blocks_y, b = item / (p.blocks_x * p.blocks_y);
         const uint32_t ab = li % NACC;
@@ -208,15 +244,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 #pragma unroll
         for (int cw = 0; cw < NCW; ++cw) {
           const int c0 = ((C::NCHUNK >= 2) ? 2 * cw + half : 0) * CH;
-          float run1[32], run2[32];            // this thread's rows of the MT tiles, one column chunk
-#pragma unroll
-          for (int i = 0; i < 32; ++i) run1[i] = run2[i] = 0.f;
 #pragma unroll 1
           for (int mt = 0; mt < MT; ++mt) {
             const int gy = by * (16 * MT) + 16 * mt + ty;
             const bool valid = gx < p.W && gy < p.H;
-            const long long pix = ((long long)b * p.H + gy) * p.W + gx;
-            uint16_t* yrow = reinterpret_cast<uint16_t*>(p.y) + pix * p.ldy + n0;
             uint32_t raw[32];
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((ab * MT + mt) * BN + c0);
             if (CH == 32) tc::tmem_ld32(taddr, raw);
@@ -226,46 +257,84 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
               for (int i = 16; i < 32; ++i) raw[i] = 0u;
             }
             tc::tmem_ld_wait();
-            if (p.stats != nullptr && valid) {
+            if (want_stats && valid) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const float f = __uint_as_float(raw[i]);
-                run1[i] += f;
-                run2[i] = fmaf(f, f, run2[i]);
+              for (int i = 0; i < CH / 2; ++i) {
+                const uint64_t v = tc::pack_f32x2(raw[2 * i], raw[2 * i + 1]);
+                run1[i] = tc::add_f32x2(run1[i], v);
+                run2[i] = tc::fma_f32x2(v, v, run2[i]);
               }
             }
-            if (valid) {
+            if (TST || valid) {
+              uint32_t dst_s = 0;
+              uint16_t* dst_g = nullptr;
+              if (TST) {   // every row is staged (rows outside the image are clipped by the tensor store)
+                dst_s = stg_base + (li & 1u) * C::STG_BYTES + (uint32_t)((mt * 128 + r) * 128);
+              } else {
+                const long long pix = ((long long)b * p.H + gy) * p.W + gx;
+                dst_g = reinterpret_cast<uint16_t*>(p.y) + pix * p.ldy + n0 + c0;
+              }
 #pragma unroll
               for (int g8 = 0; g8 < CH / 8; ++g8) {
                 float o[8];
 #pragma unroll
-                for (int ee = 0; ee < 8; ++ee) {
-                  float f = __uint_as_float(raw[g8 * 8 + ee]);
-                  if (p.scale != nullptr) f = fmaf(f, __ldg(p.scale + n0 + c0 + g8 * 8 + ee), __ldg(p.shift + n0 + c0 + g8 * 8 + ee));
-                  if (p.relu) f = fmaxf(f, 0.f);
-                  o[ee] = f;
+                for (int ee = 0; ee < 8; ++ee) o[ee] = __uint_as_float(raw[g8 * 8 + ee]);
+                if (affine) {
+#pragma unroll
+                  for (int h4 = 0; h4 < 2; ++h4) {
+                    const float4 sc = *reinterpret_cast<const float4*>(&s_scale[c0 + g8 * 8 + h4 * 4]);
+                    const float4 sh = *reinterpret_cast<const float4*>(&s_shift[c0 + g8 * 8 + h4 * 4]);
+                    o[h4 * 4 + 0] = fmaf(o[h4 * 4 + 0], sc.x, sh.x); o[h4 * 4 + 1] = fmaf(o[h4 * 4 + 1], sc.y, sh.y);
+                    o[h4 * 4 + 2] = fmaf(o[h4 * 4 + 2], sc.z, sh.z); o[h4 * 4 + 3] = fmaf(o[h4 * 4 + 3], sc.w, sh.w);
+                  }
+                }
+                if (p.relu) {
+#pragma unroll
+                  for (int ee = 0; ee < 8; ++ee) o[ee] = fmaxf(o[ee], 0.f);
                 }
                 uint4 u;
                 if (p.out_f16) {
-                  u.x = pack_f16x2(o[0], o[1]); u.y = pack_f16x2(o[2], o[3]); u.z = pack_f16x2(o[4], o[5]); u.w = pack_f16x2(o[6], o[7]);
+                  u.x = tc::cvt_f16x2_sat(o[0], o[1]); u.y = tc::cvt_f16x2_sat(o[2], o[3]);
+                  u.z = tc::cvt_f16x2_sat(o[4], o[5]); u.w = tc::cvt_f16x2_sat(o[6], o[7]);
                 } else {
                   u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]); u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
                 }
-                *reinterpret_cast<uint4*>(yrow + c0 + g8 * 8) = u;
+                if (TST) {
+                  const uint32_t chunk = (uint32_t)(c0 / 8 + g8);
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst_s + ((chunk ^ (uint32_t)(r & 7)) << 4)),
+                               "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w)
+                               : "memory");
+                } else {
+                  *reinterpret_cast<uint4*>(dst_g + g8 * 8) = u;
+                }
               }
             }
           }
-          if (p.stats != nullptr) {
-            tot1[cw] += (double)warp_transpose_sum32h(run1, lane);
-            tot2[cw] += (double)warp_transpose_sum32h(run2, lane);
-          }
+          if (NCW > 1 && want_stats) flush(cw);
+        }
+        if (NCW == 1 && want_stats && ++pending == kFlush) {
+          flush(0);
+          pending = 0;
         }
         // this accumulator set may be overwritten once every participating epilogue warp has drained it
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[ab]));
+        if (TST) {
+          // the store of item li-1 has finished reading its buffer before anyone passes this barrier, so item li+1 may
+          // overwrite that buffer without a second barrier; the store of item li is issued right after it
+          tc::fence_proxy_async_smem();
+          if (e == 0 && lane == 0) tc::tma_store_wait_read<0>();
+          tc::named_bar_sync(1, 256);
+          if (e == 0 && lane == 0) {
+            tc::tma_store_4d(&tmY, stg_base + (li & 1u) * C::STG_BYTES, n0, bx * 8, by * (16 * MT), b);
+            tc::tma_store_commit();
+          }
+        }
       }
-      if (p.stats != nullptr) {
+      if (TST && e == 0 && lane == 0) tc::tma_store_wait<0>();
+      if (want_stats) {
+        if (NCW == 1 && pending > 0) flush(0);
 #pragma unroll
         for (int cw = 0; cw < NCW; ++cw) {
           const int c0 = ((C::NCHUNK >= 2) ? 2 * cw + half : 0) * CH;
@@ -282,9 +351,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   if (warp == 1) tc::tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
-template <int KC, int BN, int MT, bool WRES>
+template <int KC, int BN, int MT, bool WRES, bool TST = false>
 static int launch_halo(const void* x, int ldx, const void* w, ConvHaloParams p, cudaStream_t st) {
-  using C = HaloCfg<KC, BN, MT, WRES>;
+  using C = HaloCfg<KC, BN, MT, WRES, TST>;
   const int cchunks = p.Cin / KC;
   const int smem = C::smem_bytes(cchunks);
   if (smem > 227 * 1024) return 1;   // does not fit: caller falls back to the per-tap kernel
@@ -293,7 +362,15 @@ static int launch_halo(const void* x, int ldx, const void* w, ConvHaloParams p, 
   const long long items = (long long)p.blocks_x * p.blocks_y * p.B;
   if (items > 0x7fffffffLL) return 1;
   p.items = (int)items;
-  CUtensorMap tmX, tmW;
+  CUtensorMap tmX, tmW, tmY;
+  if (TST) {
+    uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.B};
+    uint64_t str[3] = {(uint64_t)p.ldy * 2, (uint64_t)p.ldy * 2 * p.W, (uint64_t)p.ldy * 2 * p.W * p.H};
+    uint32_t box[4] = {(uint32_t)BN, 8u, (uint32_t)(16 * MT), 1u};
+    if (tc::encode_tensor_map_bf16(&tmY, p.y, 4, dims, str, box, 128)) return -1;   // 2-byte elements (bf16 or fp16 bits)
+  } else {
+    memset(&tmY, 0, sizeof(tmY));
+  }
   {
     uint64_t dims[4] = {(uint64_t)p.Cin, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.B};
     uint64_t str[3] = {(uint64_t)ldx * 2, (uint64_t)ldx * 2 * p.W, (uint64_t)ldx * 2 * p.W * p.H};
@@ -305,7 +382,7 @@ static int launch_halo(const void* x, int ldx, const void* w, ConvHaloParams p, 
     uint32_t box[2] = {(uint32_t)KC, (uint32_t)BN};
     if (tc::encode_tensor_map_bf16(&tmW, w, 2, dims, str, box, KC == 64 ? 128 : 32)) return -1;
   }
-  auto kern = conv3x3_halo_kernel<KC, BN, MT, WRES>;
+  auto kern = conv3x3_halo_kernel<KC, BN, MT, WRES, TST>;
   static int configured = 0;
   if (configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -317,7 +394,7 @@ static int launch_halo(const void* x, int ldx, const void* w, ConvHaloParams p, 
   if (per < 1) per = 1;
   if (per > p.items) per = p.items;
   dim3 grid((unsigned)ntiles, (unsigned)per);
-  kern<<<grid, 320, smem, st>>>(tmX, tmW, p);
+  kern<<<grid, 320, smem, st>>>(tmX, tmW, tmY, p);
   return check_launch("conv3x3_halo");
 }
 
@@ -337,13 +414,15 @@ int conv3x3_fwd_halo_bf16(const void* x, int ldx, const void* w, void* y, int ld
     }
     if (Cout % 128 == 0) return launch_halo<64, 128, 2, false>(x, ldx, w, p, st);
     if (Cout % 64 == 0) {
-      if (Cin == 64) return launch_halo<64, 64, 2, true>(x, ldx, w, p, st);
+      if (Cin == 64) return g_opt_tma_store ? launch_halo<64, 64, 2, true, true>(x, ldx, w, p, st)
+                                            : launch_halo<64, 64, 2, true>(x, ldx, w, p, st);
       return launch_halo<64, 64, 4, false>(x, ldx, w, p, st);
     }
     if (Cout == 16 && Cin == 64) return launch_halo<64, 16, 4, true>(x, ldx, w, p, st);
     return 1;
   }
-  if (Cin == 16 && Cout % 64 == 0 && Cout % 128 != 0) return launch_halo<16, 64, 4, true>(x, ldx, w, p, st);
+  if (Cin == 16 && Cout % 64 == 0 && Cout % 128 != 0)
+    return g_opt_tma_store ? launch_halo<16, 64, 4, true, true>(x, ldx, w, p, st) : launch_halo<16, 64, 4, true>(x, ldx, w, p, st);
   return 1;
 }
 

@@ -22,6 +22,7 @@
 namespace eunet {
 
 int g_opt_conv_halo = 1;
+int g_opt_tma_store = 1;
 
 PixelTile choose_pixel_tile(int B, int H, int W, int pixels) {
   PixelTile best{};
@@ -473,6 +474,10 @@ using namespace eunet;
 extern "C" int eunet_set_option(const char* name, int value) {
   if (strcmp(name, "conv_halo") == 0) {
     g_opt_conv_halo = value;
+    return 0;
+  }
+  if (strcmp(name, "tma_store") == 0) {
+    g_opt_tma_store = value;
     return 0;
   }
   set_error("unknown option '%s'", name);

@@ -217,90 +217,114 @@ __global__ void maxpool2_bwd_kernel(const T* __restrict__ dpool, int ldp, const 
 // ------------------------------------------------------------------------------------------------
 // bilinear x2 upsample, align_corners=False.  Output rows 2k / 2k+1 of input row k:
 //   out[2k]   = .25*in[k-1] + .75*in[k]   (k = 0: in[0]);   out[2k+1] = .75*in[k] + .25*in[k+1]  (k = H-1: in[H-1])
+// One thread = 8 channels of one input row k over a run of kUpSeg columns: the vertically interpolated columns
+// (top / bottom output row) slide along the row in registers, so every step costs 3 loads + 4 stores (forward) or
+// 8 loads + 1 store (adjoint) instead of 9 + 4 / 16 + 1.  Item order: channel group fastest, then k, so the threads
+// of a block share their three input rows through L1.
 // ------------------------------------------------------------------------------------------------
+constexpr int kUpSeg = 8;
+
 template <typename T>
-__global__ void upsample2_fwd_kernel(const T* __restrict__ x, int ldx, T* __restrict__ out, int ldo, int B, int H, int W,
-                                     int C) {
-  const int G = C >> 3;
-  const long long items = (long long)B * H * W * G;
+__global__ void __launch_bounds__(256)
+upsample2_fwd_kernel(const T* __restrict__ x, int ldx, T* __restrict__ out, int ldo, int B, int H, int W, int C) {
+  const int G = C >> 3, nseg = (W + kUpSeg - 1) / kUpSeg;
+  const long long items = (long long)B * nseg * H * G;
   const int Wo = 2 * W, Ho = 2 * H;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
     const int cg = (int)(i % G);
     long long q = i / G;
-    const int j = (int)(q % W); q /= W;
-    const int k = (int)(q % H);
-    const int b = (int)(q / H);
-    const float wxp = j > 0 ? 0.25f : 0.f, wxc0 = j > 0 ? 0.75f : 1.f;
-    const float wxn = j < W - 1 ? 0.25f : 0.f, wxc1 = j < W - 1 ? 0.75f : 1.f;
+    const int k = (int)(q % H); q /= H;
+    const int seg = (int)(q % nseg);
+    const int b = (int)(q / nseg);
+    const int j0 = seg * kUpSeg, j1 = min(W, j0 + kUpSeg);
     const float wyp = k > 0 ? 0.25f : 0.f, wyc0 = k > 0 ? 0.75f : 1.f;
     const float wyn = k < H - 1 ? 0.25f : 0.f, wyc1 = k < H - 1 ? 0.75f : 1.f;
-    const int jm = j > 0 ? j - 1 : 0, jp = j < W - 1 ? j + 1 : W - 1;
-    F8 h0[3], h1[3];   // horizontally interpolated rows k-1, k, k+1 for output columns 2j and 2j+1
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      int kk = k + r - 1;
-      kk = kk < 0 ? 0 : (kk > H - 1 ? H - 1 : kk);
-      const T* row = x + (((long long)b * H + kk) * W) * ldx + cg * 8;
-      const F8 a = load8(row + (long long)jm * ldx), c = load8(row + (long long)j * ldx), d = load8(row + (long long)jp * ldx);
+    const T* rm = x + (((long long)b * H + (k > 0 ? k - 1 : 0)) * W) * ldx + cg * 8;
+    const T* rc = x + (((long long)b * H + k) * W) * ldx + cg * 8;
+    const T* rp = x + (((long long)b * H + (k < H - 1 ? k + 1 : H - 1)) * W) * ldx + cg * 8;
+    F8 p0, p1, c0, c1, n0, n1;   // vertically interpolated columns j-1, j, j+1 for output rows 2k (0) and 2k+1 (1)
+    auto vcol = [&](int j, F8& v0, F8& v1) {
+      const F8 a = load8(rm + (long long)j * ldx), c = load8(rc + (long long)j * ldx), d = load8(rp + (long long)j * ldx);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        h0[r].v[e] = wxp * a.v[e] + wxc0 * c.v[e];
-        h1[r].v[e] = wxc1 * c.v[e] + wxn * d.v[e];
+        v0.v[e] = wyp * a.v[e] + wyc0 * c.v[e];
+        v1.v[e] = wyc1 * c.v[e] + wyn * d.v[e];
       }
-    }
-    F8 o00, o01, o10, o11;
+    };
+    vcol(j0 > 0 ? j0 - 1 : 0, p0, p1);
+    vcol(j0, c0, c1);
+    T* o = out + (((long long)b * Ho + 2 * k) * Wo + 2 * j0) * ldo + cg * 8;
+#pragma unroll 2
+    for (int j = j0; j < j1; ++j) {
+      vcol(j < W - 1 ? j + 1 : W - 1, n0, n1);
+      const float wl = j > 0 ? 0.25f : 0.f, wc0 = j > 0 ? 0.75f : 1.f;
+      const float wr = j < W - 1 ? 0.25f : 0.f, wc1 = j < W - 1 ? 0.75f : 1.f;
+      F8 o00, o01, o10, o11;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      o00.v[e] = wyp * h0[0].v[e] + wyc0 * h0[1].v[e];
-      o01.v[e] = wyp * h1[0].v[e] + wyc0 * h1[1].v[e];
-      o10.v[e] = wyc1 * h0[1].v[e] + wyn * h0[2].v[e];
-      o11.v[e] = wyc1 * h1[1].v[e] + wyn * h1[2].v[e];
+      for (int e = 0; e < 8; ++e) {
+        o00.v[e] = wl * p0.v[e] + wc0 * c0.v[e];
+        o01.v[e] = wc1 * c0.v[e] + wr * n0.v[e];
+        o10.v[e] = wl * p1.v[e] + wc0 * c1.v[e];
+        o11.v[e] = wc1 * c1.v[e] + wr * n1.v[e];
+      }
+      store8(o, o00);
+      store8(o + ldo, o01);
+      store8(o + (long long)Wo * ldo, o10);
+      store8(o + (long long)Wo * ldo + ldo, o11);
+      o += 2 * (long long)ldo;
+      p0 = c0; p1 = c1; c0 = n0; c1 = n1;
     }
-    T* o = out + (((long long)b * Ho + 2 * k) * Wo + 2 * j) * ldo + cg * 8;
-    store8(o, o00);
-    store8(o + ldo, o01);
-    store8(o + (long long)Wo * ldo, o10);
-    store8(o + (long long)Wo * ldo + ldo, o11);
   }
 }
 
-// adjoint: input pixel (k,j) gathers output rows 2k-1..2k+2 with weights [.25,.75,.75,.25] (edges: see header)
+// adjoint: input pixel (k,j) gathers output rows 2k-1..2k+2 / columns 2j-1..2j+2 with weights [.25,.75,.75,.25]
+// (at an edge the missing outer sample drops out and the inner weight becomes 1).  The vertically reduced output
+// columns 2j-1, 2j are carried over from the previous step.
 template <typename T>
-__global__ void upsample2_bwd_kernel(const T* __restrict__ dout, int ldo, T* __restrict__ dx, int ldx, int B, int H, int W,
-                                     int C) {
-  const int G = C >> 3;
-  const long long items = (long long)B * H * W * G;
+__global__ void __launch_bounds__(256)
+upsample2_bwd_kernel(const T* __restrict__ dout, int ldo, T* __restrict__ dx, int ldx, int B, int H, int W, int C) {
+  const int G = C >> 3, nseg = (W + kUpSeg - 1) / kUpSeg;
+  const long long items = (long long)B * nseg * H * G;
   const int Wo = 2 * W, Ho = 2 * H;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
     const int cg = (int)(i % G);
     long long q = i / G;
-    const int j = (int)(q % W); q /= W;
-    const int k = (int)(q % H);
-    const int b = (int)(q / H);
+    const int k = (int)(q % H); q /= H;
+    const int seg = (int)(q % nseg);
+    const int b = (int)(q / nseg);
+    const int j0 = seg * kUpSeg, j1 = min(W, j0 + kUpSeg);
     const float wy[4] = {k > 0 ? 0.25f : 0.f, k > 0 ? 0.75f : 1.f, k < H - 1 ? 0.75f : 1.f, k < H - 1 ? 0.25f : 0.f};
-    const float wx[4] = {j > 0 ? 0.25f : 0.f, j > 0 ? 0.75f : 1.f, j < W - 1 ? 0.75f : 1.f, j < W - 1 ? 0.25f : 0.f};
-    F8 acc;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc.v[e] = 0.f;
+    const T* rows[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      if (wy[r] == 0.f) continue;
-      const int oy = 2 * k - 1 + r;
-      F8 rowacc;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) rowacc.v[e] = 0.f;
-#pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        if (wx[s] == 0.f) continue;
-        const int ox = 2 * j - 1 + s;
-        const F8 g = load8(dout + (((long long)b * Ho + oy) * Wo + ox) * ldo + cg * 8);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) rowacc.v[e] += wx[s] * g.v[e];
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc.v[e] += wy[r] * rowacc.v[e];
+      int oy = 2 * k - 1 + r;
+      oy = oy < 0 ? 0 : (oy > Ho - 1 ? Ho - 1 : oy);     // clamped rows carry weight 0
+      rows[r] = dout + (((long long)b * Ho + oy) * Wo) * ldo + cg * 8;
     }
-    store8(dx + (((long long)b * H + k) * W + j) * ldx + cg * 8, acc);
+    auto vcol = [&](int ox, F8& v) {
+      ox = ox < 0 ? 0 : (ox > Wo - 1 ? Wo - 1 : ox);     // clamped columns carry weight 0
+      const F8 g0 = load8(rows[0] + (long long)ox * ldo), g1 = load8(rows[1] + (long long)ox * ldo);
+      const F8 g2 = load8(rows[2] + (long long)ox * ldo), g3 = load8(rows[3] + (long long)ox * ldo);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v.v[e] = wy[0] * g0.v[e] + wy[1] * g1.v[e] + wy[2] * g2.v[e] + wy[3] * g3.v[e];
+    };
+    F8 ca, cb, cc, cd;
+    vcol(2 * j0 - 1, ca);
+    vcol(2 * j0, cb);
+    T* o = dx + (((long long)b * H + k) * W + j0) * ldx + cg * 8;
+#pragma unroll 2
+    for (int j = j0; j < j1; ++j) {
+      vcol(2 * j + 1, cc);
+      vcol(2 * j + 2, cd);
+      const float w0 = j > 0 ? 0.25f : 0.f, w1 = j > 0 ? 0.75f : 1.f;
+      const float w2 = j < W - 1 ? 0.75f : 1.f, w3 = j < W - 1 ? 0.25f : 0.f;
+      F8 acc;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc.v[e] = w0 * ca.v[e] + w1 * cb.v[e] + w2 * cc.v[e] + w3 * cd.v[e];
+      store8(o, acc);
+      o += ldx;
+      ca = cc; cb = cd;
+    }
   }
 }
 
@@ -608,7 +632,7 @@ int eunet_maxpool2_bwd(const void* dpool, int ldp, const void* x, int ldx, void*
 int eunet_upsample2_fwd(const void* x, int ldx, void* out, int ldo, int dtype, int B, int H, int W, int C, void* stream) {
   if (check_vec(x, ldx, C, "upsample2_fwd(x)") || check_vec(out, ldo, C, "upsample2_fwd(out)")) return -1;
   EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "upsample2_fwd: empty tensor");
-  const long long items = (long long)B * H * W * (C / 8);
+  const long long items = (long long)B * H * ((W + kUpSeg - 1) / kUpSeg) * (C / 8);
   DISPATCH_DTYPE(dtype, upsample2_fwd_kernel<T><<<ew_grid(items), 256, 0, (cudaStream_t)stream>>>((const T*)x, ldx, (T*)out,
                                                                                                    ldo, B, H, W, C));
   return check_launch("upsample2_fwd");
@@ -617,7 +641,7 @@ int eunet_upsample2_fwd(const void* x, int ldx, void* out, int ldo, int dtype, i
 int eunet_upsample2_bwd(const void* dout, int ldo, void* dx, int ldx, int dtype, int B, int H, int W, int C, void* stream) {
   if (check_vec(dout, ldo, C, "upsample2_bwd(dout)") || check_vec(dx, ldx, C, "upsample2_bwd(dx)")) return -1;
   EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "upsample2_bwd: empty tensor");
-  const long long items = (long long)B * H * W * (C / 8);
+  const long long items = (long long)B * H * ((W + kUpSeg - 1) / kUpSeg) * (C / 8);
   DISPATCH_DTYPE(dtype, upsample2_bwd_kernel<T><<<ew_grid(items), 256, 0, (cudaStream_t)stream>>>((const T*)dout, ldo, (T*)dx,
                                                                                                    ldx, B, H, W, C));
   return check_launch("upsample2_bwd");

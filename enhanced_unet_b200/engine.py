@@ -96,10 +96,39 @@ def conv3x3_wgrad(cx: _Ctx, x: torch.Tensor, dy: torch.Tensor, B: int, H: int, W
     return dwp
 
 
-def unpack_wgrad(dwp: torch.Tensor, co: int, ci: int, hilo: bool = False) -> torch.Tensor:
-    dw = torch.empty(co, ci, 3, 3, device=dwp.device, dtype=torch.float32)
+def unpack_wgrad(dwp: torch.Tensor, co: int, ci: int, hilo: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    dw = out if out is not None else torch.empty(co, ci, 3, 3, device=dwp.device, dtype=torch.float32)
+    assert dw.is_contiguous() and dw.numel() == co * ci * 9 and dw.dtype == torch.float32
     call("eunet_unpack_wgrad3x3", ptr(dwp), ptr(dw), co, ci, dwp.shape[2], int(hilo))
     return dw
+
+
+class GradSink:
+    """Where ``backward`` puts parameter gradients.  The default allocates one fp32 tensor per parameter; the
+    data-parallel path passes a ``parallel.FlatGradBuffer`` so that gradients land in ONE flat buffer laid out in
+    production order and finished buckets can be all-reduced while the rest of backward still runs."""
+
+    def __init__(self, device: torch.device):
+        self.dev = device
+        self.grads: Dict[str, torch.Tensor] = {}
+
+    def dst(self, name: str, shape) -> torch.Tensor:
+        t = torch.empty(shape, device=self.dev, dtype=torch.float32)
+        self.grads[name] = t
+        return t
+
+    def ready(self, name: str) -> None:
+        pass
+
+
+# order in which ``backward`` finishes parameter gradients (tail first, enc1 last): the layout of flat gradient buffers
+def grad_production_order() -> List[str]:
+    names = ["enhance.1.bias", "enhance.1.weight", "enhance.3.weight", "enhance.3.bias", "enhance.0.weight", "enhance.0.bias",
+             "model.dec1.weight", "model.dec1.bias"]
+    for blk in ("dec2", "dec3", "dec4", "enc4", "enc3", "enc2", "enc1"):
+        for sub in ("4.weight", "4.bias", "3.weight", "3.bias", "1.weight", "1.bias", "0.weight", "0.bias"):
+            names.append(f"model.{blk}.{sub}")
+    return names
 
 
 def _first_layer_split(cx: _Ctx) -> bool:
@@ -247,21 +276,32 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, train: bool, act_dtype
     return out, None
 
 
-def backward(sd: Dict[str, torch.Tensor], sv: Saved, dout: torch.Tensor, act_dtype: torch.dtype, packs: PackCache
-             ) -> Dict[str, torch.Tensor]:
-    """Gradients (fp32, parameter layout) for every parameter of the state_dict."""
+def backward(sd: Dict[str, torch.Tensor], sv: Saved, dout: torch.Tensor, act_dtype: torch.dtype, packs: PackCache,
+             sink: Optional[GradSink] = None) -> Dict[str, torch.Tensor]:
+    """Gradients (fp32, parameter layout) for every parameter of the state_dict, written through ``sink`` in
+    ``grad_production_order()``."""
     B, H, W = sv.B, sv.H, sv.W
     cx = _Ctx(dout.device, act_dtype)
     f32, f64 = torch.float32, torch.float64
     dims = [(H, W), (H // 2, W // 2), (H // 4, W // 4), (H // 8, W // 8)]
     Ms = [B * h * w for h, w in dims]
-    grads: Dict[str, torch.Tensor] = {}
+    if sink is None:
+        sink = GradSink(dout.device)
+    grads = sink.grads
     dout = dout.contiguous().float()
 
-    def cast64(src: torch.Tensor, shape) -> torch.Tensor:
-        dst = torch.empty(shape, device=dout.device, dtype=f32)
+    def cast64(name: str, src: torch.Tensor, shape) -> None:
+        dst = sink.dst(name, shape)
         call("eunet_cast_f64_f32", ptr(src), ptr(dst), dst.numel())
-        return dst
+        sink.ready(name)
+
+    def zero_bias(name: str, c: int) -> None:      # conv bias in front of a train-mode BN: exact zero gradient
+        sink.dst(name, (c,)).zero_()
+        sink.ready(name)
+
+    def wgrad_into(name: str, dwp: torch.Tensor, co: int, ci: int, hilo: bool = False) -> None:
+        unpack_wgrad(dwp, co, ci, hilo, out=sink.dst(name, (co, ci, 3, 3)))
+        sink.ready(name)
 
     # ---- tail ----
     M1, M2x = Ms[0], 4 * Ms[0]
@@ -276,14 +316,14 @@ def backward(sd: Dict[str, torch.Tensor], sv: Saved, dout: torch.Tensor, act_dty
     dmid = cx.empty(M2x, 64)
     call("eunet_tail_bwd_dmid", ptr(dout4), ptr(bn.y), ptr(dmid), cx.code, ptr(bn.scale), ptr(bn.shift), ptr(bn.mean),
          ptr(bn.invstd), ptr(w3), ptr(acc), B, H, W)
-    grads["enhance.1.bias"] = cast64(acc[0:64], (64,))
-    grads["enhance.1.weight"] = cast64(acc[64:128], (64,))
-    grads["enhance.3.weight"] = cast64(acc[128:320], (3, 64, 1, 1))
-    grads["enhance.3.bias"] = cast64(acc[320:323], (3,))
+    cast64("enhance.1.bias", acc[0:64], (64,))
+    cast64("enhance.1.weight", acc[64:128], (64,))
+    cast64("enhance.3.weight", acc[128:320], (3, 64, 1, 1))
+    cast64("enhance.3.bias", acc[320:323], (3,))
     d1p = sv.act["d1p"]
     dwp = conv3x3_wgrad(cx, d1p, dmid, B, 2 * H, 2 * W, 16, 64)
-    grads["enhance.0.weight"] = unpack_wgrad(dwp, 64, 3)
-    grads["enhance.0.bias"] = torch.zeros(64, device=dout.device, dtype=f32)   # cancelled by train-mode BN
+    wgrad_into("enhance.0.weight", dwp, 64, 3)
+    zero_bias("enhance.0.bias", 64)                                            # cancelled by train-mode BN
     dd1p = cx.empty(M2x, 16)
     conv3x3(cx, dmid, packs.get(cx, "enhance.0", sd["enhance.0.weight"], True), dd1p, B, 2 * H, 2 * W, 64, 16)
     dz4 = cx.empty(M1, 4, dtype=f32)
@@ -292,8 +332,8 @@ def backward(sd: Dict[str, torch.Tensor], sv: Saved, dout: torch.Tensor, act_dty
     d2 = sv.act["d2"]
     dd2 = cx.empty(M1, 64)
     call("eunet_tail_dec1_bwd", ptr(dz4), ptr(d2), _ld(d2), ptr(dd2), _ld(dd2), cx.code, ptr(w1), ptr(acc2), M1)
-    grads["model.dec1.weight"] = cast64(acc2[0:192], (3, 64, 1, 1))
-    grads["model.dec1.bias"] = cast64(acc2[192:195], (3,))
+    cast64("model.dec1.weight", acc2[0:192], (3, 64, 1, 1))
+    cast64("model.dec1.bias", acc2[192:195], (3,))
 
     def bn_bwd(name: str, dact: torch.Tensor, M: int, C: int) -> torch.Tensor:
         s = sv.bn[name]
@@ -301,11 +341,11 @@ def backward(sd: Dict[str, torch.Tensor], sv: Saved, dout: torch.Tensor, act_dty
         call("eunet_bn_bwd_reduce", ptr(dact), _ld(dact), ptr(s.y), _ld(s.y), cx.code, M, C, ptr(s.scale), ptr(s.shift),
              ptr(s.mean), ptr(s.invstd), ptr(sums))
         dy = cx.empty(M, C)
-        dg, db = torch.empty(C, device=dout.device, dtype=f32), torch.empty(C, device=dout.device, dtype=f32)
+        dg, db = sink.dst(name + ".weight", (C,)), sink.dst(name + ".bias", (C,))
         call("eunet_bn_bwd_apply", ptr(dact), _ld(dact), ptr(s.y), _ld(s.y), ptr(dy), _ld(dy), cx.code, M, C, ptr(s.scale),
              ptr(s.shift), ptr(s.mean), ptr(s.invstd), ptr(sums), ptr(dg), ptr(db))
-        grads[name + ".weight"] = dg
-        grads[name + ".bias"] = db
+        sink.ready(name + ".weight")
+        sink.ready(name + ".bias")
         return dy
 
     def block_bwd(prefix: str, dact: torch.Tensor, lvl: int, cin: int, cout: int, need_dx: bool) -> Optional[torch.Tensor]:
@@ -314,14 +354,14 @@ def backward(sd: Dict[str, torch.Tensor], sv: Saved, dout: torch.Tensor, act_dty
         cin_p = _pad16(cin)
         xin, mid = sv.act[prefix + ".in"], sv.act[prefix + ".mid"]
         dy_b = bn_bwd(prefix + ".4", dact, M, cout)
-        grads[prefix + ".3.weight"] = unpack_wgrad(conv3x3_wgrad(cx, mid, dy_b, B, h, w, cout, cout), cout, cout)
-        grads[prefix + ".3.bias"] = torch.zeros(cout, device=dout.device, dtype=f32)
+        wgrad_into(prefix + ".3.weight", conv3x3_wgrad(cx, mid, dy_b, B, h, w, cout, cout), cout, cout)
+        zero_bias(prefix + ".3.bias", cout)
         dmid_act = cx.empty(M, cout)
         conv3x3(cx, dy_b, packs.get(cx, prefix + ".3", sd[prefix + ".3.weight"], True), dmid_act, B, h, w, cout, cout)
         dy_a = bn_bwd(prefix + ".1", dmid_act, M, cout)
-        grads[prefix + ".0.weight"] = unpack_wgrad(conv3x3_wgrad(cx, xin, dy_a, B, h, w, cin_p, cout), cout, cin,
-                                                   hilo=(prefix == "model.enc1" and _first_layer_split(cx)))
-        grads[prefix + ".0.bias"] = torch.zeros(cout, device=dout.device, dtype=f32)
+        wgrad_into(prefix + ".0.weight", conv3x3_wgrad(cx, xin, dy_a, B, h, w, cin_p, cout), cout, cin,
+                   hilo=(prefix == "model.enc1" and _first_layer_split(cx)))
+        zero_bias(prefix + ".0.bias", cout)
         if not need_dx:
             return None
         dx = cx.empty(M, cin_p)

@@ -65,10 +65,25 @@ class _UNetFunction(torch.autograd.Function):
         if sv is None:
             raise RuntimeError("EnhancedUNet backward called twice (saved activations were released)")
         sd = module._tensor_dict()
-        grads = engine.backward(sd, sv, dout, module.act_dtype, module._packs)
+        sink = module.grad_sink
+        if sink is not None:
+            sink.begin()
+        grads = engine.backward(sd, sv, dout, module.act_dtype, module._packs, sink=sink)
         ctx.saved_state = None
         names = module._param_names
-        return (None, None) + tuple(grads[n] for n in names)
+        if sink is None:
+            return (None, None) + tuple(grads[n] for n in names)
+        # data-parallel path: .grad IS the slice of the flat buffer the (possibly still running) all-reduce works on;
+        # handing the views to autograd would let AccumulateGrad clone them before the exchange has finished
+        params = dict(module.named_parameters())
+        for n in names:
+            p = params[n]
+            if p.grad is not None:
+                raise RuntimeError("EnhancedUNet with a grad_sink (data-parallel) needs gradients cleared before backward "
+                                   "(optimizer.zero_grad(set_to_none=True)); accumulation across backward passes is not "
+                                   "supported on this path")
+            p.grad = grads[n]
+        return (None, None) + (None,) * len(names)
 
 
 class EnhancedUNet(nn.Module):
@@ -88,6 +103,7 @@ class EnhancedUNet(nn.Module):
             nn.Conv2d(num_classes, 64, 3, padding=1), nn.BatchNorm2d(64), nn.ReLU(inplace=True), nn.Conv2d(64, num_classes, 1))
         self._aux_outputs = None
         self._packs = engine.PackCache()
+        self.grad_sink = None   # parallel.FlatGradBuffer when gradients are exchanged across ranks (parallel.GradientAllReduce)
         self._param_names = [n for n, _ in self.named_parameters()]
 
     # -- helpers ---------------------------------------------------------------------------------

@@ -27,61 +27,107 @@ def broadcast_parameters(tensors: Iterable[torch.Tensor], src: int = 0, group=No
         dist.broadcast(t.data if isinstance(t, torch.nn.Parameter) else t, src, group=group)
 
 
-class GradientAllReduce:
-    """Bucketed SUM all-reduce of ``.grad`` over flat fp32 buffers.
+class FlatGradBuffer:
+    """ONE flat fp32 gradient buffer laid out in the order backward FINISHES gradients
+    (``engine.grad_production_order()``: tail, dec2, dec3, dec4, enc4 ... enc1), cut into buckets of at most
+    ``bucket_bytes`` at parameter boundaries.  It is the ``engine.GradSink`` of the data-parallel path: the backward
+    kernels write every gradient straight into its slice (``dst``), and ``ready`` launches the asynchronous SUM
+    all-reduce of a bucket the moment its last gradient has been enqueued - NCCL runs it on its own stream behind
+    an event, so the exchange overlaps the rest of backward (the level-0/1 encoder blocks, i.e. most of its time).
+    ``.grad`` of every parameter is a view of the buffer; ``wait()`` joins the exchange before the optimiser step
+    (averaging is folded into ``ClippedAdamW.step(grad_scale=1/world)``).
 
-    Buckets follow REVERSE parameter order (the order backward produces gradients: tail, dec2, dec3, dec4,
-    enc4 ... enc1) and are capped at ``bucket_bytes`` (payload is 31 MB in total, i.e. latency-bound: a few
-    large buckets).  ``reduce()`` launches every bucket asynchronously and ``wait()`` copies the
-    sums back into ``.grad``; averaging is folded into the optimiser (``ClippedAdamW.step(grad_scale=1/world)``).
-    """
+    Works on any device (gloo on CPU in the tests); holds no CUDA-specific state."""
 
-    def __init__(self, params: Sequence[torch.nn.Parameter], bucket_bytes: int = 16 << 20, group=None):
-        self.params: List[torch.nn.Parameter] = list(params)
+    def __init__(self, named_shapes: Sequence, device, bucket_bytes: int = 8 << 20, group=None):
         self.group = group
-        self.buckets: List[List[torch.nn.Parameter]] = []
-        cur: List[torch.nn.Parameter] = []
-        size = 0
-        for p in reversed(self.params):
-            nbytes = p.numel() * 4
-            if cur and size + nbytes > bucket_bytes:
-                self.buckets.append(cur)
-                cur, size = [], 0
-            cur.append(p)
-            size += nbytes
-        if cur:
-            self.buckets.append(cur)
-        self._flat: List[Optional[torch.Tensor]] = [None] * len(self.buckets)
-        self._work = []
+        self.dev = torch.device(device)
+        self.names: List[str] = [n for n, _ in named_shapes]
+        self.shapes = {n: tuple(sh) for n, sh in named_shapes}
+        self.offsets = {}
+        off = 0
+        for n, sh in named_shapes:
+            self.offsets[n] = off
+            off += int(torch.Size(sh).numel())
+        self.numel = off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=self.dev)
+        self.grads = {n: self.flat[self.offsets[n]:self.offsets[n] + torch.Size(self.shapes[n]).numel()].view(self.shapes[n])
+                      for n in self.names}
+        # buckets: contiguous [lo, hi) element ranges closed by the parameter named in ``_closes``
+        self.buckets: List[tuple] = []
+        self._closes = {}
+        lo = 0
+        for i, n in enumerate(self.names):
+            hi = self.offsets[n] + torch.Size(self.shapes[n]).numel()
+            nxt = self.names[i + 1] if i + 1 < len(self.names) else None
+            nxt_hi = (self.offsets[nxt] + torch.Size(self.shapes[nxt]).numel()) if nxt else None
+            if nxt is None or (nxt_hi - lo) * 4 > bucket_bytes:
+                self._closes[n] = len(self.buckets)
+                self.buckets.append((lo, hi))
+                lo = hi
+        self._work: List = []
+        self._launched = 0
 
-    def reduce(self) -> None:
+    @classmethod
+    def for_model(cls, model: torch.nn.Module, bucket_bytes: int = 8 << 20, group=None) -> "FlatGradBuffer":
+        from . import engine
+        params = dict(model.named_parameters())
+        order = engine.grad_production_order()
+        if set(order) != set(params):
+            raise RuntimeError("FlatGradBuffer: the model's parameters do not match the hot path's production order")
+        dev = next(iter(params.values())).device
+        return cls([(n, params[n].shape) for n in order], dev, bucket_bytes, group)
+
+    # ---- engine.GradSink protocol ----
+    def dst(self, name: str, shape) -> torch.Tensor:
+        t = self.grads[name]
+        if tuple(t.shape) != tuple(shape):
+            raise RuntimeError(f"FlatGradBuffer: gradient of {name} has shape {tuple(shape)}, expected {tuple(t.shape)}")
+        return t
+
+    def ready(self, name: str) -> None:
+        b = self._closes.get(name)
+        if b is None:
+            return
+        if b != self._launched:
+            raise RuntimeError(f"FlatGradBuffer: bucket {b} closed out of order (expected {self._launched})")
+        self._launched += 1
         if world_size(self.group) == 1:
             return
-        self._work = []
-        for i, bucket in enumerate(self.buckets):
-            n = sum(p.numel() for p in bucket)
-            dev = bucket[0].grad.device
-            if self._flat[i] is None or self._flat[i].device != dev:
-                self._flat[i] = torch.empty(n, dtype=torch.float32, device=dev)
-            flat = self._flat[i]
-            off = 0
-            for p in bucket:
-                if p.grad is None:
-                    raise RuntimeError("GradientAllReduce: parameter without gradient")
-                flat[off:off + p.numel()].copy_(p.grad.reshape(-1))
-                off += p.numel()
-            self._work.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        lo, hi = self.buckets[b]
+        self._work.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    # ---- step protocol ----
+    def begin(self) -> None:
+        """Call before a backward pass (after the previous step's ``wait``)."""
+        if self._work:
+            raise RuntimeError("FlatGradBuffer.begin: the previous exchange was not waited for")
+        self._launched = 0
 
     def wait(self) -> None:
-        if not self._work:
-            return
-        for w, bucket, flat in zip(self._work, self.buckets, self._flat):
+        """Join every bucket's all-reduce (the current stream waits on NCCL's; no host sync on CUDA)."""
+        if self._launched not in (0, len(self.buckets)):
+            raise RuntimeError(f"FlatGradBuffer.wait: only {self._launched} of {len(self.buckets)} buckets were produced")
+        for w in self._work:
             w.wait()
-            off = 0
-            for p in bucket:
-                p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
-                off += p.numel()
         self._work = []
+
+
+class GradientAllReduce:
+    """Data-parallel gradient exchange for an ``EnhancedUNet``: attaches a ``FlatGradBuffer`` to the model so that
+    ``loss.backward()`` writes gradients into it and launches the bucket all-reduces as it goes (overlapped with the
+    remaining backward kernels).  ``wait()`` before ``optimizer.step``.  At world size 1 nothing is exchanged."""
+
+    def __init__(self, model: torch.nn.Module, bucket_bytes: int = 8 << 20, group=None):
+        self.model = model
+        self.buffer = FlatGradBuffer.for_model(model, bucket_bytes, group)
+        model.grad_sink = self.buffer
+
+    def wait(self) -> None:
+        self.buffer.wait()
+
+    def detach(self) -> None:
+        self.model.grad_sink = None
 
 
 def allreduce_counts(counts: torch.Tensor, group=None) -> torch.Tensor:

@@ -31,20 +31,35 @@ def _worker(rank, world, port, tmp):
         ref = EnhancedUNet(3)
         for a, b in zip(m.state_dict().values(), ref.state_dict().values()):
             assert torch.equal(a, b)               # everyone holds rank 0's parameters
-        params = list(m.parameters())
+        # the exchange as backward drives it: gradients are written into the flat buffer in production order and every
+        # bucket's all-reduce is launched the moment its last gradient is there
+        from enhanced_unet_b200 import engine
+        ar = parallel.GradientAllReduce(m, bucket_bytes=4 << 20)
+        buf = m.grad_sink
+        assert buf is ar.buffer and buf.numel == sum(p.numel() for p in m.parameters())
+        assert len(buf.buckets) >= 3 and buf.buckets[0][0] == 0 and buf.buckets[-1][1] == buf.numel
+        assert all(a[1] == b[0] for a, b in zip(buf.buckets, buf.buckets[1:]))          # contiguous, in order
+        assert buf.names[0].startswith("enhance.") and buf.names[-1] == "model.enc1.0.bias"   # the tail first
+        params = dict(m.named_parameters())
         g = torch.Generator().manual_seed(100 + rank)
-        for p in params:
-            p.grad = torch.randn(p.shape, generator=g)
-        mine = [p.grad.clone() for p in params]
-        ar = parallel.GradientAllReduce(params, bucket_bytes=4 << 20)
-        assert len(ar.buckets) >= 3 and sum(len(b) for b in ar.buckets) == len(params)
-        assert ar.buckets[0][0] is params[-1]       # reverse execution order: the tail first
-        ar.reduce()
-        ar.wait()
         other = torch.Generator().manual_seed(100 + (1 - rank))
-        for p, a in zip(params, mine):
-            b = torch.randn(p.shape, generator=other)
-            assert torch.allclose(p.grad, a + b, rtol=0, atol=1e-6)
+        want = {}
+        buf.begin()
+        for n in engine.grad_production_order():
+            a = torch.randn(params[n].shape, generator=g)
+            want[n] = a + torch.randn(params[n].shape, generator=other)
+            buf.dst(n, params[n].shape).copy_(a)
+            buf.ready(n)
+        buf.wait()
+        for n in buf.names:
+            assert torch.allclose(buf.grads[n], want[n], rtol=0, atol=1e-6), n
+        # a second step reuses the buffer; closing a bucket out of order is an error, not a silent wrong exchange
+        buf.begin()
+        try:
+            buf.ready(buf.names[-1])
+            raise AssertionError("out-of-order bucket was accepted")
+        except RuntimeError:
+            pass
         # metrics: each rank counts its shard; the int64 sum is the single-process result
         rng = np.random.default_rng(7)
         pred, gt = rng.integers(0, 3, (6, 16, 16)), rng.integers(0, 3, (6, 16, 16))

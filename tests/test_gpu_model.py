@@ -229,3 +229,30 @@ def test_inference_configs_masks_and_counts(shape):
     want_mask = oracle.convert_probs_to_mask(probs[0].cpu().numpy())
     assert np.array_equal(masks[0].cpu().numpy().astype(np.int64), want_mask)
     assert np.array_equal(cm[0].cpu().numpy(), oracle.confusion_counts(want_mask[None], gt[0].cpu().numpy()[None])[0])
+
+
+def test_flat_gradient_sink_matches_autograd_path():
+    """Data-parallel plumbing at world size 1: with parallel.GradientAllReduce attached, backward writes every gradient
+    into ONE flat buffer (production order) and sets .grad to views of it - the same numbers as the autograd path."""
+    import oracle
+    from enhanced_unet_b200 import parallel
+    from enhanced_unet_b200.ops import combined_loss
+    sd = oracle.make_state_dict(3)
+    x = oracle.make_input(2, 64, 64, 7).cuda()
+    t = oracle.make_target(2, 64, 64, 8).cuda()
+    m = _model("bf16", sd).train()
+    combined_loss(m(x), t).backward()
+    want = {n: p.grad.clone() for n, p in m.named_parameters()}
+    m2 = _model("bf16", sd).train()
+    ar = parallel.GradientAllReduce(m2)
+    for step in range(2):                       # the buffer is reused from step to step
+        m2.zero_grad(set_to_none=True)
+        m2.load_state_dict(sd, strict=True)     # reset the running statistics; parameters are unchanged
+        combined_loss(m2(x), t).backward()
+        ar.wait()
+        lo, hi = ar.buffer.flat.data_ptr(), ar.buffer.flat.data_ptr() + 4 * ar.buffer.numel
+        for n, p in m2.named_parameters():
+            assert p.grad is not None and lo <= p.grad.data_ptr() < hi, n
+            assert nerr(p.grad, want[n]) <= 1e-4, (step, n, nerr(p.grad, want[n]))   # atomics: summation order only
+    with pytest.raises(RuntimeError):           # accumulation over two backward passes is refused, not silently wrong
+        combined_loss(m2(x), t).backward()
