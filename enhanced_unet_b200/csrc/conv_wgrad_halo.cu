@@ -126,10 +126,156 @@ conv3x3_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
   if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// 16-channel inputs (the 3-channel layers enc1.0 / enhance.0, padded to 16): the layer is a pure stream over dY
+// (128 B per pixel against 32 B of X), so the point is to touch every dY byte once and keep many tiles in flight.
+// Roles are swapped against the kernel above: A = dY with M = 64 output channels (one 64-channel box; an M = 128
+// instruction with a zero-filled second box spends its shared-memory read cycles on zeros: 57 instead of ~30 clocks
+// per MMA, measured), B = the X halo tile, whose three taps of a filter row are three 16-channel
+// MN-major blocks one halo row (32 B) apart (LBO = 32), 8-pixel K groups 10 halo rows apart:
+//     D_dy[co, (dx, ci)] += sum_p dY[p, co] * X[p + (dy, dx), ci]        three accumulators of N = 48
+// One X box + two dY boxes per 16x8-pixel tile instead of nine tap boxes per 64 pixels (per-tap kernel).
+// ------------------------------------------------------------------------------------------------------------
+template <int STAGES>
+__global__ void __launch_bounds__(192, 1)
+conv3x3_wgrad16_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                            const WgradHaloParams p) {
+  constexpr int X_BYTES = 180 * 32, X_SLOT = 6 * 1024, D_BYTES = 128 * 128, STAGE_BYTES = X_SLOT + D_BYTES;
+  constexpr uint32_t TMEM_COLS = 256;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int t_begin = blockIdx.y * p.tiles_per_split;
+  const int t_end = min(p.tiles, t_begin + p.tiles_per_split);
+  const int kiters = t_end - t_begin;
+  if (kiters <= 0) return;
+
+  const uint32_t sbase = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int co0 = blockIdx.x * 64;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { tc::mbar_init(tc::smem_u32(&full_bar[s]), 1); tc::mbar_init(tc::smem_u32(&empty_bar[s]), 1); }
+    tc::mbar_init(tc::smem_u32(&accum_bar), 1);
+    tc::mbar_fence_init();
+    tc::tma_prefetch_desc(&tmX);
+    tc::tma_prefetch_desc(&tmDY);
+  }
+  if (warp == 1) tc::tmem_alloc(tc::smem_u32(&tmem_base_s), TMEM_COLS);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      for (int it = 0; it < kiters; ++it) {
+        const int s = it % STAGES;
+        tc::mbar_wait(tc::smem_u32(&empty_bar[s]), (((uint32_t)(it / STAGES)) & 1u) ^ 1u);
+        const uint32_t fb = tc::smem_u32(&full_bar[s]);
+        tc::mbar_expect_tx(fb, X_BYTES + D_BYTES);
+        const int t = t_begin + it;
+        const int bx = t % p.blocks_x, by = (t / p.blocks_x) % p.blocks_y, b = t / (p.blocks_x * p.blocks_y);
+        const uint32_t xs = sbase + s * STAGE_BYTES;
+        tc::tma_load_4d(xs, &tmX, fb, 0, bx * 8 - 1, by * 16 - 1, b);
+        tc::tma_load_4d(xs + X_SLOT, &tmDY, fb, co0, bx * 8, by * 16, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (tc::elect_one()) {
+      constexpr uint32_t idesc = tc::make_idesc_bf16(64, 48, 1, 1);   // both operands MN-major
+      for (int it = 0; it < kiters; ++it) {
+        const int s = it % STAGES;
+        tc::mbar_wait(tc::smem_u32(&full_bar[s]), ((uint32_t)(it / STAGES)) & 1u);
+        tc::tc_fence_after();
+        const uint32_t xs = sbase + s * STAGE_BYTES, ds = xs + X_SLOT;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {       // K = 16 pixels = output rows 2j, 2j+1 of the tile
+          const uint64_t adesc = tc::make_smem_desc(ds + j * 2048, 0, 1024, tc::kSwizzle128);
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            const uint64_t bdesc = tc::make_smem_desc(xs + (uint32_t)((dy * 10 + j * 20) * 32), 32, 10 * 32, tc::kSwizzle32);
+            tc::umma_bf16(tmem_base + dy * 48, adesc, bdesc, idesc, (it | j) != 0 ? 1u : 0u);
+          }
+        }
+        tc::umma_commit(tc::smem_u32(&empty_bar[s]));
+      }
+      tc::umma_commit(tc::smem_u32(&accum_bar));
+    }
+  } else {
+    // M = 64 accumulator layout (cta_group::1): row 16 q + l lives in TMEM lane 32 q + l, l < 16
+    const int q = warp & 3;
+    const int co = co0 + q * 16 + lane;
+    tc::mbar_wait(tc::smem_u32(&accum_bar), 0);
+    tc::tc_fence_after();
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {      // TMEM column of (dy, dx, ci) = dy * 48 + dx * 16 + ci = tap * 16 + ci
+      uint32_t raw[16];
+      tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tap * 16), raw);
+      tc::tmem_ld_wait();
+      if (lane < 16 && co < p.Cout) {
+        float* dst = p.dw + ((long long)co * 9 + tap) * 16;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) atomicAdd(dst + i, __uint_as_float(raw[i]));
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+static int conv3x3_wgrad16_halo(const void* x, int ldx, const void* dy, int lddy, float* dw, int B, int H, int W, int Cout,
+                                cudaStream_t st) {
+  constexpr int STAGES = 8;
+  constexpr int SMEM = 1024 + STAGES * (6 * 1024 + 128 * 128);
+  WgradHaloParams p;
+  p.dw = dw; p.B = B; p.H = H; p.W = W; p.Cin = 16; p.Cout = Cout;
+  p.blocks_x = (W + 7) / 8;
+  p.blocks_y = (H + 15) / 16;
+  const long long tiles = (long long)p.blocks_x * p.blocks_y * B;
+  if (tiles > 0x7fffffffLL) return 1;
+  p.tiles = (int)tiles;
+  p.ci_chunks = 1;
+  p.debug_skip_store = 0;
+  const int co_tiles = (Cout + 63) / 64;
+  int splits = kNumSMs / co_tiles;          // one CTA per SM (177 KB of stages each)
+  if (splits > p.tiles) splits = p.tiles;
+  if (splits < 1) splits = 1;
+  p.tiles_per_split = (p.tiles + splits - 1) / splits;
+  splits = (p.tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  CUtensorMap tmX, tmDY;
+  {
+    uint64_t dims[4] = {16ull, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)ldx * 2, (uint64_t)ldx * 2 * W, (uint64_t)ldx * 2 * W * H};
+    uint32_t box[4] = {16u, 10u, 18u, 1u};
+    if (tc::encode_tensor_map_bf16(&tmX, x, 4, dims, str, box, 32)) return -1;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)lddy * 2, (uint64_t)lddy * 2 * W, (uint64_t)lddy * 2 * W * H};
+    uint32_t box[4] = {64u, 8u, 16u, 1u};
+    if (tc::encode_tensor_map_bf16(&tmDY, dy, 4, dims, str, box, 128)) return -1;
+  }
+  auto kern = conv3x3_wgrad16_halo_kernel<STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    EUNET_REQUIRE(e == cudaSuccess, "conv3x3_wgrad16_halo: cudaFuncSetAttribute(%d): %s", SMEM, cudaGetErrorString(e));
+    configured = true;
+  }
+  dim3 grid((unsigned)co_tiles, (unsigned)splits);
+  kern<<<grid, 192, SMEM, st>>>(tmX, tmDY, p);
+  return check_launch("conv3x3_wgrad16_halo");
+}
+
 // returns 0 = launched, 1 = shape not covered, < 0 = error
 int conv3x3_wgrad_halo_bf16(const void* x, int ldx, const void* dy, int lddy, float* dw, int B, int H, int W, int Cin, int Cout,
                             cudaStream_t st) {
-  if (Cin % 64 != 0 || H < 8 || W < 8) return 1;
+  if (H < 8 || W < 8) return 1;
+  if (Cin == 16) return conv3x3_wgrad16_halo(x, ldx, dy, lddy, dw, B, H, W, Cout, st);
+  if (Cin % 64 != 0) return 1;
   // many (ci chunk, co tile) columns with few pixel tiles each: the per-tap kernel (N = 192 per MMA, fewer atomics) wins
   if (g_opt_conv_halo < 2 && (long long)Cin * Cout > 128LL * 256) return 1;
   constexpr int STAGES = 4;
