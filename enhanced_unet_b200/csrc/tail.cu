@@ -366,8 +366,8 @@ __device__ __forceinline__ void load3<__nv_bfloat16>(const __nv_bfloat16* p, flo
 }
 
 template <typename T>
-__global__ void tail_up_bwd_kernel(const T* __restrict__ dd1p, const float* __restrict__ dout, float* __restrict__ dz4, int B,
-                                   int H, int W) {
+__global__ void tail_up_bwd_kernel(const T* __restrict__ dd1p, int stride, const float* __restrict__ dout,
+                                   float* __restrict__ dz4, int B, int H, int W) {
   const int Wo = 2 * W, Ho = 2 * H;
   const long long HWo = (long long)Ho * Wo;
   for (int row = blockIdx.x; row < B * H; row += gridDim.x)
@@ -387,7 +387,7 @@ __global__ void tail_up_bwd_kernel(const T* __restrict__ dd1p, const float* __re
         const int ox = 2 * j - 1 + s;
         const long long op = (long long)b * HWo + (long long)oy * Wo + ox;
         float v[3];
-        load3<T>(dd1p + op * 16, v);
+        load3<T>(dd1p + op * stride, v);
         const float* dp = dout + (long long)b * 3 * HWo + (long long)oy * Wo + ox;
         const float wgt = wy[r] * wx[s];
         a0 += wgt * (v[0] + __ldg(dp));
@@ -506,10 +506,12 @@ int eunet_tail_bwd_dmid(const float* dout, const void* mid, void* dmid, int dtyp
   return check_launch("tail_bwd_dmid");
 }
 
-int eunet_tail_up_bwd(const void* dd1p, int dtype, const float* dout, float* dz4, int B, int H, int W, void* stream) {
+int eunet_tail_up_bwd(const void* dd1p, int dtype, int dd1_stride, const float* dout, float* dz4, int B, int H, int W,
+                      void* stream) {
   EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "tail_up_bwd: bad shape");
+  EUNET_REQUIRE(dd1_stride >= 4 && dd1_stride % 4 == 0, "tail_up_bwd: dd1_stride %d must be a multiple of 4 (>= 4)", dd1_stride);
   DISPATCH_DTYPE(dtype, tail_up_bwd_kernel<T><<<clamp_grid((long long)B * H, 16), 256, 0, (cudaStream_t)stream>>>(
-                            (const T*)dd1p, dout, dz4, B, H, W));
+                            (const T*)dd1p, dd1_stride, dout, dz4, B, H, W));
   return check_launch("tail_up_bwd");
 }
 

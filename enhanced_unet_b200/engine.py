@@ -324,10 +324,18 @@ def backward(sd: Dict[str, torch.Tensor], sv: Saved, dout: torch.Tensor, act_dty
     dwp = conv3x3_wgrad(cx, d1p, dmid, B, 2 * H, 2 * W, 16, 64)
     wgrad_into("enhance.0.weight", dwp, 64, 3)
     zero_bias("enhance.0.bias", 64)                                            # cancelled by train-mode BN
-    dd1p = cx.empty(M2x, 16)
-    conv3x3(cx, dmid, packs.get(cx, "enhance.0", sd["enhance.0.weight"], True), dd1p, B, 2 * H, 2 * W, 64, 16)
     dz4 = cx.empty(M1, 4, dtype=f32)
-    call("eunet_tail_up_bwd", ptr(dd1p), cx.code, ptr(dout), ptr(dz4), B, H, W)
+    wflip = packs.get(cx, "enhance.0", sd["enhance.0.weight"], True)
+    if cx.dt == torch.bfloat16 and 2 * H >= 8 and 2 * W >= 8:
+        # 3 real gradient channels: transposed dgrad (every dmid row read once), fp32 [pixels][4] output
+        dd1 = cx.empty(M2x, 4, dtype=f32)
+        call("eunet_conv3x3_dgrad_few", ptr(dmid), _ld(dmid), ptr(wflip), ptr(dd1), B, 2 * H, 2 * W, 64, 16,
+             flops=2.0 * M2x * 64 * 27)
+        call("eunet_tail_up_bwd", ptr(dd1), lib.F32, 4, ptr(dout), ptr(dz4), B, H, W)
+    else:
+        dd1p = cx.empty(M2x, 16)
+        conv3x3(cx, dmid, wflip, dd1p, B, 2 * H, 2 * W, 64, 16)
+        call("eunet_tail_up_bwd", ptr(dd1p), cx.code, 16, ptr(dout), ptr(dz4), B, H, W)
     acc2 = cx.zeros(200, dtype=f64)
     d2 = sv.act["d2"]
     dd2 = cx.empty(M1, 64)

@@ -32,6 +32,7 @@ SIGNATURES = {
     "eunet_pack_weight3x3": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
     "eunet_unpack_wgrad3x3": [_p, _p, _i, _i, _i, _i, _p],
     "eunet_conv3x3_fwd": [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _i, _p],
+    "eunet_conv3x3_dgrad_few": [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p],
     "eunet_conv3x3_wgrad": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p],
     "eunet_bn_finalize": [_p, _ll, _p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _i, _p],
     "eunet_bn_fold_eval": [_p, _p, _p, _p, _p, _f, _p, _p, _i, _p],
@@ -48,7 +49,7 @@ SIGNATURES = {
     "eunet_tail_out_fwd": [_p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "eunet_tail_bwd_reduce": [_p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "eunet_tail_bwd_dmid": [_p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
-    "eunet_tail_up_bwd": [_p, _i, _p, _p, _i, _i, _i, _p],
+    "eunet_tail_up_bwd": [_p, _i, _i, _p, _p, _i, _i, _i, _p],
     "eunet_tail_dec1_bwd": [_p, _p, _i, _p, _i, _i, _p, _p, _ll, _p],
     "eunet_cast_f64_f32": [_p, _p, _ll, _p],
     "eunet_loss_fwd": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p],

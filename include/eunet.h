@@ -77,6 +77,14 @@ int eunet_conv3x3_fwd(const void* x, int ldx, const void* w_packed, void* y, int
 int eunet_conv3x3_wgrad(const void* x, int ldx, const void* dy, int lddy, float* dw_packed, int dtype, int B, int H, int W,
                         int Cin, int Cout, void* stream);
 
+/* Data gradient of a 3x3 convolution with <= 3 real INPUT channels (enhance.0, models.py:309; autograd dgrad of
+ * loss.backward(), train_eval.py:338), bf16 tensor-core path only:
+ *   dx4[p][i] = sum_{tap,co} dy[p + tap - (1,1), co] * w_packed_flip[i][tap][co],  i < 3;  dx4[p][3] = 0
+ * dy: [B*H*W, 64] bf16 (row stride lddy); w_packed_flip: eunet_pack_weight3x3(..., transpose_flip = 1) output
+ * [cin_pad][9][64] bf16 (cin_pad >= 8); dx4: fp32 [B*H*W][4]. */
+int eunet_conv3x3_dgrad_few(const void* dy, int lddy, const void* w_packed_flip, float* dx4, int B, int H, int W, int Cout,
+                            int cin_pad, void* stream);
+
 /* ---- nn.BatchNorm2d (models.py:220,223,310): train-mode statistics -> affine, running stats ---- */
 int eunet_bn_finalize(const double* stats, long long count, const float* gamma, const float* beta, const float* conv_bias,
                       float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
@@ -121,8 +129,10 @@ int eunet_tail_bwd_reduce(const float* dout4, const void* mid, int dtype, const 
 int eunet_tail_bwd_dmid(const float* dout4, const void* mid, void* dmid, int dtype, const float* scale, const float* shift,
                         const float* mean, const float* invstd, const float* w3, const double* acc, int B, int H, int W,
                         void* stream);
-int eunet_tail_up_bwd(const void* dd1p /*[B,2H,2W,16]*/, int dtype, const float* dout, float* dz4, int B, int H, int W,
-                      void* stream);
+/* dd1p: gradient w.r.t. d1, `dd1_stride` elements of `dtype` per pixel of which the first 3 are read
+ * (16 = the padded conv3x3 dgrad output; 4 with dtype fp32 = eunet_conv3x3_dgrad_few's dx4) */
+int eunet_tail_up_bwd(const void* dd1p /*[B,2H,2W,dd1_stride]*/, int dtype, int dd1_stride, const float* dout, float* dz4,
+                      int B, int H, int W, void* stream);
 int eunet_tail_dec1_bwd(const float* dz4, const void* d2, int ldd2, void* dd2, int lddd2, int dtype, const float* w1,
                         double* acc /*[192 + 3]*/, long long M, void* stream);
 /* double accumulators -> fp32 parameter gradients */

@@ -291,6 +291,26 @@ def test_conv3x3_dgrad_and_wgrad(k, dtn, case):
     assert nerr(dw.cpu(), w.grad) < 2e-5     # fp32 accumulation in both modes (inputs are identical)
 
 
+@pytest.mark.parametrize("shape", [(2, 16, 24), (1, 40, 20), (3, 8, 8), (2, 128, 136), (1, 250, 64)])
+def test_conv3x3_dgrad_few_channels(k, shape):
+    """Transposed tcgen05 dgrad for a conv with 3 real input channels (enhance.0): fp32 [pixels][4] output against
+    autograd of F.conv2d on the bf16-rounded operands (fp32 accumulation in both: only summation order differs)."""
+    B, H, W = shape
+    g = torch.Generator().manual_seed(B * 1000 + H)
+    x = torch.randn(B, 3, H, W, generator=g, requires_grad=True)
+    w = rnd("bf16", torch.randn(64, 3, 3, 3, generator=g) / 5.0)
+    dy = rnd("bf16", torch.randn(B, 64, H, W, generator=g))
+    F.conv2d(x, w, None, padding=1).backward(dy)
+    dyd = nhwc(dy, torch.bfloat16, ld=64 + 8, off=8)
+    wpT = torch.empty(16, 9, 64, dtype=torch.bfloat16, device="cuda")
+    k.call("eunet_pack_weight3x3", w.cuda().data_ptr(), wpT.data_ptr(), k.BF16, 64, 3, 64, 16, 1)
+    dx4 = torch.full((B * H * W, 4), 9.0, device="cuda")
+    k.call("eunet_conv3x3_dgrad_few", dyd.data_ptr(), dyd.stride(0), wpT.data_ptr(), dx4.data_ptr(), B, H, W, 64, 16)
+    torch.cuda.synchronize()
+    assert torch.all(dx4[:, 3] == 0)
+    assert nerr(nchw(dx4[:, :3], B, H, W), x.grad) < 2e-5
+
+
 def test_pack_input_and_padded_weights(k):
     g = torch.Generator().manual_seed(4)
     x = torch.rand(2, 3, 8, 8, generator=g)
