@@ -483,6 +483,25 @@ __global__ void pack_input_kernel(const float* __restrict__ x, T* __restrict__ o
   }
 }
 
+// packed element (r, tap, k) of one filter tensor w [Co][Ci][3][3]:
+//   mode 0: out [CoPad][9][CiPad]            = w[r][k][tap]                       (forward operand)
+//   mode 1: out [CiPad][9][CoPad]            = w[k][r][8 - tap]                   (dgrad operand: transposed + flipped)
+//   mode 2: out [CoPad][9][CiPad], Ci == 3   = {w_hi, w_hi, w_lo} for the {x_hi, x_lo, x_hi} input split
+template <typename T>
+__device__ __forceinline__ T pack_weight_value(const float* __restrict__ w, int Co, int Ci, int r, int tap, int k, int mode) {
+  float v = 0.f;
+  if (mode == 0) {
+    if (r < Co && k < Ci) v = w[((long long)r * Ci + k) * 9 + tap];
+  } else if (mode == 1) {
+    if (k < Co && r < Ci) v = w[((long long)k * Ci + r) * 9 + (8 - tap)];
+  } else if (r < Co && k < 9) {
+    const float wv = w[((long long)r * Ci + k % 3) * 9 + tap];
+    const float hi = round_to<T>(wv);
+    v = k < 6 ? hi : wv - hi;
+  }
+  return from_f32<T>(v);
+}
+
 template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int Co, int Ci, int CoPad, int CiPad,
                                    int transpose_flip) {
@@ -493,17 +512,44 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
     const int k = (int)(i % inner);
     const int tap = (int)((i / inner) % 9);
     const int r = (int)(i / ((long long)inner * 9));
-    float v = 0.f;
-    if (transpose_flip == 0) {
-      if (r < Co && k < Ci) v = w[((long long)r * Ci + k) * 9 + tap];
-    } else if (transpose_flip == 1) {
-      if (k < Co && r < Ci) v = w[((long long)k * Ci + r) * 9 + (8 - tap)];
-    } else if (r < Co && k < 9) {   // mode 2 (Ci == 3): {w_hi, w_hi, w_lo} for the {x_hi, x_lo, x_hi} input split
-      const float wv = w[((long long)r * Ci + k % 3) * 9 + tap];
-      const float hi = round_to<T>(wv);
-      v = k < 6 ? hi : wv - hi;
+    out[i] = pack_weight_value<T>(w, Co, Ci, r, tap, k, transpose_flip);
+  }
+}
+
+// ONE launch packs every stale filter of the network (30 tensors per training step: forward + dgrad operand of 15
+// convolutions).  The table travels by value as a kernel parameter; work unit = 1024 packed elements of one tensor.
+constexpr int kPackMax = 32;
+constexpr int kPackChunk = 1024;
+struct PackTable {
+  const float* w[kPackMax];
+  void* out[kPackMax];
+  int co[kPackMax], ci[kPackMax], copad[kPackMax], cipad[kPackMax], mode[kPackMax];
+  int cstart[kPackMax + 1];
+  int count;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) pack_weight_multi_kernel(const __grid_constant__ PackTable t) {
+  const int total = t.cstart[t.count];
+  for (int c = blockIdx.x; c < total; c += gridDim.x) {
+    int lo = 0, hi = t.count;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (t.cstart[mid] <= c) lo = mid; else hi = mid;
     }
-    out[i] = from_f32<T>(v);
+    const int mode = t.mode[lo], Co = t.co[lo], Ci = t.ci[lo];
+    const int rows = mode == 1 ? t.cipad[lo] : t.copad[lo], inner = mode == 1 ? t.copad[lo] : t.cipad[lo];
+    const int items = rows * 9 * inner;
+    const float* w = t.w[lo];
+    T* out = reinterpret_cast<T*>(t.out[lo]);
+#pragma unroll
+    for (int u = 0; u < kPackChunk / 256; ++u) {
+      const int i = (c - t.cstart[lo]) * kPackChunk + u * 256 + threadIdx.x;
+      if (i < items) {
+        const int k = i % inner, tap = (i / inner) % 9, r = i / (inner * 9);
+        out[i] = pack_weight_value<T>(w, Co, Ci, r, tap, k, mode);
+      }
+    }
   }
 }
 
@@ -665,6 +711,27 @@ int eunet_pack_weight3x3(const float* w, void* out, int dtype, int Co, int Ci, i
   DISPATCH_DTYPE(dtype, pack_weight_kernel<T><<<ew_grid(items), 256, 0, (cudaStream_t)stream>>>(w, (T*)out, Co, Ci, CoPad,
                                                                                                  CiPad, transpose_flip));
   return check_launch("pack_weight3x3");
+}
+
+int eunet_pack_weight3x3_multi(const void* const* w, void* const* out, const int* co, const int* ci, const int* copad,
+                                const int* cipad, const int* mode, int count, int dtype, void* stream) {
+  EUNET_REQUIRE(count > 0 && count <= kPackMax, "pack_weight3x3_multi: %d tensors (max %d)", count, kPackMax);
+  PackTable t;
+  t.count = count;
+  t.cstart[0] = 0;
+  for (int i = 0; i < count; ++i) {
+    EUNET_REQUIRE(co[i] > 0 && ci[i] > 0 && copad[i] >= co[i] && cipad[i] >= ci[i] && mode[i] >= 0 && mode[i] <= 2 &&
+                      (mode[i] != 2 || (ci[i] == 3 && cipad[i] >= 9)),
+                  "pack_weight3x3_multi: bad entry %d", i);
+    const long long items = (long long)copad[i] * 9 * cipad[i];
+    EUNET_REQUIRE(items < (1LL << 30), "pack_weight3x3_multi: tensor %d too large", i);
+    t.w[i] = (const float*)w[i]; t.out[i] = out[i];
+    t.co[i] = co[i]; t.ci[i] = ci[i]; t.copad[i] = copad[i]; t.cipad[i] = cipad[i]; t.mode[i] = mode[i];
+    t.cstart[i + 1] = t.cstart[i] + (int)((items + kPackChunk - 1) / kPackChunk);
+  }
+  const int grid = clamp_grid(t.cstart[count], 16);
+  DISPATCH_DTYPE(dtype, pack_weight_multi_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(t));
+  return check_launch("pack_weight3x3_multi");
 }
 
 int eunet_unpack_wgrad3x3(const float* dw_packed, float* dw, int Co, int Ci, int CiPad, int hilo, void* stream) {

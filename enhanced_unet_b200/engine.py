@@ -62,22 +62,78 @@ class PackCache:
     def __init__(self):
         self._c: Dict[Tuple[str, int, int], Tuple[int, int, torch.Tensor]] = {}
 
-    def get(self, cx: _Ctx, name: str, w: torch.Tensor, flip: bool, hilo: bool = False) -> torch.Tensor:
-        key = (name, 2 if hilo else int(flip), cx.code)
-        ver = (w._version, w.data_ptr())
+    @staticmethod
+    def _key(cx: _Ctx, name: str, flip: bool, hilo: bool):
+        return (name, 2 if hilo else int(flip), cx.code)
+
+    def _hit(self, key, w: torch.Tensor) -> Optional[torch.Tensor]:
         hit = self._c.get(key)
-        if hit is not None and hit[0] == ver and hit[2].device == w.device:
+        if hit is not None and hit[0] == (w._version, w.data_ptr()) and hit[2].device == w.device:
             return hit[2]
+        return None
+
+    def get(self, cx: _Ctx, name: str, w: torch.Tensor, flip: bool, hilo: bool = False) -> torch.Tensor:
+        key = self._key(cx, name, flip, hilo)
+        out = self._hit(key, w)
+        if out is not None:
+            return out
         co, ci = w.shape[0], w.shape[1]
         cop, cip = _pad16(co), _pad16(ci)
         rows, inner = (cip, cop) if flip else (cop, cip)
         out = cx.empty(rows, 9, inner)
         call("eunet_pack_weight3x3", ptr(w), ptr(out), cx.code, co, ci, cop, cip, 2 if hilo else int(flip))
-        self._c[key] = (ver, 0, out)
+        self._c[key] = ((w._version, w.data_ptr()), 0, out)
         return out
+
+    def prepare(self, cx: _Ctx, sd: Dict[str, torch.Tensor], specs) -> None:
+        """Pack every stale filter of ``specs`` = [(conv name, flip, hilo)] in ONE launch (after an optimiser step all
+        30 operands of a training step are stale).  Later ``get`` calls hit the cache."""
+        import ctypes
+        todo = []
+        for name, flip, hilo in specs:
+            w = sd[name + ".weight"]
+            key = self._key(cx, name, flip, hilo)
+            if self._hit(key, w) is None:
+                co, ci = w.shape[0], w.shape[1]
+                cop, cip = _pad16(co), _pad16(ci)
+                rows, inner = (cip, cop) if flip else (cop, cip)
+                old = self._c.get(key)
+                out = old[2] if old is not None and old[2].shape == (rows, 9, inner) and old[2].device == w.device else cx.empty(rows, 9, inner)
+                todo.append((key, w, out, co, ci, cop, cip, 2 if hilo else int(flip)))
+        for i in range(0, len(todo), 32):
+            part = todo[i:i + 32]
+            n = len(part)
+            VP, IA = ctypes.c_void_p * n, ctypes.c_int * n
+            call("eunet_pack_weight3x3_multi", VP(*[t[1].data_ptr() for t in part]), VP(*[t[2].data_ptr() for t in part]),
+                 IA(*[t[3] for t in part]), IA(*[t[4] for t in part]), IA(*[t[5] for t in part]), IA(*[t[6] for t in part]),
+                 IA(*[t[7] for t in part]), n, cx.code)
+        for key, w, out, *_ in todo:
+            self._c[key] = ((w._version, w.data_ptr()), 0, out)
+
+    def invalidate(self):
+        """Parameters were updated in place behind autograd's back (optimiser kernels): every packed copy is stale, the
+        buffers are kept for the next ``prepare``."""
+        self._c = {k: (None, 0, v[2]) for k, v in self._c.items()}
 
     def clear(self):
         self._c.clear()
+
+
+def pack_specs(cx: _Ctx, train: bool):
+    """(conv, flip, hilo) of every packed filter a forward (+ backward when ``train``) pass uses."""
+    specs = []
+    for prefix, _, _ in BLOCKS:
+        first = prefix == "model.enc1"
+        specs.append((prefix + ".0", False, first and _first_layer_split(cx)))
+        specs.append((prefix + ".3", False, False))
+        if train:
+            if not first:
+                specs.append((prefix + ".0", True, False))
+            specs.append((prefix + ".3", True, False))
+    specs.append(("enhance.0", False, False))
+    if train:
+        specs.append(("enhance.0", True, False))
+    return specs
 
 
 def conv3x3(cx: _Ctx, x: torch.Tensor, wp: torch.Tensor, y: torch.Tensor, B: int, H: int, W: int, cin: int, cout: int,
@@ -89,8 +145,34 @@ def conv3x3(cx: _Ctx, x: torch.Tensor, wp: torch.Tensor, y: torch.Tensor, B: int
          ptr(shift), int(relu), out_raw, flops=2.0 * B * H * W * cout * 9 * cin)
 
 
-def conv3x3_wgrad(cx: _Ctx, x: torch.Tensor, dy: torch.Tensor, B: int, H: int, W: int, cin: int, cout: int) -> torch.Tensor:
-    dwp = cx.zeros(cout, 9, cin, dtype=torch.float32)
+class _ZeroPool:
+    """One zero-filled fp32 workspace (a single fill launch) that hands out the packed wgrad accumulators of a backward pass."""
+
+    def __init__(self, cx: _Ctx, numel: int):
+        self.buf = cx.zeros(numel, dtype=torch.float32)
+        self.off = 0
+
+    def take(self, *shape) -> torch.Tensor:
+        n = 1
+        for d in shape:
+            n *= d
+        if self.off + n > self.buf.numel():
+            raise RuntimeError("wgrad workspace exhausted")
+        t = self.buf[self.off:self.off + n].view(*shape)
+        self.off += (n + 63) // 64 * 64
+        return t
+
+
+def wgrad_workspace_numel() -> int:
+    n = 64 * 9 * 16 + 64                                       # enhance.0
+    for _, cin, cout in BLOCKS:
+        n += cout * 9 * _pad16(cin) + cout * 9 * cout + 128
+    return n
+
+
+def conv3x3_wgrad(cx: _Ctx, x: torch.Tensor, dy: torch.Tensor, B: int, H: int, W: int, cin: int, cout: int,
+                  pool: Optional[_ZeroPool] = None) -> torch.Tensor:
+    dwp = pool.take(cout, 9, cin) if pool is not None else cx.zeros(cout, 9, cin, dtype=torch.float32)
     call("eunet_conv3x3_wgrad", ptr(x), _ld(x), ptr(dy), _ld(dy), ptr(dwp), cx.code, B, H, W, cin, cout,
          flops=2.0 * B * H * W * cout * 9 * cin)
     return dwp
@@ -201,6 +283,7 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, train: bool, act_dtype
     dims = [(H, W), (H // 2, W // 2), (H // 4, W // 4), (H // 8, W // 8)]
     Ms = [B * h * w for h, w in dims]
 
+    packs.prepare(cx, sd, pack_specs(cx, train and want_saved))
     x16 = cx.empty(Ms[0], 16)
     hilo = _first_layer_split(cx)
     call("eunet_pack_input_nchw", ptr(x), ptr(x16), cx.code, B, 3, H, W, 16, int(hilo))
@@ -288,6 +371,7 @@ def backward(sd: Dict[str, torch.Tensor], sv: Saved, dout: torch.Tensor, act_dty
     if sink is None:
         sink = GradSink(dout.device)
     grads = sink.grads
+    pool = _ZeroPool(cx, wgrad_workspace_numel())
     dout = dout.contiguous().float()
 
     def cast64(name: str, src: torch.Tensor, shape) -> None:
@@ -321,7 +405,7 @@ def backward(sd: Dict[str, torch.Tensor], sv: Saved, dout: torch.Tensor, act_dty
     cast64("enhance.3.weight", acc[128:320], (3, 64, 1, 1))
     cast64("enhance.3.bias", acc[320:323], (3,))
     d1p = sv.act["d1p"]
-    dwp = conv3x3_wgrad(cx, d1p, dmid, B, 2 * H, 2 * W, 16, 64)
+    dwp = conv3x3_wgrad(cx, d1p, dmid, B, 2 * H, 2 * W, 16, 64, pool)
     wgrad_into("enhance.0.weight", dwp, 64, 3)
     zero_bias("enhance.0.bias", 64)                                            # cancelled by train-mode BN
     dz4 = cx.empty(M1, 4, dtype=f32)
@@ -362,12 +446,12 @@ def backward(sd: Dict[str, torch.Tensor], sv: Saved, dout: torch.Tensor, act_dty
         cin_p = _pad16(cin)
         xin, mid = sv.act[prefix + ".in"], sv.act[prefix + ".mid"]
         dy_b = bn_bwd(prefix + ".4", dact, M, cout)
-        wgrad_into(prefix + ".3.weight", conv3x3_wgrad(cx, mid, dy_b, B, h, w, cout, cout), cout, cout)
+        wgrad_into(prefix + ".3.weight", conv3x3_wgrad(cx, mid, dy_b, B, h, w, cout, cout, pool), cout, cout)
         zero_bias(prefix + ".3.bias", cout)
         dmid_act = cx.empty(M, cout)
         conv3x3(cx, dy_b, packs.get(cx, prefix + ".3", sd[prefix + ".3.weight"], True), dmid_act, B, h, w, cout, cout)
         dy_a = bn_bwd(prefix + ".1", dmid_act, M, cout)
-        wgrad_into(prefix + ".0.weight", conv3x3_wgrad(cx, xin, dy_a, B, h, w, cin_p, cout), cout, cin,
+        wgrad_into(prefix + ".0.weight", conv3x3_wgrad(cx, xin, dy_a, B, h, w, cin_p, cout, pool), cout, cin,
                    hilo=(prefix == "model.enc1" and _first_layer_split(cx)))
         zero_bias(prefix + ".0.bias", cout)
         if not need_dx:

@@ -64,7 +64,7 @@ class Trainer:
         self.total_epochs = max(1, total_epochs)
         self.dice_loss_weight, self.focal_loss_weight, self.tversky_loss_weight = 2.5, 2.5, 1.0   # train_eval.py:83-85
         base_lr = 4e-3                                                                             # train_eval.py:112
-        on_update = getattr(getattr(model, "_packs", None), "clear", None)
+        on_update = getattr(getattr(model, "_packs", None), "invalidate", None)
         self.optimizer = ClippedAdamW(model.parameters(), lr=base_lr, weight_decay=1e-4, betas=(0.9, 0.999), max_norm=1.0,
                                       on_update=on_update)                                         # 120 + 341
         self.warmup_epochs = max(1, min(5, self.total_epochs // 6))

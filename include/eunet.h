@@ -57,6 +57,9 @@ int eunet_pack_input_nchw(const float* x, void* out, int dtype, int B, int C, in
  * transpose_flip = 2: forward form for a hi/lo split 3-channel input: input channels {0-2, 3-5, 6-8} = {w_hi, w_hi, w_lo}. */
 int eunet_pack_weight3x3(const float* w, void* out, int dtype, int Co, int Ci, int CoPad, int CiPad, int transpose_flip,
                          void* stream);
+/* the same packing for up to 32 filter tensors in ONE launch (all arrays have `count` entries; mode = transpose_flip) */
+int eunet_pack_weight3x3_multi(const void* const* w, void* const* out, const int* co, const int* ci, const int* copad,
+                               const int* cipad, const int* mode, int count, int dtype, void* stream);
 /* dw_packed [Co][9][CiPad] fp32 -> dw [Co,Ci,3,3] fp32 (layout of nn.Conv2d.weight.grad); hilo: sum the x_hi / x_lo channels */
 int eunet_unpack_wgrad3x3(const float* dw_packed, float* dw, int Co, int Ci, int CiPad, int hilo, void* stream);
 

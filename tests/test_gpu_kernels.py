@@ -311,6 +311,31 @@ def test_conv3x3_dgrad_few_channels(k, shape):
     assert nerr(nchw(dx4[:, :3], B, H, W), x.grad) < 2e-5
 
 
+@pytest.mark.parametrize("dtn", ["fp32", "bf16"])
+def test_pack_weight_multi_matches_single(k, dtn):
+    import ctypes
+    dt = DT[dtn]
+    g = torch.Generator().manual_seed(11)
+    entries = [(64, 3, 2), (64, 64, 0), (64, 64, 1), (128, 64, 0), (256, 768, 1), (64, 3, 1), (64, 192, 0)]   # (Co, Ci, mode)
+    ws, outs, want = [], [], []
+    for co, ci, mode in entries:
+        w = torch.randn(co, ci, 3, 3, generator=g).cuda()
+        cop, cip = (co + 15) // 16 * 16, (ci + 15) // 16 * 16
+        rows, inner = (cip, cop) if mode == 1 else (cop, cip)
+        single = torch.empty(rows, 9, inner, dtype=dt, device="cuda")
+        k.call("eunet_pack_weight3x3", w.data_ptr(), single.data_ptr(), k.dtype_code(dt), co, ci, cop, cip, mode)
+        ws.append(w); want.append(single)
+        outs.append(torch.full((rows, 9, inner), 3.0, dtype=dt, device="cuda"))
+    n = len(entries)
+    VP, IA = ctypes.c_void_p * n, ctypes.c_int * n
+    pad = lambda c: (c + 15) // 16 * 16
+    k.call("eunet_pack_weight3x3_multi", VP(*[w.data_ptr() for w in ws]), VP(*[o.data_ptr() for o in outs]),
+           IA(*[e[0] for e in entries]), IA(*[e[1] for e in entries]), IA(*[pad(e[0]) for e in entries]),
+           IA(*[pad(e[1]) for e in entries]), IA(*[e[2] for e in entries]), n, k.dtype_code(dt))
+    for o, wnt, e in zip(outs, want, entries):
+        assert torch.equal(o, wnt), e
+
+
 def test_pack_input_and_padded_weights(k):
     g = torch.Generator().manual_seed(4)
     x = torch.rand(2, 3, 8, 8, generator=g)
