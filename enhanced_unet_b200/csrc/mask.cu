@@ -118,6 +118,45 @@ static inline dim3 img_grid(long long HW, int B) {
 
 using namespace eunet;
 
+namespace eunet {
+// F.interpolate(mode='bilinear', align_corners=False, antialias=False) on planar fp32 [planes][Hin][Win] -> [planes][Hout][Wout]
+// (the multi-scale views of Evaluator._run_tta_inference, train_eval.py:441-451).  ATen's source-index rule:
+// src = ratio * (dst + 0.5) - 0.5, clamped at 0; i0 = (int)src, i1 = i0 + (i0 < in - 1), lambda = src - i0.
+__global__ void __launch_bounds__(256)
+resize_bilinear_kernel(const float* __restrict__ src, float* __restrict__ dst, int Hin, int Win, int Hout, int Wout, float rh,
+                       float rw) {
+  const long long plane = blockIdx.y;
+  const float* s = src + plane * (long long)Hin * Win;
+  float* d = dst + plane * (long long)Hout * Wout;
+  const long long n = (long long)Hout * Wout;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int oy = (int)(i / Wout), ox = (int)(i % Wout);
+    float sy = rh * (oy + 0.5f) - 0.5f, sx = rw * (ox + 0.5f) - 0.5f;
+    sy = sy < 0.f ? 0.f : sy;
+    sx = sx < 0.f ? 0.f : sx;
+    int y0 = (int)sy, x0 = (int)sx;
+    y0 = y0 < Hin - 1 ? y0 : Hin - 1;
+    x0 = x0 < Win - 1 ? x0 : Win - 1;
+    const int y1 = y0 + (y0 < Hin - 1 ? 1 : 0), x1 = x0 + (x0 < Win - 1 ? 1 : 0);
+    const float ly = sy - (float)y0, lx = sx - (float)x0;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const float v00 = __ldg(s + (long long)y0 * Win + x0), v01 = __ldg(s + (long long)y0 * Win + x1);
+    const float v10 = __ldg(s + (long long)y1 * Win + x0), v11 = __ldg(s + (long long)y1 * Win + x1);
+    d[i] = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+  }
+}
+}  // namespace eunet
+
+extern "C" int eunet_resize_bilinear(const float* src, float* dst, int planes, int Hin, int Win, int Hout, int Wout, float ratio_h,
+                                     float ratio_w, void* stream) {
+  using namespace eunet;
+  EUNET_REQUIRE(planes > 0 && planes <= 65535 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0, "resize_bilinear: bad shape");
+  EUNET_REQUIRE(ratio_h > 0.f && ratio_w > 0.f, "resize_bilinear: ratios must be positive");
+  const dim3 grid = img_grid((long long)Hout * Wout, planes);
+  resize_bilinear_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst, Hin, Win, Hout, Wout, ratio_h, ratio_w);
+  return check_launch("resize_bilinear");
+}
+
 extern "C" int eunet_softmax_probs(const float* logits, float* probs, int B, int H, int W, int logits_scale, void* stream) {
   EUNET_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, "softmax_probs: bad shape");
   EUNET_REQUIRE(logits_scale == 1 || logits_scale == 2, "softmax_probs: logits_scale must be 1 or 2");

@@ -133,3 +133,103 @@ extern "C" int eunet_confusion4x4(const void* pred, const void* gt, int elem_byt
     confusion_kernel<unsigned char><<<grid, 256, 0, st>>>((const unsigned char*)pred, (const unsigned char*)gt, px_per_image, c);
   return check_launch("confusion4x4");
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Instance matching support (reference metrics.py:61-194, calculate_instance_metrics): the reference evaluates
+// calculate_iou(pred_mask, gt_mask) - two full-image logical passes - for every (prediction, ground truth) pair.
+// Here every mask is packed ONCE into a bit plane and all |P| x |G| intersection counts come from AND + popcount
+// over the bit planes ("binary GEMM"); unions follow from the areas (U = A_p + A_g - I).  Integer work: bit-exact.
+// ------------------------------------------------------------------------------------------------------------
+namespace eunet {
+
+// masks [n][hw] uint8 (non-zero = member) -> bits [n][words] (bit i of word w = pixel 32 w + i), area [n]
+__global__ void __launch_bounds__(256) pack_mask_bits_kernel(const unsigned char* __restrict__ masks, long long hw, long long words,
+                                                             unsigned int* __restrict__ bits, unsigned long long* __restrict__ area) {
+  const long long img = blockIdx.y;
+  const unsigned char* m = masks + img * hw;
+  unsigned long long cnt = 0;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long w = warp0; w < words; w += nwarps) {
+    const long long px = w * 32 + lane;
+    const bool on = px < hw && m[px] != 0;
+    const unsigned int word = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) {
+      bits[img * words + w] = word;
+      cnt += __popc(word);
+    }
+  }
+  if (lane == 0 && cnt) atomicAdd(&area[img], cnt);
+}
+
+// inter[p][g] += popc(a[p][w] & b[g][w]) over this block's word range.  Block = 8 x 8 pairs x 4 word lanes.
+constexpr int kPairChunk = 512;   // words per block iteration (2 KB per mask row)
+__global__ void __launch_bounds__(256) pair_intersections_kernel(const unsigned int* __restrict__ a, int na,
+                                                                 const unsigned int* __restrict__ b, int nb, long long words,
+                                                                 unsigned long long* __restrict__ inter) {
+  __shared__ unsigned int sa[8][kPairChunk], sb[8][kPairChunk];
+  const int pa0 = blockIdx.x * 8, pb0 = blockIdx.y * 8;
+  const int pair = threadIdx.x >> 2, wl = threadIdx.x & 3;
+  const int ia = pair >> 3, ib = pair & 7;
+  unsigned long long cnt = 0;
+  for (long long w0 = (long long)blockIdx.z * kPairChunk; w0 < words; w0 += (long long)gridDim.z * kPairChunk) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 8 * kPairChunk; i += 256) {
+      const int r = i / kPairChunk, c = i % kPairChunk;
+      const long long w = w0 + c;
+      sa[r][c] = (pa0 + r < na && w < words) ? a[(long long)(pa0 + r) * words + w] : 0u;
+      sb[r][c] = (pb0 + r < nb && w < words) ? b[(long long)(pb0 + r) * words + w] : 0u;
+    }
+    __syncthreads();
+    unsigned int c32 = 0;
+#pragma unroll 8
+    for (int c = wl; c < kPairChunk; c += 4) c32 += __popc(sa[ia][c] & sb[ib][c]);
+    cnt += c32;
+  }
+  cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+  cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+  if (wl == 0 && cnt && pa0 + ia < na && pb0 + ib < nb) atomicAdd(&inter[(long long)(pa0 + ia) * nb + pb0 + ib], cnt);
+}
+
+}  // namespace eunet
+
+extern "C" int eunet_pack_mask_bits(const unsigned char* masks, int n, long long hw, unsigned int* bits, long long* area,
+                                    void* stream) {
+  using namespace eunet;
+  EUNET_REQUIRE(n >= 0 && hw >= 0, "pack_mask_bits: negative sizes");
+  if (n == 0) return 0;
+  EUNET_REQUIRE(n <= 65535, "pack_mask_bits: at most 65535 masks per call (got %d)", n);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(area, 0, sizeof(long long) * n, st);
+  EUNET_REQUIRE(e == cudaSuccess, "pack_mask_bits: memset: %s", cudaGetErrorString(e));
+  const long long words = (hw + 31) / 32;
+  if (words == 0) return 0;
+  long long bx = (words + 7) / 8;                      // 8 warps per block, one word per warp and iteration
+  const long long cap = ((long long)kNumSMs * 8 + n - 1) / n;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  dim3 grid((unsigned)bx, (unsigned)n);
+  pack_mask_bits_kernel<<<grid, 256, 0, st>>>(masks, hw, words, bits, reinterpret_cast<unsigned long long*>(area));
+  return check_launch("pack_mask_bits");
+}
+
+extern "C" int eunet_pair_intersections(const unsigned int* a_bits, int na, const unsigned int* b_bits, int nb, long long words,
+                                        long long* inter, void* stream) {
+  using namespace eunet;
+  EUNET_REQUIRE(na >= 0 && nb >= 0 && words >= 0, "pair_intersections: negative sizes");
+  if (na == 0 || nb == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(inter, 0, sizeof(long long) * (size_t)na * nb, st);
+  EUNET_REQUIRE(e == cudaSuccess, "pair_intersections: memset: %s", cudaGetErrorString(e));
+  if (words == 0) return 0;
+  const int gx = (na + 7) / 8, gy = (nb + 7) / 8;
+  EUNET_REQUIRE(gy <= 65535, "pair_intersections: too many masks (%d)", nb);
+  long long gz = (words + kPairChunk - 1) / kPairChunk;
+  const long long cap = ((long long)kNumSMs * 4 + (long long)gx * gy - 1) / ((long long)gx * gy);
+  if (gz > cap) gz = cap;
+  if (gz < 1) gz = 1;
+  if (gz > 65535) gz = 65535;
+  dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)gz);
+  pair_intersections_kernel<<<grid, 256, 0, st>>>(a_bits, na, b_bits, nb, words, reinterpret_cast<unsigned long long*>(inter));
+  return check_launch("pair_intersections");
+}

@@ -28,6 +28,8 @@ SIGNATURES = {
     "eunet_device_info": [_p, _p, _p, _p],
     "eunet_set_option": [C.c_char_p, _i],
     "eunet_confusion4x4": [_p, _p, _i, _ll, _ll, _p, _p],
+    "eunet_pack_mask_bits": [_p, _i, _ll, _p, _p, _p],
+    "eunet_pair_intersections": [_p, _i, _p, _i, _ll, _p, _p],
     "eunet_pack_input_nchw": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "eunet_pack_weight3x3": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
     "eunet_pack_weight3x3_multi": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
@@ -55,6 +57,7 @@ SIGNATURES = {
     "eunet_cast_f64_f32": [_p, _p, _ll, _p],
     "eunet_loss_fwd": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p],
     "eunet_loss_bwd": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p],
+    "eunet_resize_bilinear": [_p, _p, _i, _i, _i, _i, _i, _f, _f, _p],
     "eunet_softmax_probs": [_p, _p, _i, _i, _i, _i, _p],
     "eunet_probs_to_mask": [_p, _p, _p, _i, _i, _i, _p],
     "eunet_fusion_gate_fwd": [_p, _p, _p, _p, _i, _p, _i, _i, _i, _p],

@@ -79,3 +79,34 @@ def combined_loss(logits: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     if not logits.is_cuda:
         raise RuntimeError("combined_loss needs CUDA tensors (no CPU fallback)")
     return _CombinedLoss.apply(logits, target)
+
+
+def pair_intersections(a: torch.Tensor, b: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """All pairwise intersection counts of two sets of membership masks (reference metrics.py:95-101 evaluates
+    ``calculate_iou`` per pair on the host).  ``a`` [P, ...], ``b`` [G, ...]: CUDA uint8/bool masks of the same
+    per-mask shape (non-zero = member).  Returns int64 (inter [P,G], area_a [P], area_b [G]); bit-exact."""
+    if not (a.is_cuda and b.is_cuda):
+        raise RuntimeError("pair_intersections needs CUDA tensors (no CPU fallback)")
+    if a.shape[1:] != b.shape[1:]:
+        raise RuntimeError(f"mask shapes differ: {tuple(a.shape[1:])} vs {tuple(b.shape[1:])}")
+    P, G = a.shape[0], b.shape[0]
+    hw = a[0].numel() if P else (b[0].numel() if G else 0)
+    words = (hw + 31) // 32
+    dev = a.device
+    out = torch.zeros(P, G, device=dev, dtype=torch.int64)
+    areas = []
+    bits = []
+    for m, n in ((a, P), (b, G)):
+        m = (m != 0).to(torch.uint8).contiguous() if m.dtype != torch.uint8 else m.contiguous()
+        bt = torch.empty(n, words, device=dev, dtype=torch.int32)
+        ar = torch.zeros(n, device=dev, dtype=torch.int64)
+        done = 0
+        while done < n:
+            k = min(65535, n - done)
+            call("eunet_pack_mask_bits", m[done:].data_ptr(), k, hw, bt[done:].data_ptr(), ar[done:].data_ptr())
+            done += k
+        bits.append(bt)
+        areas.append(ar)
+    if P and G:
+        call("eunet_pair_intersections", bits[0].data_ptr(), P, bits[1].data_ptr(), G, words, out.data_ptr())
+    return out, areas[0], areas[1]

@@ -135,12 +135,52 @@ class Evaluator:
     def _run_model_single(self, image: torch.Tensor) -> torch.Tensor:
         return self._run_model_batch(image.unsqueeze(0))[0]
 
+    @staticmethod
+    def _resize(x: torch.Tensor, size=None, scale_factor: float = None) -> torch.Tensor:
+        """``F.interpolate(x, size= | scale_factor=, mode='bilinear', align_corners=False)`` for [B,C,h,w] fp32 on the
+        resize kernel, with ATen's output-size (floor(in * scale)) and source-ratio conventions."""
+        import math
+        b, c, h, w = x.shape
+        if scale_factor is not None:
+            ho, wo = int(math.floor(h * scale_factor)), int(math.floor(w * scale_factor))
+            ratio = float(np.float32(1.0 / scale_factor))
+            rh = rw = ratio
+        else:
+            ho, wo = size
+            rh, rw = float(np.float32(h) / np.float32(ho)), float(np.float32(w) / np.float32(wo))
+        x = x.contiguous().float()
+        out = torch.empty(b, c, ho, wo, device=x.device, dtype=torch.float32)
+        done = 0
+        xs, os_ = x.view(b * c, h, w), out.view(b * c, ho, wo)
+        while done < b * c:
+            k = min(65535, b * c - done)
+            call("eunet_resize_bilinear", ptr(xs[done:]), ptr(os_[done:]), k, h, w, ho, wo, rh, rw)
+            done += k
+        return out
+
+    @torch.no_grad()
+    def _run_tta_batch(self, images: torch.Tensor) -> torch.Tensor:
+        """Reference _run_tta_inference (train_eval.py:419-453) for a batch: mean of the base view, the horizontal and
+        vertical flips (index remaps) and the 0.75x / 1.25x bilinear views resized back to the input size."""
+        images = images.to(self.device)
+        h, w = images.shape[-2:]
+        p = self._run_model_batch(images)
+        p = p + self._run_model_batch(images.flip(-1)).flip(-1)
+        p = p + self._run_model_batch(images.flip(-2)).flip(-2)
+        for scale in (0.75, 1.25):
+            scaled = self._resize(images, scale_factor=scale)
+            p = p + self._resize(self._run_model_batch(scaled), size=(h, w))
+        return p / 5.0
+
+    def _run_tta_inference(self, image: torch.Tensor) -> torch.Tensor:
+        """Single-image form with the reference's signature ([3,h,w] -> [3,h,w] probabilities)."""
+        if not self.tta:
+            return self._run_model_single(image)
+        return self._run_tta_batch(image.unsqueeze(0))[0]
+
     @torch.no_grad()
     def _probs(self, images: torch.Tensor) -> torch.Tensor:
-        p = self._run_model_batch(images)
-        if self.tta:   # the exact-index-remap views of _run_tta_inference (419-453): horizontal and vertical flips
-            p = p + self._run_model_batch(images.flip(-1)).flip(-1) + self._run_model_batch(images.flip(-2)).flip(-2)
-            p = p / 3.0
+        p = self._run_tta_batch(images) if self.tta else self._run_model_batch(images)
         return p.contiguous()
 
     @torch.no_grad()

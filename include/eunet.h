@@ -45,6 +45,13 @@ int eunet_set_option(const char* name, int value);
 int eunet_confusion4x4(const void* pred, const void* gt, int elem_bytes, long long n_images, long long px_per_image,
                        long long* counts /* [n_images][4][4], overwritten */, void* stream);
 
+/* ---- instance matching support (metrics.py:61-194 calculate_instance_metrics; IoU of every prediction / ground-truth
+ * pair, metrics.py:95-101): masks [n][hw] uint8 (non-zero = member) -> bit planes [n][(hw+31)/32] + areas [n] (int64);
+ * inter[p][g] = |a_p AND b_g| for all pairs from the bit planes.  Integer, bit-exact. */
+int eunet_pack_mask_bits(const unsigned char* masks, int n, long long hw, unsigned int* bits, long long* area, void* stream);
+int eunet_pair_intersections(const unsigned int* a_bits, int na, const unsigned int* b_bits, int nb, long long words,
+                             long long* inter /*[na][nb]*/, void* stream);
+
 /* ---- layout / parameter packing (host glue of models.py:227-238: NCHW fp32 tensors at the boundary) ---- */
 /* x [B,C,H,W] fp32 -> NHWC with Cpad channels (zero padded), dtype.
  * split_hilo (C == 3): channels {0-2, 3-5, 6-8} = {hi, lo, hi} with hi = dtype(x), lo = dtype(x - hi); together with
@@ -153,6 +160,11 @@ int eunet_loss_bwd(const float* logits, const long long* target, int B, int H, i
  * Evaluator._convert_probs_to_mask train_eval.py:455-568) ---- */
 /* probs[b,c,h,w] = softmax_c(resize(logits)); logits_scale 2: logits are [B,3,2H,2W] and are 2x2-averaged first */
 int eunet_softmax_probs(const float* logits, float* probs /*[B,3,H,W]*/, int B, int H, int W, int logits_scale, void* stream);
+/* F.interpolate(mode='bilinear', align_corners=False) on planar fp32 [planes][Hin][Win] -> [planes][Hout][Wout]: the
+ * 0.75x / 1.25x views of Evaluator._run_tta_inference (train_eval.py:441-451).  ratio = source step per destination pixel
+ * exactly as ATen forms it: (float)(1.0 / scale_factor) when a scale factor was given, (float)in / out for size=. */
+int eunet_resize_bilinear(const float* src, float* dst, int planes, int Hin, int Win, int Hout, int Wout, float ratio_h,
+                          float ratio_w, void* stream);
 /* argmax + threshold cascade + the two global pixel-ratio filters, per image; mask uint8 [B,H,W];
  * counts int32 [B][2] = (live, dead) pixel counts after the cascade and before the ratio filters (overwritten) */
 int eunet_probs_to_mask(const float* probs, unsigned char* mask, int* counts, int B, int H, int W, void* stream);

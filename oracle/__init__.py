@@ -30,4 +30,7 @@ from .metrics_oracle import (  # noqa: F401
     calculate_semantic_metrics,
     metrics_from_counts,
     convert_probs_to_mask,
+    calculate_instance_metrics,
+    make_instance_case,
+    INSTANCE_CASES,
 )

@@ -201,17 +201,64 @@ def fusion_case(ref_models):
     print("fusion ysum", y.sum().item())
 
 
+def instances_case(ref_metrics):
+    """metrics.calculate_instance_metrics (metrics.py:61-194) on seeded synthetic instance sets."""
+    from .metrics_oracle import INSTANCE_CASES, make_instance_case
+    out = {}
+    for name, spec in INSTANCE_CASES.items():
+        pm, pl, ps, gm, gl = make_instance_case(*spec)
+        m = ref_metrics.calculate_instance_metrics(pm, pl, ps, gm, gl)
+        keys = sorted(m.keys())
+        out[f"{name}/keys"] = np.array(keys)
+        out[f"{name}/values"] = np.array([float(m[k]) for k in keys], dtype=np.float64)
+        print("instances", name, {k: round(float(m[k]), 4) for k in keys})
+    np.savez_compressed(os.path.join(OUT, "instances.npz"), **out)
+
+
+def tta_case(ref_te, ref_models):
+    """Evaluator._run_tta_inference (train_eval.py:419-453): 5 views incl. the 0.75x / 1.25x bilinear rescales."""
+    model = _ref_model(ref_models, make_state_dict(0)).eval()
+    ev = ref_te.Evaluator(model, torch.device("cpu"), "enhanced_unet")
+    assert ev.enable_tta
+    out = {}
+    for name, (h, w, seed) in {"48x40": (48, 40, 21), "64x64": (64, 64, 22)}.items():
+        img = make_input(1, h, w, seed)[0]
+        with torch.no_grad():
+            base = ev._run_model_single(img)
+            tta = ev._run_tta_inference(img)
+        out[f"{name}/meta"] = np.array([h, w, seed])
+        out[f"{name}/base"] = base.numpy()
+        out[f"{name}/tta"] = tta.numpy()
+        print("tta", name, float(tta.sum()), float((tta - base).abs().max()))
+    np.savez_compressed(os.path.join(OUT, "tta.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     ref_models, ref_metrics, ref_te = ref_import.load()
-    model_case(ref_models, ref_te, "b2_32x32", 2, 32, 32, 0, 1, 2)
-    model_case(ref_models, ref_te, "b1_16x24", 1, 16, 24, 3, 4, 5)
-    model_case(ref_models, ref_te, "b2_64x64", 2, 64, 64, 6, 7, 8)
-    loss_case(ref_te, ref_models)
-    metrics_case(ref_metrics)
-    mask_case(ref_te, ref_models)
-    fusion_case(ref_models)
+    import sys
+    only = set(sys.argv[1:])          # e.g. ``python -m oracle.make_golden instances tta`` regenerates just those fixtures
+
+    def want(name):
+        return not only or name in only
+
+    if want("model"):
+        model_case(ref_models, ref_te, "b2_32x32", 2, 32, 32, 0, 1, 2)
+        model_case(ref_models, ref_te, "b1_16x24", 1, 16, 24, 3, 4, 5)
+        model_case(ref_models, ref_te, "b2_64x64", 2, 64, 64, 6, 7, 8)
+    if want("loss"):
+        loss_case(ref_te, ref_models)
+    if want("metrics"):
+        metrics_case(ref_metrics)
+    if want("mask"):
+        mask_case(ref_te, ref_models)
+    if want("fusion"):
+        fusion_case(ref_models)
+    if want("instances"):
+        instances_case(ref_metrics)
+    if want("tta"):
+        tta_case(ref_te, ref_models)
 
 
 if __name__ == "__main__":

@@ -121,3 +121,68 @@ def convert_probs_to_mask(probs: np.ndarray) -> np.ndarray:
             keep = (dead > f(0.55)) & (dead > bg * f(1.4)) & (bg < f(0.25))
         pred[dm & (~keep)] = 0
     return pred
+
+
+def calculate_instance_metrics(pred_masks, pred_labels, pred_scores, gt_masks, gt_labels, iou_threshold: float = 0.05) -> Dict:
+    """metrics.py:61-194, restated literally (per class: score-ordered greedy matching on calculate_iou, mean IoU of the
+    matches - or of all best IoUs when nothing matched -, precision, recall, precision*recall as "AP")."""
+    metrics: Dict = {"live_iou": 0.0, "live_precision": 0.0, "live_recall": 0.0, "live_ap": 0.0,
+                     "dead_iou": 0.0, "dead_precision": 0.0, "dead_recall": 0.0, "dead_ap": 0.0}
+    for label, name in ((0, "live"), (1, "dead")):
+        pred = [(m, s) for m, l, s in zip(pred_masks, pred_labels, pred_scores) if l == label]
+        gt = [m for m, l in zip(gt_masks, gt_labels) if l == label]
+        if len(gt) == 0:
+            continue
+        ious, all_ious, matched_gt = [], [], set()
+        for pm, _score in sorted(pred, key=lambda x: x[1], reverse=True):
+            best_iou, best_idx = 0.0, -1
+            for i, gm in enumerate(gt):
+                if i in matched_gt:
+                    continue
+                iou = calculate_iou(pm, gm)
+                if iou > best_iou:
+                    best_iou, best_idx = iou, i
+            all_ious.append(best_iou)
+            if best_iou >= iou_threshold and best_idx >= 0:
+                ious.append(best_iou)
+                matched_gt.add(best_idx)
+        metrics[f"{name}_iou"] = np.mean(ious) if ious else (np.mean(all_ious) if all_ious else 0.0)
+        metrics[f"{name}_precision"] = len(ious) / len(pred) if pred else 0.0
+        metrics[f"{name}_recall"] = len(ious) / len(gt) if gt else 0.0
+        if metrics[f"{name}_precision"] == 0.0 and metrics[f"{name}_iou"] > 0.0 and pred:
+            avg = np.mean(all_ious) if all_ious else 0.0
+            if not avg < 0.1:
+                metrics[f"{name}_avg_iou_below_threshold"] = avg
+        if pred:
+            metrics[f"{name}_ap"] = metrics[f"{name}_precision"] * metrics[f"{name}_recall"]
+    return metrics
+
+
+def make_instance_case(seed: int, h: int, w: int, n_gt: int, n_pred: int):
+    """Seeded synthetic instance set: random discs as ground truth, jittered / spurious discs as predictions."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+
+    def disc(cy, cx, r):
+        return ((yy - cy) ** 2 + (xx - cx) ** 2 <= r * r).astype(np.uint8)
+
+    gts = [(rng.uniform(0, h), rng.uniform(0, w), rng.uniform(2, 7), int(rng.integers(0, 2))) for _ in range(n_gt)]
+    gt_masks = [disc(cy, cx, r) for cy, cx, r, _ in gts]
+    gt_labels = [l for *_, l in gts]
+    pred_masks, pred_labels, pred_scores = [], [], []
+    for _ in range(n_pred):
+        if gts and rng.random() < 0.7:
+            cy, cx, r, l = gts[int(rng.integers(0, len(gts)))]
+            cy, cx, r = cy + rng.normal(0, 1.5), cx + rng.normal(0, 1.5), max(1.0, r + rng.normal(0, 1.0))
+            if rng.random() < 0.15:
+                l = 1 - l
+        else:
+            cy, cx, r, l = rng.uniform(0, h), rng.uniform(0, w), rng.uniform(1, 6), int(rng.integers(0, 2))
+        pred_masks.append(disc(cy, cx, r))
+        pred_labels.append(int(l))
+        pred_scores.append(float(np.round(rng.uniform(0.2, 1.0), 2)))      # rounded: ties exercise the stable sort
+    return pred_masks, pred_labels, pred_scores, gt_masks, gt_labels
+
+
+INSTANCE_CASES = {"mixed": (5, 48, 56, 9, 14), "no_pred": (6, 32, 32, 4, 0), "no_gt": (7, 32, 32, 0, 5),
+                  "dense": (8, 64, 64, 25, 40), "tiny": (9, 8, 8, 2, 3)}

@@ -153,3 +153,71 @@ def test_trainer_and_evaluator_entry_points(tmp_path, monkeypatch):
     assert len(saved["model_state_dict"]) == 109
     out = evaluate_model("enhanced_unet", None, "cuda", ckpt, batches=SyntheticCellBatches(1, 2, 64, seed=2))
     assert 0.0 <= out["sem_mean_iou_all"] <= 1.0
+
+
+def test_instance_metrics_dropin_bit_exact(golden_dir):
+    """calculate_instance_metrics (metrics.py:61-194) through the bit-plane pairwise-intersection kernels: float64-identical
+    to the reference fixture and to the CPU oracle; the pairwise IoU matrix equals calculate_iou pair by pair."""
+    import oracle
+    from enhanced_unet_b200 import metrics
+    g = np.load(os.path.join(golden_dir, "instances.npz"))
+    for name, spec in oracle.INSTANCE_CASES.items():
+        args = oracle.make_instance_case(*spec)
+        m = metrics.calculate_instance_metrics(*args)
+        keys = sorted(m.keys())
+        assert keys == [str(k) for k in g[f"{name}/keys"]], name
+        assert np.array_equal(np.array([float(m[k]) for k in keys]), g[f"{name}/values"]), name
+    pm, _, _, gm, _ = oracle.make_instance_case(31, 37, 45, 12, 17)          # ragged size: 1665 pixels, not a multiple of 32
+    pm.append(np.zeros((37, 45), np.uint8)); gm.append(np.zeros((37, 45), np.uint8))   # empty masks: the union == 0 rule
+    iou = metrics.pairwise_iou(pm, gm)
+    want = np.array([[float(oracle.calculate_iou(a, b)) for b in gm] for a in pm])
+    assert np.array_equal(iou, want)
+    # counts at a full-size shape: checksum of the intersection matrix against torch integer arithmetic
+    from enhanced_unet_b200.ops import pair_intersections
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    a = (torch.rand(40, 1024, 1024, device="cuda", generator=gen) < 0.3).to(torch.uint8)
+    b = (torch.rand(24, 1024, 1024, device="cuda", generator=gen) < 0.2).to(torch.uint8)
+    inter, aa, ab = pair_intersections(a, b)
+    assert torch.equal(aa, a.flatten(1).long().sum(1)) and torch.equal(ab, b.flatten(1).long().sum(1))
+    want = (a.flatten(1).float() @ b.flatten(1).float().t()).long()         # exact: counts < 2^24
+    assert torch.equal(inter, want)
+
+
+@pytest.mark.parametrize("case", [(2, 3, 48, 40, 0.75), (1, 3, 48, 40, 1.25), (2, 3, 36, 30, (48, 40)), (1, 2, 7, 5, (13, 11)),
+                                  (1, 1, 64, 64, (32, 32)), (1, 3, 1, 1, (4, 3))])
+def test_resize_bilinear_matches_torch(case):
+    from enhanced_unet_b200.train_eval import Evaluator
+    b, c, h, w, how = case
+    x = torch.randn(b, c, h, w, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    if isinstance(how, tuple):
+        got = Evaluator._resize(x, size=how)
+        want = torch.nn.functional.interpolate(x, size=how, mode="bilinear", align_corners=False)
+    else:
+        got = Evaluator._resize(x, scale_factor=how)
+        want = torch.nn.functional.interpolate(x, scale_factor=how, mode="bilinear", align_corners=False)
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) <= 2e-6
+
+
+@pytest.mark.parametrize("dtype,tol", [("fp32", 2e-5), ("bf16", 4e-3)])
+def test_tta_inference_matches_reference_fixture(golden_dir, dtype, tol):
+    """Evaluator._run_tta_inference (train_eval.py:419-453): base + 2 flips + 0.75x / 1.25x views, against the reference."""
+    import oracle
+    from enhanced_unet_b200.models import EnhancedUNet
+    from enhanced_unet_b200.train_eval import Evaluator
+    g = np.load(os.path.join(golden_dir, "tta.npz"))
+    m = EnhancedUNet(3, dtype=dtype)
+    m.load_state_dict(oracle.make_state_dict(0), strict=True)
+    ev = Evaluator(m.cuda().eval(), "cuda", "enhanced_unet", tta=True)
+    for name in ("48x40", "64x64"):
+        h, w, seed = [int(v) for v in g[f"{name}/meta"]]
+        img = oracle.make_input(1, h, w, seed)[0].cuda()
+        base = ev._run_model_single(img).cpu().numpy()
+        tta = ev._run_tta_inference(img).cpu().numpy()
+        assert tta.shape == (3, h, w)
+        eb, et = np.abs(base - g[f"{name}/base"]).max(), np.abs(tta - g[f"{name}/tta"]).max()
+        effect = np.abs(g[f"{name}/tta"] - g[f"{name}/base"]).max()
+        print(f"[tta {dtype} {name}] base err {eb:.2e}, tta err {et:.2e} (tta-vs-base effect {effect:.2e})")
+        assert eb <= tol and et <= tol
+        if dtype == "fp32":
+            assert et < 0.05 * effect          # the check resolves the augmentation itself, not just the base forward

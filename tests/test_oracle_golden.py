@@ -129,3 +129,18 @@ def test_oracle_against_live_reference():
     a = ref_metrics.calculate_semantic_metrics(pred, gt)
     b = oracle.calculate_semantic_metrics(pred, gt)
     assert all(float(a[k]) == float(b[k]) for k in a)
+
+
+def test_instance_metrics_oracle_matches_reference_fixture(golden_dir):
+    """metrics.py:61-194: greedy score-ordered instance matching; values are float64-identical to the reference run."""
+    g = _load(golden_dir, "instances.npz")
+    for name, spec in oracle.INSTANCE_CASES.items():
+        m = oracle.calculate_instance_metrics(*oracle.make_instance_case(*spec))
+        keys = sorted(m.keys())
+        assert keys == [str(k) for k in g[f"{name}/keys"]], name
+        assert np.array_equal(np.array([float(m[k]) for k in keys]), g[f"{name}/values"]), name
+    if ref_import.available():
+        _, ref_metrics, _ = ref_import.load()
+        args = oracle.make_instance_case(11, 40, 40, 7, 9)
+        a, b = oracle.calculate_instance_metrics(*args), ref_metrics.calculate_instance_metrics(*args)
+        assert sorted(a) == sorted(b) and all(float(a[k]) == float(b[k]) for k in a)
