@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "conv.cuh"
 #include "tc_common.cuh"
+#include "../../include/eunet.h"
 
 namespace eunet {
 
@@ -31,6 +32,11 @@ struct ConvHaloParams {
   const float* shift;
   int relu;
   int out_f16;
+  // EPI = 1 (fused 2Hx2W tail, reference models.py:310-313 + 337): out = d14 + b3 + W3 . relu(acc * scale + shift)
+  const float* w3;    // [3][64]
+  const float* b3;    // [3]
+  const float* d14;   // fp32 [pixels][4]: the residual d1
+  float* out;         // fp32 NCHW [B,3,H,W]
 };
 
 __device__ __forceinline__ float warp_transpose_sum32h(float (&v)[32], int lane) {
@@ -71,7 +77,7 @@ struct HaloCfg {
   }
 };
 
-template <int KC, int BN, int MT, bool WRES, bool TST>
+template <int KC, int BN, int MT, bool WRES, bool TST, int EPI>
 __global__ void __launch_bounds__(320, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmY, const ConvHaloParams p) {
@@ -83,6 +89,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   __shared__ __align__(8) uint64_t a_full[AS], a_empty[AS], b_full[BS], b_empty[BS], acc_full[2], acc_empty[2], w_full;
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_scale[BN], s_shift[BN];   // folded-BN affine of this CTA's channel tile (eval epilogue)
+  // EPI = 1: enhance.3 weights and the exchange buffer through which the two warps of a TMEM lane quarter (32 channels
+  // each) combine their partial class sums: [item parity][quarter][tile][lane][3]
+  __shared__ __align__(16) float s_w3[EPI ? 3 * BN : 4];
+  __shared__ float s_xch[EPI ? 2 * 4 * MT * 32 * 3 : 1];
 
   const uint32_t sbase = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = sbase, b_base = sbase + AS * C::A_SLOT;
@@ -92,6 +102,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       s_scale[i] = p.scale[blockIdx.x * BN + i];
       s_shift[i] = p.shift[blockIdx.x * BN + i];
     }
+  if (EPI == 1)
+    for (int i = threadIdx.x; i < 3 * BN; i += blockDim.x) s_w3[i] = p.w3[i];
   // blockIdx.x = N tile (fastest in launch order: the CTAs that read the same halo tiles run together and share them
   // through L2), blockIdx.y = persistent CTA index over the pixel blocks
   const int n0 = blockIdx.x * BN;
@@ -215,7 +227,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     if (active) {
       const int r = q * 32 + lane;                 // GEMM row inside a 128-row tile: (ty, tx) = (r / 8, r % 8)
       const int ty = r >> 3, tx = r & 7;
-      const bool want_stats = p.stats != nullptr, affine = p.scale != nullptr;
+      const bool want_stats = p.stats != nullptr, affine = EPI == 0 && p.scale != nullptr, do_store = p.y != nullptr;
       double tot1[NCW], tot2[NCW];
 #pragma unroll
       for (int cw = 0; cw < NCW; ++cw) tot1[cw] = tot2[cw] = 0.0;
@@ -241,6 +253,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         tc::mbar_wait(tc::smem_u32(&acc_full[ab]), (li / NACC) & 1u);
         tc::tc_fence_after();
         const int gx = bx * 8 + tx;
+        float part[EPI ? MT : 1][3];
 #pragma unroll
         for (int cw = 0; cw < NCW; ++cw) {
           const int c0 = ((C::NCHUNK >= 2) ? 2 * cw + half : 0) * CH;
@@ -265,7 +278,24 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 run2[i] = tc::fma_f32x2(v, v, run2[i]);
               }
             }
-            if (TST || valid) {
+            if (EPI == 1) {
+              // this warp's 32 channels of relu(bn(acc)) . W3 for the pixel of this thread
+              float t0 = 0.f, t1 = 0.f, t2 = 0.f, u0 = 0.f, u1 = 0.f, u2 = 0.f;     // two chains per class (ILP)
+#pragma unroll
+              for (int i = 0; i < CH; i += 4) {
+                const float4 sc = *reinterpret_cast<const float4*>(&s_scale[c0 + i]), sh = *reinterpret_cast<const float4*>(&s_shift[c0 + i]);
+                const float4 w0 = *reinterpret_cast<const float4*>(&s_w3[c0 + i]), w1 = *reinterpret_cast<const float4*>(&s_w3[BN + c0 + i]);
+                const float4 w2 = *reinterpret_cast<const float4*>(&s_w3[2 * BN + c0 + i]);
+                const float a0 = fmaxf(fmaf(__uint_as_float(raw[i]), sc.x, sh.x), 0.f), a1 = fmaxf(fmaf(__uint_as_float(raw[i + 1]), sc.y, sh.y), 0.f);
+                const float a2 = fmaxf(fmaf(__uint_as_float(raw[i + 2]), sc.z, sh.z), 0.f), a3 = fmaxf(fmaf(__uint_as_float(raw[i + 3]), sc.w, sh.w), 0.f);
+                t0 = fmaf(a2, w0.z, fmaf(a0, w0.x, t0)); u0 = fmaf(a3, w0.w, fmaf(a1, w0.y, u0));
+                t1 = fmaf(a2, w1.z, fmaf(a0, w1.x, t1)); u1 = fmaf(a3, w1.w, fmaf(a1, w1.y, u1));
+                t2 = fmaf(a2, w2.z, fmaf(a0, w2.x, t2)); u2 = fmaf(a3, w2.w, fmaf(a1, w2.y, u2));
+              }
+              t0 += u0; t1 += u1; t2 += u2;
+              part[EPI ? mt : 0][0] = t0; part[EPI ? mt : 0][1] = t1; part[EPI ? mt : 0][2] = t2;
+            }
+            if (do_store && (TST || valid)) {
               uint32_t dst_s = 0;
               uint16_t* dst_g = nullptr;
               if (TST) {   // every row is staged (rows outside the image are clipped by the tensor store)
@@ -320,7 +350,38 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[ab]));
-        if (TST) {
+        if (EPI == 1) {
+          // combine the two 32-channel halves of every pixel: the upper-half warp hands its partial sums over through
+          // shared memory (double-buffered by item parity: ONE 64-thread barrier per quarter and item), the lower-half
+          // warp adds the residual d1 and the bias and writes the three logit planes
+          float* xq = s_xch + (((li & 1u) * 4 + q) * MT) * 96;
+          if (half == 1) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              xq[mt * 96 + lane] = part[EPI ? mt : 0][0];
+              xq[mt * 96 + 32 + lane] = part[EPI ? mt : 0][1];
+              xq[mt * 96 + 64 + lane] = part[EPI ? mt : 0][2];
+            }
+          }
+          tc::named_bar_sync(2 + q, 64);
+          if (half == 0) {
+            const float bb0 = __ldg(p.b3), bb1 = __ldg(p.b3 + 1), bb2 = __ldg(p.b3 + 2);
+            const long long HW = (long long)p.H * p.W;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              const int gy = by * (16 * MT) + 16 * mt + ty;
+              if (gx < p.W && gy < p.H) {
+                const long long hw = (long long)gy * p.W + gx;
+                const float4 d = __ldg(reinterpret_cast<const float4*>(p.d14) + (long long)b * HW + hw);
+                float* o = p.out + (long long)b * 3 * HW + hw;
+                o[0] = d.x + bb0 + (part[EPI ? mt : 0][0] + xq[mt * 96 + lane]);
+                o[HW] = d.y + bb1 + (part[EPI ? mt : 0][1] + xq[mt * 96 + 32 + lane]);
+                o[2 * HW] = d.z + bb2 + (part[EPI ? mt : 0][2] + xq[mt * 96 + 64 + lane]);
+              }
+            }
+          }
+        }
+        if (TST && do_store) {
           // the store of item li-1 has finished reading its buffer before anyone passes this barrier, so item li+1 may
           // overwrite that buffer without a second barrier; the store of item li is issued right after it
           tc::fence_proxy_async_smem();
@@ -332,7 +393,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           }
         }
       }
-      if (TST && e == 0 && lane == 0) tc::tma_store_wait<0>();
+      if (TST && do_store && e == 0 && lane == 0) tc::tma_store_wait<0>();
       if (want_stats) {
         if (NCW == 1 && pending > 0) flush(0);
 #pragma unroll
@@ -351,7 +412,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   if (warp == 1) tc::tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
-template <int KC, int BN, int MT, bool WRES, bool TST = false>
+template <int KC, int BN, int MT, bool WRES, bool TST = false, int EPI = 0>
 static int launch_halo(const void* x, int ldx, const void* w, ConvHaloParams p, cudaStream_t st) {
   using C = HaloCfg<KC, BN, MT, WRES, TST>;
   const int cchunks = p.Cin / KC;
@@ -363,7 +424,7 @@ static int launch_halo(const void* x, int ldx, const void* w, ConvHaloParams p, 
   if (items > 0x7fffffffLL) return 1;
   p.items = (int)items;
   CUtensorMap tmX, tmW, tmY;
-  if (TST) {
+  if (TST && p.y != nullptr) {
     uint64_t dims[4] = {(uint64_t)p.Cout, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.B};
     uint64_t str[3] = {(uint64_t)p.ldy * 2, (uint64_t)p.ldy * 2 * p.W, (uint64_t)p.ldy * 2 * p.W * p.H};
     uint32_t box[4] = {(uint32_t)BN, 8u, (uint32_t)(16 * MT), 1u};
@@ -382,7 +443,7 @@ static int launch_halo(const void* x, int ldx, const void* w, ConvHaloParams p, 
     uint32_t box[2] = {(uint32_t)KC, (uint32_t)BN};
     if (tc::encode_tensor_map_bf16(&tmW, w, 2, dims, str, box, KC == 64 ? 128 : 32)) return -1;
   }
-  auto kern = conv3x3_halo_kernel<KC, BN, MT, WRES, TST>;
+  auto kern = conv3x3_halo_kernel<KC, BN, MT, WRES, TST, EPI>;
   static int configured = 0;
   if (configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -405,7 +466,9 @@ int conv3x3_fwd_halo_bf16(const void* x, int ldx, const void* w, void* y, int ld
   p.y = y; p.ldy = ldy; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.blocks_x = p.blocks_y = p.items = 0;
   p.stats = stats; p.scale = scale; p.shift = shift; p.relu = relu; p.out_f16 = out_raw ? 1 : 0;
-  if (H < 8 || W < 8) return 1;           // tiny images: the batch-folding per-tap kernel wastes less
+  p.w3 = p.b3 = p.d14 = nullptr; p.out = nullptr;
+  if (H < 8 || W < 8) return 1;
+  if (y == nullptr && !(Cin == 16 && Cout == 64)) return 1;   // statistics-only pass: only the 16 -> 64 kernel skips stores           // tiny images: the batch-folding per-tap kernel wastes less
   if (Cin % 64 == 0) {
     if (Cout % 256 == 0) {
       // BN = 256: one 128-row tile per item leaves room for two accumulator sets (2 x 256 columns), so the statistics
@@ -426,4 +489,32 @@ int conv3x3_fwd_halo_bf16(const void* x, int ldx, const void* w, void* y, int ld
   return 1;
 }
 
+// Fused forward of the 2Hx2W tail (see ConvHaloParams): 3x3 convolution of the padded d1 (16 -> 64), folded / batch
+// BatchNorm affine + ReLU, the 1x1 enhance.3 projection, residual and bias, straight from the TMEM accumulators.
+// mid != nullptr additionally stores the RAW fp16 convolution output (the training backward reads it).
+int conv3x3_tail_fwd_bf16(const void* x16, const void* w, void* mid, const float* scale, const float* shift, const float* w3,
+                          const float* b3, const float* d14, float* out, int B, int H, int W, cudaStream_t st) {
+  ConvHaloParams p;
+  p.y = mid; p.ldy = 64; p.B = B; p.H = H; p.W = W; p.Cin = 16; p.Cout = 64;
+  p.blocks_x = p.blocks_y = p.items = 0;
+  p.stats = nullptr; p.scale = scale; p.shift = shift; p.relu = 0; p.out_f16 = 1;
+  p.w3 = w3; p.b3 = b3; p.d14 = d14; p.out = out;
+  if (H < 8 || W < 8) return 1;
+  if (mid != nullptr) return launch_halo<16, 64, 4, true, true, 1>(x16, 16, w, p, st);
+  return launch_halo<16, 64, 4, true, false, 1>(x16, 16, w, p, st);
+}
+
 }  // namespace eunet
+
+extern "C" int eunet_conv3x3_tail_fwd(const void* d1p16, const void* w_packed, void* mid_raw, const float* scale, const float* shift,
+                                      const float* w3, const float* b3, const float* d14, float* out, int B, int H2, int W2,
+                                      void* stream) {
+  using namespace eunet;
+  EUNET_REQUIRE(B > 0 && H2 >= 8 && W2 >= 8, "conv3x3_tail_fwd: needs B > 0 and a >= 8x8 output grid (got %d, %dx%d)", B, H2, W2);
+  EUNET_REQUIRE(d1p16 && w_packed && scale && shift && w3 && b3 && d14 && out, "conv3x3_tail_fwd: null operand");
+  EUNET_REQUIRE((reinterpret_cast<uintptr_t>(d14) & 15) == 0 && (reinterpret_cast<uintptr_t>(mid_raw) & 15) == 0,
+                "conv3x3_tail_fwd: d14 / mid must be 16-byte aligned");
+  const int rc = conv3x3_tail_fwd_bf16(d1p16, w_packed, mid_raw, scale, shift, w3, b3, d14, out, B, H2, W2, (cudaStream_t)stream);
+  EUNET_REQUIRE(rc <= 0, "conv3x3_tail_fwd: shape not covered");
+  return rc;
+}

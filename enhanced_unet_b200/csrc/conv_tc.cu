@@ -387,6 +387,7 @@ static int conv3x3_fwd_bf16(const void* x, int ldx, const void* w, void* y, int 
     const int rc = conv3x3_fwd_halo_bf16(x, ldx, w, y, ldy, B, H, W, Cin, Cout, stats, scale, shift, relu, out_raw, st);
     if (rc <= 0) return rc;   // launched (0) or failed (< 0); 1 = not covered, fall through to the per-tap kernel
   }
+  EUNET_REQUIRE(y != nullptr, "conv3x3_fwd(bf16): y == NULL (statistics only) is implemented for 16 -> 64 channels on >= 8x8 images");
   const int KC = (Cin % 64 == 0) ? 64 : 16;
   const int BN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0) ? 128 : (Cout % 64 == 0) ? 64 : 16;
   const PixelTile t = choose_pixel_tile(B, H, W, 128);

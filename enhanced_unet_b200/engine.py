@@ -28,6 +28,7 @@ BLOCKS = [  # (prefix, Cin, Cout) - reference models.py:203-211
 ]
 BN_MOMENTUM = 0.1
 BN_EPS = 1e-5
+FUSED_TAIL = None      # None: fused 2Hx2W tail epilogue in eval mode only; True / False force it (benchmarks, tests)
 
 
 def _pad16(c: int) -> int:
@@ -339,20 +340,39 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, train: bool, act_dtype
     d14 = cx.empty(M2x, 4, dtype=f32)
     call("eunet_tail_up_fwd", ptr(z4), ptr(d1p), ptr(d14), cx.code, B, H, W)
     out = torch.empty(B, 3, 2 * H, 2 * W, device=x.device, dtype=f32)
-    midt = cx.empty(M2x, 64, dtype=cx.raw)
+    wp0 = packs.get(cx, "enhance.0", sd["enhance.0.weight"], False)
+    # tensor-core path: BN + ReLU + enhance.3 + residual in the conv epilogue.  Inference only: in training the 64-channel
+    # tensor has to be stored for the backward pass anyway and the separate bandwidth pass is faster than the heavier
+    # epilogue (measured: 1.53 ms fused + 0.25 ms statistics pass against 0.49 + 0.79 ms).
+    fused = cx.dt == torch.bfloat16 and ((not train) if FUSED_TAIL is None else bool(FUSED_TAIL))
     if train:
         stats = cx.zeros(128, dtype=torch.float64)
-        conv3x3(cx, d1p, packs.get(cx, "enhance.0", sd["enhance.0.weight"], False), midt, B, 2 * H, 2 * W, 16, 64, stats=stats)
+        midt = cx.empty(M2x, 64, dtype=cx.raw) if (want_saved or not fused) else None
+        if fused:   # pass 1: batch statistics only (nothing stored); pass 2 below recomputes the tiles
+            call("eunet_conv3x3_fwd", ptr(d1p), 16, ptr(wp0), None, 64, cx.code, B, 2 * H, 2 * W, 16, 64, ptr(stats), None, None, 0, 1,
+                 flops=2.0 * M2x * 64 * 9 * 16)
+        else:
+            conv3x3(cx, d1p, wp0, midt, B, 2 * H, 2 * W, 16, 64, stats=stats)
         scale, shift, mean, invstd = (cx.empty(64, dtype=f32) for _ in range(4))
         call("eunet_bn_finalize", ptr(stats), M2x, ptr(sd["enhance.1.weight"]), ptr(sd["enhance.1.bias"]),
              ptr(sd["enhance.0.bias"]), ptr(sd["enhance.1.running_mean"]), ptr(sd["enhance.1.running_var"]),
              ptr(sd["enhance.1.num_batches_tracked"]), BN_MOMENTUM, BN_EPS, ptr(scale), ptr(shift), ptr(mean), ptr(invstd), 64)
         sv.bn["enhance.1"] = _BNSaved(midt, scale, shift, mean, invstd)
     else:
-        _conv_bn_eval(cx, packs, sd, "enhance.0", "enhance.1", d1p, B, 2 * H, 2 * W, 16, 64, midt)
-        scale, shift = torch.ones(64, device=x.device, dtype=f32), torch.zeros(64, device=x.device, dtype=f32)
-    call("eunet_tail_out_fwd", ptr(d14), ptr(midt), cx.code, ptr(scale), ptr(shift), ptr(w3), ptr(sd["enhance.3.bias"]), ptr(out),
-         B, H, W)
+        scale, shift = cx.empty(64, dtype=f32), cx.empty(64, dtype=f32)
+        call("eunet_bn_fold_eval", ptr(sd["enhance.1.weight"]), ptr(sd["enhance.1.bias"]), ptr(sd["enhance.0.bias"]),
+             ptr(sd["enhance.1.running_mean"]), ptr(sd["enhance.1.running_var"]), BN_EPS, ptr(scale), ptr(shift), 64)
+        midt = None
+    if fused:
+        call("eunet_conv3x3_tail_fwd", ptr(d1p), ptr(wp0), ptr(midt), ptr(scale), ptr(shift), ptr(w3), ptr(sd["enhance.3.bias"]),
+             ptr(d14), ptr(out), B, 2 * H, 2 * W, flops=2.0 * M2x * 64 * 9 * 16)
+    else:
+        if not train:   # fp32 mode, eval: conv with the folded affine + ReLU, then the 1x1 + residual pass
+            midt = cx.empty(M2x, 64, dtype=cx.raw)
+            conv3x3(cx, d1p, wp0, midt, B, 2 * H, 2 * W, 16, 64, scale=scale, shift=shift, relu=True)
+            scale, shift = torch.ones(64, device=x.device, dtype=f32), torch.zeros(64, device=x.device, dtype=f32)
+        call("eunet_tail_out_fwd", ptr(d14), ptr(midt), cx.code, ptr(scale), ptr(shift), ptr(w3), ptr(sd["enhance.3.bias"]), ptr(out),
+             B, H, W)
     if train and want_saved:
         sv.act.update(dict(cat2=cat2, cat3=cat3, cat4=cat4, d2=d2, d1p=d1p, z4=z4))
         return out, sv

@@ -35,6 +35,7 @@ SIGNATURES = {
     "eunet_pack_weight3x3_multi": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
     "eunet_unpack_wgrad3x3": [_p, _p, _i, _i, _i, _i, _p],
     "eunet_conv3x3_fwd": [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _i, _p],
+    "eunet_conv3x3_tail_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "eunet_conv3x3_dgrad_few": [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p],
     "eunet_conv3x3_wgrad": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p],
     "eunet_bn_finalize": [_p, _ll, _p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _i, _p],

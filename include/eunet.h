@@ -79,10 +79,19 @@ int eunet_unpack_wgrad3x3(const float* dw_packed, float* dw, int Co, int Ci, int
  *   scale/shift != NULL: y = y*scale[co] + shift[co] (folded eval-mode BN and/or bias); relu: max(y,0).
  *   out_raw: element type of y.  0 = the activation dtype (bf16 / fp32); 1 = the RAW dtype used for tensors
  *            that feed a BatchNorm (fp16 in bf16 mode - 8x finer than bf16 where the batch mean dominates -
- *            and fp32 in fp32 mode).  The bn_* / tail_* entry points read raw tensors in that dtype. */
+ *            and fp32 in fp32 mode).  The bn_* / tail_* entry points read raw tensors in that dtype.
+ *   y == NULL (bf16, Cin = 16 -> Cout = 64 only): statistics-only pass, nothing is stored. */
 int eunet_conv3x3_fwd(const void* x, int ldx, const void* w_packed, void* y, int ldy, int dtype, int B, int H, int W,
                       int Cin, int Cout, double* stats, const float* scale, const float* shift, int relu, int out_raw,
                       void* stream);
+/* Fused forward of the 2Hx2W tail (models.py:309-313 enhance head + 337 residual), bf16 tensor-core path:
+ *   out[b,k,p] = d14[p][k] + b3[k] + sum_c w3[k][c] * relu(conv3x3(d1p16; w_packed)[p,c] * scale[c] + shift[c])
+ * d1p16: [B*H2*W2, 16] bf16 (d1 padded to 16 channels); w_packed: eunet_pack_weight3x3 of enhance.0 ([64][9][16]);
+ * scale/shift: BatchNorm affine (batch statistics in training, folded running statistics in eval); d14: fp32 [pixels][4];
+ * out: fp32 NCHW [B,3,H2,W2].  mid_raw != NULL additionally stores the RAW fp16 convolution output [pixels][64]
+ * (read by tail_bwd_*); NULL (inference) never materialises the 64-channel tensor. */
+int eunet_conv3x3_tail_fwd(const void* d1p16, const void* w_packed, void* mid_raw, const float* scale, const float* shift,
+                           const float* w3, const float* b3, const float* d14, float* out, int B, int H2, int W2, void* stream);
 /* dw[co][tap][ci] += sum_p dy[p,co] * x[p+tap,ci]   (fp32 accumulate into caller-zeroed dw_packed) */
 int eunet_conv3x3_wgrad(const void* x, int ldx, const void* dy, int lddy, float* dw_packed, int dtype, int B, int H, int W,
                         int Cin, int Cout, void* stream);

@@ -336,6 +336,42 @@ def test_pack_weight_multi_matches_single(k, dtn):
         assert torch.equal(o, wnt), e
 
 
+@pytest.mark.parametrize("shape", [(2, 16, 24), (1, 72, 40), (3, 8, 8), (2, 136, 128)])
+@pytest.mark.parametrize("store_mid", [True, False])
+def test_conv3x3_tail_fwd_fused_epilogue(k, shape, store_mid):
+    """Fused 2Hx2W tail: conv3x3 (3 -> 64, tcgen05) + BN affine + ReLU + 1x1 (64 -> 3) + residual + bias from the TMEM
+    accumulators, against the same chain in torch fp32 on the bf16-rounded conv operands; plus the statistics-only pass."""
+    B, H, W = shape
+    g = torch.Generator().manual_seed(B * 100 + H)
+    d1 = torch.randn(B, 3, H, W, generator=g)
+    w0 = torch.randn(64, 3, 3, 3, generator=g) / 5.0
+    sc, sh = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.5
+    w3, b3 = torch.randn(3, 64, generator=g) / 8.0, torch.randn(3, generator=g)
+    mid = _conv_ref(rnd("bf16", d1), rnd("bf16", w0))
+    want = d1 + b3[None, :, None, None] + torch.einsum("kc,bchw->bkhw", w3, F.relu(mid * sc[None, :, None, None] + sh[None, :, None, None]))
+    M = B * H * W
+    x16 = torch.zeros(M, 16, dtype=torch.bfloat16, device="cuda")
+    x16[:, :3] = d1.permute(0, 2, 3, 1).reshape(M, 3).to(torch.bfloat16).cuda()
+    d14 = torch.zeros(M, 4, device="cuda")
+    d14[:, :3] = d1.permute(0, 2, 3, 1).reshape(M, 3).cuda()
+    wp = torch.empty(64, 9, 16, dtype=torch.bfloat16, device="cuda")
+    k.call("eunet_pack_weight3x3", w0.cuda().data_ptr(), wp.data_ptr(), k.BF16, 64, 3, 64, 16, 0)
+    out = torch.full((B, 3, H, W), 7.0, device="cuda")
+    midt = torch.full((M, 64), 3.0, dtype=torch.float16, device="cuda") if store_mid else None
+    scd, shd, w3d, b3d = sc.cuda(), sh.cuda(), w3.cuda().contiguous(), b3.cuda()     # keep the device copies alive
+    k.call("eunet_conv3x3_tail_fwd", x16.data_ptr(), wp.data_ptr(), midt.data_ptr() if store_mid else None, scd.data_ptr(),
+           shd.data_ptr(), w3d.data_ptr(), b3d.data_ptr(), d14.data_ptr(), out.data_ptr(), B, H, W)
+    torch.cuda.synchronize()
+    assert nerr(out.cpu(), want) < 2e-5
+    if store_mid:
+        assert nerr(nchw(midt, B, H, W), mid) < 1e-3            # raw fp16 storage of the fp32 accumulators
+    # statistics-only pass (y == NULL): the same sums as the storing call
+    s1 = torch.zeros(128, dtype=torch.float64, device="cuda")
+    k.call("eunet_conv3x3_fwd", x16.data_ptr(), 16, wp.data_ptr(), None, 64, k.BF16, B, H, W, 16, 64, s1.data_ptr(), None, None, 0, 1)
+    assert nerr(s1[:64].cpu(), mid.double().sum((0, 2, 3))) < 1e-4
+    assert nerr(s1[64:].cpu(), (mid.double() ** 2).sum((0, 2, 3))) < 1e-4
+
+
 def test_pack_input_and_padded_weights(k):
     g = torch.Generator().manual_seed(4)
     x = torch.rand(2, 3, 8, 8, generator=g)
