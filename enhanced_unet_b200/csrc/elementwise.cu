@@ -346,9 +346,12 @@ bn_bwd_reduce_kernel(const T* __restrict__ dact, int ldd, const TY* __restrict__
   const int G = C >> 3, R = 256 / G;
   const int cg = threadIdx.x % G, r = threadIdx.x / G;
   const F8 sc = load8(scale + cg * 8), sh = load8(shift + cg * 8), mu = load8(mean + cg * 8), is = load8(invstd + cg * 8);
-  float sg[8], sgx[8];
+  float sg[8], sgx[8], beta[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) sg[e] = sgx[e] = 0.f;
+  for (int e = 0; e < 8; ++e) {
+    sg[e] = sgx[e] = 0.f;
+    beta[e] = fmaf(sc.v[e], mu.v[e], sh.v[e]);
+  }
   const long long p0 = (long long)blockIdx.x * R + r, step = (long long)gridDim.x * R;
   const long long n = p0 < M ? (M - p0 + step - 1) / step : 0;   // this thread's pixel count
 #pragma unroll
@@ -370,18 +373,22 @@ bn_bwd_reduce_kernel(const T* __restrict__ dact, int ldd, const TY* __restrict__
     cp_async_commit();
     cp_async_wait<kBnStages - 1>();
     const F8 d = sd.get((int)(i % kBnStages)), v = sy.get((int)(i % kBnStages));
+    // pre = sc * (v - mean) + beta; masked sums with predicated accumulation (5 instructions per element), the
+    // invstd factor of xhat is applied once at the end
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float g = fmaf(v.v[e], sc.v[e], sh.v[e]) > 0.f ? d.v[e] : 0.f;
-      sg[e] += g;
-      sgx[e] += g * ((v.v[e] - mu.v[e]) * is.v[e]);
+      const float xc = v.v[e] - mu.v[e];
+      if (fmaf(xc, sc.v[e], beta[e]) > 0.f) {
+        sg[e] += d.v[e];
+        sgx[e] = fmaf(d.v[e], xc, sgx[e]);
+      }
     }
   }
   cp_async_wait<0>();
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     red[0][r * C + cg * 8 + e] = sg[e];
-    red[1][r * C + cg * 8 + e] = sgx[e];
+    red[1][r * C + cg * 8 + e] = sgx[e] * is.v[e];
   }
   __syncthreads();
   for (int t = threadIdx.x; t < 2 * C; t += 256) {
