@@ -36,7 +36,8 @@ def test_library_exports_every_declared_symbol(built_lib):
 
 
 def test_library_is_sm100a_tensor_core_code(built_lib):
-    """The shipped binary must contain tcgen05 / TMA machine code (UTCHMMA, UTMALDG, LDTM) for sm_100a."""
+    """The shipped binary must contain tcgen05 / TMA machine code (UTCHMMA, UTMALDG loads, UTMASTG stores, LDTM) and
+    the packed-fp32 epilogue arithmetic (FADD2 / FFMA2) for sm_100a."""
     import shutil
     import subprocess
     from enhanced_unet_b200 import lib
@@ -45,7 +46,7 @@ def test_library_is_sm100a_tensor_core_code(built_lib):
         pytest.skip("cuobjdump not available")
     out = subprocess.run([cuobjdump, "-sass", lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
-    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+    for mnemonic in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "FADD2", "FFMA2"):
         assert mnemonic in out, mnemonic
 
 
