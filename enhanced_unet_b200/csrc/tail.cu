@@ -311,9 +311,10 @@ tail_bwd_dmid_kernel(const float* __restrict__ dout, const TY* __restrict__ mid,
   const long long HWo = (long long)Ho * Wo, M = (long long)B * HWo;
   const F8 sc = load8(scale + cg * 8), sh = load8(shift + cg * 8), mu = load8(mean + cg * 8), is = load8(invstd + cg * 8);
   // dmid = sc * (g' - k1 - xhat * k2) with g' = [pre > 0] * sum_k g_k w_k, xhat = (v - mean) * invstd, rewritten as
-  //     dmid = -(A + Bc * xc) + [pre > 0] * sum_k g_k * (sc w_k),   xc = v - mean, A = sc k1, Bc = sc k2 invstd
-  // (7 instructions per element: the kernel is as much issue- as DRAM-bound)
-  float ws[3][8], A[8], Bc[8], beta[8];
+  //     dmid = A + Bc v + [sc v + sh > 0] * sum_k g_k * (sc w_k),   Bc = -sc k2 invstd, A = -sc k1 - Bc mean
+  // (7 instructions per element; the same expression, in the same order, as the transform stage of
+  // tail_bwd_fused_kernel, so both paths produce bit-identical bf16 gradients)
+  float ws[3][8], A[8], Bc[8];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const F8 t = load8(w3 + k * 64 + cg * 8);
@@ -323,9 +324,8 @@ tail_bwd_dmid_kernel(const float* __restrict__ dout, const TY* __restrict__ mid,
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const float k1 = (float)(acc[cg * 8 + e] / (double)M), k2 = (float)(acc[64 + cg * 8 + e] / (double)M);
-    A[e] = -sc.v[e] * k1;
     Bc[e] = -sc.v[e] * k2 * is.v[e];
-    beta[e] = fmaf(sc.v[e], mu.v[e], sh.v[e]);
+    A[e] = -sc.v[e] * k1 - Bc[e] * mu.v[e];
   }
   extern __shared__ __align__(16) char dyn_smem[];
   Stream8<TY, kTailStages> sm(dyn_smem, 256);
@@ -355,9 +355,8 @@ tail_bwd_dmid_kernel(const float* __restrict__ dout, const TY* __restrict__ mid,
     F8 o;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float xc = v.v[e] - mu.v[e];
-      float r = fmaf(Bc[e], xc, A[e]);
-      if (fmaf(xc, sc.v[e], beta[e]) > 0.f) r = fmaf(g2, ws[2][e], fmaf(g1, ws[1][e], fmaf(g0, ws[0][e], r)));
+      float r = fmaf(Bc[e], v.v[e], A[e]);
+      if (fmaf(v.v[e], sc.v[e], sh.v[e]) > 0.f) r = fmaf(g2, ws[2][e], fmaf(g1, ws[1][e], fmaf(g0, ws[0][e], r)));
       o.v[e] = r;
     }
     store8(dmid + p * 64 + cg * 8, o);

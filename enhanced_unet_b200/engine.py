@@ -28,6 +28,7 @@ BLOCKS = [  # (prefix, Cin, Cout) - reference models.py:203-211
 ]
 BN_MOMENTUM = 0.1
 BN_EPS = 1e-5
+FUSED_TAIL_BWD = True  # bf16 mode: dmid + wgrad + dgrad of enhance.0 in one kernel (False: the three separate kernels)
 FUSED_TAIL = None      # None: fused 2Hx2W tail epilogue in eval mode only; True / False force it (benchmarks, tests)
 
 
@@ -417,29 +418,40 @@ def backward(sd: Dict[str, torch.Tensor], sv: Saved, dout: torch.Tensor, act_dty
     call("eunet_tail_pack3", ptr(dout), ptr(dout4), B, 2 * H, 2 * W)
     call("eunet_tail_bwd_reduce", ptr(dout4), ptr(bn.y), cx.code, ptr(bn.scale), ptr(bn.shift), ptr(bn.mean), ptr(bn.invstd),
          ptr(w3), ptr(acc), B, H, W)
-    dmid = cx.empty(M2x, 64)
-    call("eunet_tail_bwd_dmid", ptr(dout4), ptr(bn.y), ptr(dmid), cx.code, ptr(bn.scale), ptr(bn.shift), ptr(bn.mean),
-         ptr(bn.invstd), ptr(w3), ptr(acc), B, H, W)
     cast64("enhance.1.bias", acc[0:64], (64,))
     cast64("enhance.1.weight", acc[64:128], (64,))
     cast64("enhance.3.weight", acc[128:320], (3, 64, 1, 1))
     cast64("enhance.3.bias", acc[320:323], (3,))
     d1p = sv.act["d1p"]
-    dwp = conv3x3_wgrad(cx, d1p, dmid, B, 2 * H, 2 * W, 16, 64, pool)
-    wgrad_into("enhance.0.weight", dwp, 64, 3)
-    zero_bias("enhance.0.bias", 64)                                            # cancelled by train-mode BN
     dz4 = cx.empty(M1, 4, dtype=f32)
     wflip = packs.get(cx, "enhance.0", sd["enhance.0.weight"], True)
-    if cx.dt == torch.bfloat16 and 2 * H >= 8 and 2 * W >= 8:
-        # 3 real gradient channels: transposed dgrad (every dmid row read once), fp32 [pixels][4] output
+    tc_path = cx.dt == torch.bfloat16 and 2 * H >= 8 and 2 * W >= 8
+    if tc_path and FUSED_TAIL_BWD:
+        # ONE kernel: BN/ReLU backward on chip, wgrad and the 3-channel transposed dgrad from the same staged tile
+        dwp = pool.take(64, 9, 16)
         dd1 = cx.empty(M2x, 4, dtype=f32)
-        call("eunet_conv3x3_dgrad_few", ptr(dmid), _ld(dmid), ptr(wflip), ptr(dd1), B, 2 * H, 2 * W, 64, 16,
-             flops=2.0 * M2x * 64 * 27)
+        call("eunet_tail_bwd_fused", ptr(dout4), ptr(bn.y), ptr(d1p), ptr(wflip), ptr(bn.scale), ptr(bn.shift), ptr(bn.mean),
+             ptr(bn.invstd), ptr(w3), ptr(acc), ptr(dd1), ptr(dwp), B, 2 * H, 2 * W, flops=2 * 2.0 * M2x * 64 * 27)
+        wgrad_into("enhance.0.weight", dwp, 64, 3)
+        zero_bias("enhance.0.bias", 64)                                        # cancelled by train-mode BN
         call("eunet_tail_up_bwd", ptr(dd1), lib.F32, 4, ptr(dout), ptr(dz4), B, H, W)
     else:
-        dd1p = cx.empty(M2x, 16)
-        conv3x3(cx, dmid, wflip, dd1p, B, 2 * H, 2 * W, 64, 16)
-        call("eunet_tail_up_bwd", ptr(dd1p), cx.code, 16, ptr(dout), ptr(dz4), B, H, W)
+        dmid = cx.empty(M2x, 64)
+        call("eunet_tail_bwd_dmid", ptr(dout4), ptr(bn.y), ptr(dmid), cx.code, ptr(bn.scale), ptr(bn.shift), ptr(bn.mean),
+             ptr(bn.invstd), ptr(w3), ptr(acc), B, H, W)
+        dwp = conv3x3_wgrad(cx, d1p, dmid, B, 2 * H, 2 * W, 16, 64, pool)
+        wgrad_into("enhance.0.weight", dwp, 64, 3)
+        zero_bias("enhance.0.bias", 64)                                        # cancelled by train-mode BN
+        if tc_path:
+            # 3 real gradient channels: transposed dgrad (every dmid row read once), fp32 [pixels][4] output
+            dd1 = cx.empty(M2x, 4, dtype=f32)
+            call("eunet_conv3x3_dgrad_few", ptr(dmid), _ld(dmid), ptr(wflip), ptr(dd1), B, 2 * H, 2 * W, 64, 16,
+                 flops=2.0 * M2x * 64 * 27)
+            call("eunet_tail_up_bwd", ptr(dd1), lib.F32, 4, ptr(dout), ptr(dz4), B, H, W)
+        else:
+            dd1p = cx.empty(M2x, 16)
+            conv3x3(cx, dmid, wflip, dd1p, B, 2 * H, 2 * W, 64, 16)
+            call("eunet_tail_up_bwd", ptr(dd1p), cx.code, 16, ptr(dout), ptr(dz4), B, H, W)
     acc2 = cx.zeros(200, dtype=f64)
     d2 = sv.act["d2"]
     dd2 = cx.empty(M1, 64)

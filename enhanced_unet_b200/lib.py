@@ -53,6 +53,7 @@ SIGNATURES = {
     "eunet_tail_out_fwd": [_p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "eunet_tail_bwd_reduce": [_p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "eunet_tail_bwd_dmid": [_p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "eunet_tail_bwd_fused": [_p] * 12 + [_i, _i, _i, _p],
     "eunet_tail_up_bwd": [_p, _i, _i, _p, _p, _i, _i, _i, _p],
     "eunet_tail_dec1_bwd": [_p, _p, _i, _p, _i, _i, _p, _p, _ll, _p],
     "eunet_cast_f64_f32": [_p, _p, _ll, _p],

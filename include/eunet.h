@@ -148,6 +148,14 @@ int eunet_tail_bwd_reduce(const float* dout4, const void* mid, int dtype, const 
 int eunet_tail_bwd_dmid(const float* dout4, const void* mid, void* dmid, int dtype, const float* scale, const float* shift,
                         const float* mean, const float* invstd, const float* w3, const double* acc, int B, int H, int W,
                         void* stream);
+/* Fused backward of the enhance head at 2Hx2W (bf16 tensor-core path): replaces eunet_tail_bwd_dmid + eunet_conv3x3_wgrad
+ * + eunet_conv3x3_dgrad_few for enhance.0 - the 64-channel gradient dmid is formed on chip and never written:
+ *   dmid = BN/ReLU backward of (mid_raw, dout4) with the sums `acc` from eunet_tail_bwd_reduce,
+ *   dw_packed[co][tap][ci] += sum_p dmid[p,co] * d1p16[p+tap,ci]      (fp32 [64][9][16], caller-zeroed),
+ *   dx4[p][i] = sum_{tap,co} dmid[p+tap-(1,1),co] * w_packed_flip[i][tap][co], i < 3   (fp32 [pixels][4]). */
+int eunet_tail_bwd_fused(const float* dout4, const void* mid_raw, const void* d1p16, const void* w_packed_flip,
+                         const float* scale, const float* shift, const float* mean, const float* invstd, const float* w3,
+                         const double* acc, float* dx4, float* dw_packed, int B, int H2, int W2, void* stream);
 /* dd1p: gradient w.r.t. d1, `dd1_stride` elements of `dtype` per pixel of which the first 3 are read
  * (16 = the padded conv3x3 dgrad output; 4 with dtype fp32 = eunet_conv3x3_dgrad_few's dx4) */
 int eunet_tail_up_bwd(const void* dd1p /*[B,2H,2W,dd1_stride]*/, int dtype, int dd1_stride, const float* dout, float* dz4,

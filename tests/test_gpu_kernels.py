@@ -372,6 +372,49 @@ def test_conv3x3_tail_fwd_fused_epilogue(k, shape, store_mid):
     assert nerr(s1[64:].cpu(), (mid.double() ** 2).sum((0, 2, 3))) < 1e-4
 
 
+@pytest.mark.parametrize("shape", [(2, 16, 24), (1, 72, 40), (3, 8, 8), (2, 144, 136)])
+def test_tail_bwd_fused_matches_separate_kernels(k, shape):
+    """eunet_tail_bwd_fused (BN/ReLU backward formed on chip + wgrad + 3-channel transposed dgrad of enhance.0 from one staged
+    tile) against the three separate kernels it replaces (tail_bwd_dmid -> conv3x3_wgrad / conv3x3_dgrad_few), which are
+    themselves pinned against torch; the bf16 dmid is bit-identical in both, only fp32 summation order differs."""
+    B, H2, W2 = shape
+    M = B * H2 * W2
+    g = torch.Generator(device="cuda").manual_seed(B * 7 + H2)
+    mid = (torch.randn(M, 64, device="cuda", generator=g) * 1.5 + 0.3).to(torch.float16)
+    dout4 = torch.randn(M, 4, device="cuda", generator=g)
+    dout4[:, 3] = 0
+    d1p = torch.zeros(M, 16, dtype=torch.bfloat16, device="cuda")
+    d1p[:, :3] = torch.randn(M, 3, device="cuda", generator=g).to(torch.bfloat16)
+    w0 = torch.randn(64, 3, 3, 3, device="cuda", generator=g) / 5.0
+    wflip = torch.empty(16, 9, 64, dtype=torch.bfloat16, device="cuda")
+    k.call("eunet_pack_weight3x3", w0.data_ptr(), wflip.data_ptr(), k.BF16, 64, 3, 64, 16, 1)
+    mean = mid.float().mean(0)
+    invstd = 1.0 / torch.sqrt(mid.float().var(0, unbiased=False) + 1e-5)
+    gamma, beta = torch.rand(64, device="cuda", generator=g) + 0.5, torch.randn(64, device="cuda", generator=g) * 0.3
+    scale = (gamma * invstd).contiguous()
+    shift = (beta - mean * scale).contiguous()
+    w3 = (torch.randn(3, 64, device="cuda", generator=g) / 8.0).contiguous()
+    acc = torch.zeros(328, dtype=torch.float64, device="cuda")
+    # geometry arguments of the tail kernels are the HALF resolution (H, W) of a 2H x 2W grid
+    assert H2 % 2 == 0 and W2 % 2 == 0
+    k.call("eunet_tail_bwd_reduce", dout4.data_ptr(), mid.data_ptr(), k.BF16, scale.data_ptr(), shift.data_ptr(), mean.data_ptr(),
+           invstd.data_ptr(), w3.data_ptr(), acc.data_ptr(), B, H2 // 2, W2 // 2)
+    dmid = torch.empty(M, 64, dtype=torch.bfloat16, device="cuda")
+    k.call("eunet_tail_bwd_dmid", dout4.data_ptr(), mid.data_ptr(), dmid.data_ptr(), k.BF16, scale.data_ptr(), shift.data_ptr(),
+           mean.data_ptr(), invstd.data_ptr(), w3.data_ptr(), acc.data_ptr(), B, H2 // 2, W2 // 2)
+    dw_ref = torch.zeros(64, 9, 16, device="cuda")
+    k.call("eunet_conv3x3_wgrad", d1p.data_ptr(), 16, dmid.data_ptr(), 64, dw_ref.data_ptr(), k.BF16, B, H2, W2, 16, 64)
+    dx_ref = torch.empty(M, 4, device="cuda")
+    k.call("eunet_conv3x3_dgrad_few", dmid.data_ptr(), 64, wflip.data_ptr(), dx_ref.data_ptr(), B, H2, W2, 64, 16)
+    dw = torch.zeros(64, 9, 16, device="cuda")
+    dx = torch.full((M, 4), 5.0, device="cuda")
+    k.call("eunet_tail_bwd_fused", dout4.data_ptr(), mid.data_ptr(), d1p.data_ptr(), wflip.data_ptr(), scale.data_ptr(),
+           shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), w3.data_ptr(), acc.data_ptr(), dx.data_ptr(), dw.data_ptr(), B, H2, W2)
+    torch.cuda.synchronize()
+    assert nerr(dx, dx_ref) < 2e-5, nerr(dx, dx_ref)
+    assert nerr(dw, dw_ref) < 2e-5, nerr(dw, dw_ref)
+
+
 def test_pack_input_and_padded_weights(k):
     g = torch.Generator().manual_seed(4)
     x = torch.rand(2, 3, 8, 8, generator=g)
