@@ -237,7 +237,7 @@ conv3x3_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 // wgrad
 // ------------------------------------------------------------------------------------------------
 template <int KC, int TAPS, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, 2)
 conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                         const ConvWgradParams p) {
   constexpr int KP = 64;                                    // pixels (GEMM K) per stage
@@ -340,9 +340,14 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       tc::tmem_ld_wait();
       if (co < p.Cout) {
         const int tt = c0 / KC, ci = c0 % KC;   // a CH-column chunk never straddles a tap (KC % CH == 0)
+        // 16-byte vector reductions: this thread's CH values are contiguous (one (co, tap) row of the packed gradient),
+        // but the rows of neighbouring lanes are 9*Cin floats apart, so every warp instruction touches 32 lines
         float* dst = p.dw + ((long long)co * 9 + tap0 + tt) * p.Cin + ci0 + ci;
 #pragma unroll
-        for (int i = 0; i < CH; ++i) atomicAdd(dst + i, __uint_as_float(raw[i]));
+        for (int i = 0; i < CH; i += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "r"(raw[i]), "r"(raw[i + 1]), "r"(raw[i + 2]),
+                       "r"(raw[i + 3])
+                       : "memory");
       }
     }
   }
@@ -464,7 +469,8 @@ static int conv3x3_wgrad_bf16(const void* x, int ldx, const void* dy, int lddy, 
   EUNET_REQUIRE(t.tiles() <= 0x7fffffffLL, "conv3x3_wgrad(bf16): too many tiles");
   p.tiles = (int)t.tiles();
   p.tiles_per_split = 0;
-  if (KC == 64) return launch_wgrad<64, 3, 4>(tmX, tmDY, p, st);
+  // two stages of 40 KB: TWO CTAs per SM (256 TMEM columns each), so one CTA's reduction epilogue runs under the other's MMAs
+  if (KC == 64) return launch_wgrad<64, 3, 2>(tmX, tmDY, p, st);
   return launch_wgrad<16, 9, 4>(tmX, tmDY, p, st);
 }
 
