@@ -236,7 +236,10 @@ conv3x3_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 // ------------------------------------------------------------------------------------------------
 // wgrad
 // ------------------------------------------------------------------------------------------------
-template <int KC, int TAPS, int STAGES>
+// RH ("row halo", 8x8-pixel tiles, TAPS = 3): the three taps of a filter row come from ONE X box of 8 rows x 10 pixels
+// (tap dx = +dx rows inside the box: LBO = one row, 8-pixel K groups 10 rows apart) instead of three shifted 8x8 boxes:
+// 26 KB instead of 40 KB through L2 per stage (the wide layers pull ~28 TB/s L2->SM with three boxes).
+template <int KC, int TAPS, int STAGES, bool RH>
 __global__ void __launch_bounds__(192, 2)
 conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                         const ConvWgradParams p) {
@@ -244,7 +247,8 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   constexpr int DYB = KP * 128;                             // one 64-channel dY block
   constexpr int A_BYTES = 2 * DYB;                          // 128 output channels
   constexpr int XB = KP * KC * 2;                           // one tap tile of X
-  constexpr int B_BYTES = TAPS * XB, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int B_BYTES = RH ? 80 * KC * 2 : TAPS * XB, STAGE_BYTES = A_BYTES + B_BYTES;
+  static_assert(!RH || TAPS == 3, "row-halo X boxes serve the three taps of one filter row");
   constexpr int N = TAPS * KC;
   constexpr int TAPGROUPS = 9 / TAPS;
   constexpr uint32_t TMEM_COLS = 256;
@@ -297,10 +301,14 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         const uint32_t a_dst = sbase + s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
         tc::tma_load_4d(a_dst, &tmDY, fb, co0, x0, y0, b0);
         tc::tma_load_4d(a_dst + DYB, &tmDY, fb, co0 + 64, x0, y0, b0);   // beyond Cout -> zero filled
+        if (RH) {
+          tc::tma_load_4d(b_dst, &tmX, fb, ci0, x0 - 1, y0 + tap0 / 3 - 1, b0);
+        } else {
 #pragma unroll
-        for (int tt = 0; tt < TAPS; ++tt) {
-          const int tap = tap0 + tt;
-          tc::tma_load_4d(b_dst + tt * XB, &tmX, fb, ci0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, b0);
+          for (int tt = 0; tt < TAPS; ++tt) {
+            const int tap = tap0 + tt;
+            tc::tma_load_4d(b_dst + tt * XB, &tmX, fb, ci0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, b0);
+          }
         }
       }
     }
@@ -319,7 +327,8 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         for (int j = 0; j < KP / 16; ++j) {
           // MN-major: LBO = stride between 64-/16-channel blocks, SBO = stride between 8-pixel groups
           const uint64_t adesc = tc::make_smem_desc(a_addr + j * 16 * 128, DYB, 8 * 128, tc::kSwizzle128);
-          const uint64_t bdesc = tc::make_smem_desc(b_addr + j * 16 * B_ROW, XB, 8 * B_ROW, B_LAYOUT);
+          const uint64_t bdesc = RH ? tc::make_smem_desc(b_addr + j * 20 * B_ROW, B_ROW, 10 * B_ROW, B_LAYOUT)
+                                    : tc::make_smem_desc(b_addr + j * 16 * B_ROW, XB, 8 * B_ROW, B_LAYOUT);
           tc::umma_bf16(tmem_base, adesc, bdesc, idesc, (it | j) != 0 ? 1u : 0u);
         }
         tc::umma_commit(tc::smem_u32(&empty_bar[s]));
@@ -426,10 +435,10 @@ static int conv3x3_fwd_bf16(const void* x, int ldx, const void* w, void* y, int 
   return -1;
 }
 
-template <int KC, int TAPS, int STAGES>
+template <int KC, int TAPS, int STAGES, bool RH = false>
 static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDY, ConvWgradParams p, cudaStream_t st) {
-  constexpr int SMEM = STAGES * (2 * 64 * 128 + TAPS * 64 * KC * 2) + 1024;
-  auto kern = conv3x3_wgrad_tc_kernel<KC, TAPS, STAGES>;
+  constexpr int SMEM = STAGES * (2 * 64 * 128 + (RH ? 80 * KC * 2 : TAPS * 64 * KC * 2)) + 1024;
+  auto kern = conv3x3_wgrad_tc_kernel<KC, TAPS, STAGES, RH>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -460,7 +469,14 @@ static int conv3x3_wgrad_bf16(const void* x, int ldx, const void* dy, int lddy, 
   const int KC = (Cin % 64 == 0) ? 64 : 16;
   const PixelTile t = choose_pixel_tile(B, H, W, 64);
   CUtensorMap tmX, tmDY;
-  if (make_act_map(&tmX, x, ldx, Cin, B, H, W, KC, t, KC == 64 ? 128 : 32)) return -1;
+  const bool row_halo = KC == 64 && t.bw == 8 && t.bh == 8 && t.bb == 1 && g_opt_conv_halo != 5;
+  if (row_halo) {
+    PixelTile tx = t;
+    tx.bw = 10;                 // 8 rows x (8 + 2) pixels: the three dx taps are row shifts inside the box
+    if (make_act_map(&tmX, x, ldx, Cin, B, H, W, KC, tx, 128)) return -1;
+  } else if (make_act_map(&tmX, x, ldx, Cin, B, H, W, KC, t, KC == 64 ? 128 : 32)) {
+    return -1;
+  }
   if (make_act_map(&tmDY, dy, lddy, Cout, B, H, W, 64, t, 128)) return -1;
   ConvWgradParams p;
   p.dw = dw;
@@ -470,6 +486,7 @@ static int conv3x3_wgrad_bf16(const void* x, int ldx, const void* dy, int lddy, 
   p.tiles = (int)t.tiles();
   p.tiles_per_split = 0;
   // two stages of 40 KB: TWO CTAs per SM (256 TMEM columns each), so one CTA's reduction epilogue runs under the other's MMAs
+  if (KC == 64 && row_halo) return launch_wgrad<64, 3, 3, true>(tmX, tmDY, p, st);
   if (KC == 64) return launch_wgrad<64, 3, 2>(tmX, tmDY, p, st);
   return launch_wgrad<16, 9, 4>(tmX, tmDY, p, st);
 }
