@@ -276,8 +276,10 @@ int conv3x3_wgrad_halo_bf16(const void* x, int ldx, const void* dy, int lddy, fl
   if (H < 8 || W < 8) return 1;
   if (Cin == 16) return conv3x3_wgrad16_halo(x, ldx, dy, lddy, dw, B, H, W, Cout, st);
   if (Cin % 64 != 0) return 1;
-  // many (ci chunk, co tile) columns with few pixel tiles each: the per-tap kernel (N = 192 per MMA, fewer atomics) wins
-  if (g_opt_conv_halo < 2 && (long long)Cin * Cout > 128LL * 256) return 1;
+  // Cout a multiple of 128: the per-tap kernel (M = 128 output channels, N = 192 per MMA, two CTAs per SM, row-halo X
+  // boxes) is not shared-memory-port bound and wins (measured 1.0-1.25 PF against 0.85-1.02 PF here); this kernel keeps
+  // the Cout = 64 layers, where the per-tap kernel would waste half of its M = 128 rows
+  if (g_opt_conv_halo < 2 && Cout % 128 == 0) return 1;
   constexpr int STAGES = 4;
   constexpr int SMEM = 1024 + STAGES * (23 * 1024 + 128 * 128);
   WgradHaloParams p;
