@@ -467,9 +467,10 @@ static int conv3x3_wgrad_bf16(const void* x, int ldx, const void* dy, int lddy, 
     if (rc <= 0) return rc;
   }
   const int KC = (Cin % 64 == 0) ? 64 : 16;
-  const PixelTile t = choose_pixel_tile(B, H, W, 64);
+  PixelTile t = choose_pixel_tile(B, H, W, 64);
   CUtensorMap tmX, tmDY;
-  const bool row_halo = KC == 64 && t.bw == 8 && t.bh == 8 && t.bb == 1 && g_opt_conv_halo != 5;
+  const bool row_halo = KC == 64 && H >= 8 && W >= 8 && g_opt_conv_halo != 5;
+  if (row_halo) t = PixelTile{8, 8, 1, (W + 7) / 8, (H + 7) / 8, B};   // 8x8-pixel tiles: the row-halo X box is 8 rows x 10 pixels
   if (row_halo) {
     PixelTile tx = t;
     tx.bw = 10;                 // 8 rows x (8 + 2) pixels: the three dx taps are row shifts inside the box
