@@ -332,8 +332,8 @@ def main_gpu(args):
                                                  "(conv3x3_halo_kernel / conv3x3_fwd_tc_kernel)",
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                     # dram__bytes_read+write per launch, ncu --set full, mean of the 8 launches in
-                    # profiles/conv_halo_r1c_ncu_summary.txt (equals the algorithmic input+output bytes of those layers +-3 %)
-                    "traffic": 2.62e8, "peak_source": which,
+                    # profiles/conv_halo_r1e_ncu_summary.txt (equals the algorithmic input+output bytes of those layers +-3 %)
+                    "traffic": 3.63e8, "peak_source": which,
                     "launches_per_step": n // 2, "kernel_ms_per_step": msk / 2,
                     "wgrad_tflops": (wg[0] / (wg[1] / 1e3) / 1e12) if wg else None,
                     "hbm_kernels": hbm, "hbm_peak_gbs": hbm_peak,

@@ -221,3 +221,28 @@ def test_tta_inference_matches_reference_fixture(golden_dir, dtype, tol):
         assert eb <= tol and et <= tol
         if dtype == "fp32":
             assert et < 0.05 * effect          # the check resolves the augmentation itself, not just the base forward
+
+
+def test_host_batch_prefetcher_round_trips():
+    """data.HostBatchPrefetcher: double-buffered pinned-host -> device staging returns every submitted batch intact and in
+    order, also when a consumer kernel is still reading the slot that is about to be refilled."""
+    from enhanced_unet_b200.data import HostBatchPrefetcher
+    pf = HostBatchPrefetcher("cuda")
+    g = torch.Generator().manual_seed(3)
+    batches = [(torch.rand(4, 3, 64, 64, generator=g).pin_memory(), torch.randint(0, 3, (4, 64, 64), generator=g).pin_memory())
+               for _ in range(5)]
+    sums = []
+    pf.submit(*batches[0])
+    for i in range(5):
+        x, t = pf.get()
+        if i + 1 < 5:
+            pf.submit(*batches[i + 1])
+        big = x.double()
+        for _ in range(20):                  # keep the compute stream busy on this slot while the next copy is in flight
+            big = big * 1.0000001
+        sums.append((x.clone(), t.clone()))
+    torch.cuda.synchronize()
+    for (x, t), (hx, ht) in zip(sums, batches):
+        assert torch.equal(x.cpu(), hx) and torch.equal(t.cpu(), ht)
+    with pytest.raises(RuntimeError):
+        pf.get()
