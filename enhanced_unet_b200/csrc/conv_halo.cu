@@ -63,7 +63,7 @@ struct HaloCfg {
   static constexpr int NACC = (2 * MT * BN <= 512) ? 2 : 1;
   static constexpr int TMEM_NEED = NACC * MT * BN;
   static constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
-  static constexpr int ASTAGES = (KC == 16) ? 3 : 2;
+  static constexpr int ASTAGES = (KC == 16 || BN == 128) ? 3 : 2;      // BN = 128: a third 44 KB halo slot (384 -> 128 at H/2: +12 %)
   static constexpr int BSTAGES = WRES ? 0 : (BN >= 128 ? 4 : 6);
   static constexpr int CH = BN >= 32 ? 32 : 16;
   static constexpr int NCHUNK = BN / CH;

@@ -487,7 +487,7 @@ static int conv3x3_wgrad_bf16(const void* x, int ldx, const void* dy, int lddy, 
   p.tiles = (int)t.tiles();
   p.tiles_per_split = 0;
   // two stages of 40 KB: TWO CTAs per SM (256 TMEM columns each), so one CTA's reduction epilogue runs under the other's MMAs
-  if (KC == 64 && row_halo) return launch_wgrad<64, 3, 3, true>(tmX, tmDY, p, st);
+  if (KC == 64 && row_halo) return launch_wgrad<64, 3, 4, true>(tmX, tmDY, p, st);   // 4 x 26 KB: still two CTAs per SM
   if (KC == 64) return launch_wgrad<64, 3, 2>(tmX, tmDY, p, st);
   return launch_wgrad<16, 9, 4>(tmX, tmDY, p, st);
 }
