@@ -26,6 +26,21 @@ static void bn_ring_smem_attr(const void* kernel, int bytes) {
   if (bytes > 48 * 1024) (void)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
+// Persistent-style grid for a grid-stride REDUCTION kernel: exactly one resident wave (SMs x blocks that fit per SM), so
+// no partially filled last wave (1184 blocks at 3 resident per SM = 2.67 waves) and 2.7x fewer end-of-block fp64 atomics.
+// (The streaming apply kernels measured 2-3 % slower with it and keep 8 blocks per SM.)
+template <typename K>
+static int one_wave_grid(K kernel, int threads, int dyn_smem, long long max_blocks) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem) != cudaSuccess || per_sm < 1) {
+    (void)cudaGetLastError();
+    per_sm = 2;
+  }
+  long long g = (long long)kNumSMs * per_sm;
+  if (g > max_blocks) g = max_blocks;
+  return (int)(g < 1 ? 1 : g);
+}
+
 static inline int ew_grid(long long items, int threads = 256) {
   long long blocks = (items + threads - 1) / threads;
   long long cap = (long long)kNumSMs * 16;
@@ -621,7 +636,9 @@ int eunet_bn_apply_relu(const void* y, int ldy, void* out, int ldo, void* pooled
   } else {
     EUNET_REQUIRE(C <= 2048 && 256 % (C / 8) == 0, "bn_apply_relu: C/8=%d must divide 256", C / 8);
     DISPATCH_DTYPE(dtype, bn_ring_smem_attr((const void*)bn_apply_relu_kernel<T, TY>, Stream8<TY, 6>::bytes(256));
-                   bn_apply_relu_kernel<T, TY><<<clamp_grid((M + 256 / (C / 8) - 1) / (256 / (C / 8)), 8), 256, Stream8<TY, 6>::bytes(256), st>>>((const TY*)y, ldy, (T*)out, ldo, M, C,
+                   const int R = 256 / (C / 8);
+                   const int grid = clamp_grid((M + R - 1) / R, 8);
+                   bn_apply_relu_kernel<T, TY><<<grid, 256, Stream8<TY, 6>::bytes(256), st>>>((const TY*)y, ldy, (T*)out, ldo, M, C,
                                                                                          scale, shift));
   }
   return check_launch("bn_apply_relu");
@@ -633,11 +650,11 @@ int eunet_bn_bwd_reduce(const void* dact, int ldd, const void* y, int ldy, int d
   EUNET_REQUIRE(C <= 2048 && 256 % (C / 8) == 0, "bn_bwd_reduce: C/8=%d must divide 256", C / 8);
   EUNET_REQUIRE(M > 0, "bn_bwd_reduce: empty tensor");
   const int R = 256 / (C / 8);
-  const int grid = clamp_grid((M + R - 1) / R, 8);
-  DISPATCH_DTYPE(dtype, bn_ring_smem_attr((const void*)bn_bwd_reduce_kernel<T, TY>, (int)(8 * 256 * kBnStages * (sizeof(T) + sizeof(TY))));
-                 bn_bwd_reduce_kernel<T, TY><<<grid, 256, 8 * 256 * kBnStages * (sizeof(T) + sizeof(TY)), (cudaStream_t)stream>>>((const T*)dact, ldd, (const TY*)y, ldy,
-                                                                                         M, C, scale, shift, mean, invstd,
-                                                                                         sums));
+  DISPATCH_DTYPE(dtype, const int smem = (int)(8 * 256 * kBnStages * (sizeof(T) + sizeof(TY)));
+                 bn_ring_smem_attr((const void*)bn_bwd_reduce_kernel<T, TY>, smem);
+                 const int grid = one_wave_grid(bn_bwd_reduce_kernel<T, TY>, 256, smem, (M + R - 1) / R);
+                 bn_bwd_reduce_kernel<T, TY><<<grid, 256, smem, (cudaStream_t)stream>>>((const T*)dact, ldd, (const TY*)y, ldy, M, C, scale,
+                                                                                     shift, mean, invstd, sums));
   return check_launch("bn_bwd_reduce");
 }
 
