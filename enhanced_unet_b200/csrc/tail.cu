@@ -464,6 +464,12 @@ static inline int ew_grid(long long items) { return clamp_grid((items + 255) / 2
 
 }  // namespace eunet
 
+namespace eunet {
+int g_opt_tail_out_tma = 1;
+int tail_out_fwd_tma(const float* d14, const void* mid, const float* scale, const float* shift, const float* w3, const float* b3,
+                     float* out, int B, int H, int W, cudaStream_t st);
+}  // namespace eunet
+
 using namespace eunet;
 
 extern "C" {
@@ -495,6 +501,10 @@ int eunet_tail_up_fwd(const float* z4, void* d1p, float* d14, int dtype, int B, 
 int eunet_tail_out_fwd(const float* d14, const void* mid, int dtype, const float* scale, const float* shift, const float* w3,
                        const float* b3, float* out, int B, int H, int W, void* stream) {
   EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "tail_out_fwd: bad shape");
+  if (dtype == EUNET_BF16 && g_opt_tail_out_tma) {
+    const int rc = tail_out_fwd_tma(d14, mid, scale, shift, w3, b3, out, B, H, W, (cudaStream_t)stream);
+    if (rc <= 0) return rc;      // launched or failed; 1 = too small, use the thread-per-pixel kernel
+  }
   DISPATCH_DTYPE(dtype, tail_ring_attr((const void*)tail_out_fwd_kernel<TY>, 3 * 128 * (64 * (int)sizeof(TY) + 16));
                  tail_out_fwd_kernel<TY><<<clamp_grid((4LL * B * H * W + 127) / 128, 4), 128, 3 * 128 * (64 * (int)sizeof(TY) + 16), (cudaStream_t)stream>>>(
                             d14, (const TY*)mid, scale, shift, w3, b3, out, B, H, W));

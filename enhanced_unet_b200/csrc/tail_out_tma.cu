@@ -1,0 +1,174 @@
+// Training-mode forward of the 2Hx2W tail after the enhance.0 convolution (reference models.py:310-313 + 337):
+//     out[b,k,p] = d1[p][k] + b3[k] + sum_c w3[k][c] * relu(mid[p][c] * scale[c] + shift[c])
+// over the RAW fp16 conv output `mid` (2.15 GB at batch 16 / 512^2): a pure stream, 128 B in and 12 B out per pixel.
+// (In inference this pass does not exist: the conv epilogue produces `out` directly, conv_halo.cu EPI = 1.)
+//
+// The thread-per-pixel kernel in tail.cu spends 88 shared-memory loads per pixel on the per-channel constants at 16 %
+// occupancy (ncu: short_scoreboard) and reaches 0.5 of the HBM roofline.  Here the roles are turned around:
+//   * two persistent CTAs per SM; warp 0 streams 128-pixel tiles of `mid` (16 KB, 128B-swizzled rows) and of the residual
+//     d14 (2 KB) through a 3-stage TMA ring;
+//   * compute warp w owns CHANNEL CHUNK w (8 channels): its 40 constants live in registers for the whole kernel, lane l
+//     walks pixels l, l+32, l+64, l+96 of the tile - one conflict-free 16-byte shared-memory load per (pixel, chunk);
+//   * the eight partial class sums of a pixel meet in a double-buffered shared-memory array; after ONE 256-thread named
+//     barrier per tile the first four warps add them, the residual and the bias and store the three logit planes with
+//     fully coalesced 128-byte rows.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "../../include/eunet.h"
+
+namespace eunet {
+
+constexpr int kToStages = 3;                       // 3 x 18 KB + 32 KB of partials = 87 KB: TWO CTAs per SM
+constexpr int kToTile = 128;                       // pixels per tile
+constexpr int kToMid = kToTile * 128;              // 16 KB
+constexpr int kToRes = kToTile * 16;               // 2 KB
+constexpr int kToStage = kToMid + kToRes;          // 18 KB (multiple of 1024)
+constexpr int kToPart = kToTile * 8 * 16;          // partial sums [pixel][chunk] float4: 16 KB per buffer
+
+struct TailOutParams {
+  const float* scale;
+  const float* shift;
+  const float* w3;
+  const float* b3;
+  float* out;
+  long long M, HW;      // pixels in total / per image (2H * 2W)
+  int tiles;
+};
+
+__global__ void __launch_bounds__(288, 2)
+tail_out_tma_kernel(const __grid_constant__ CUtensorMap tmMid, const __grid_constant__ CUtensorMap tmRes, const TailOutParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full[kToStages], empty[kToStages];
+  const uint32_t sbase = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* const gen0 = smem_raw + (sbase - tc::smem_u32(smem_raw));
+  const uint32_t part_base = sbase + kToStages * kToStage;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kToStages; ++s) { tc::mbar_init(tc::smem_u32(&full[s]), 1); tc::mbar_init(tc::smem_u32(&empty[s]), 8); }
+    tc::mbar_fence_init();
+    tc::tma_prefetch_desc(&tmMid);
+    tc::tma_prefetch_desc(&tmRes);
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
+        const uint32_t s = it % kToStages;
+        tc::mbar_wait(tc::smem_u32(&empty[s]), ((it / kToStages) & 1u) ^ 1u);
+        const uint32_t fb = tc::smem_u32(&full[s]);
+        tc::mbar_expect_tx(fb, kToStage);             // out-of-range rows of the last tile are zero-filled, bytes still count
+        tc::tma_load_2d(sbase + s * kToStage, &tmMid, fb, 0, t * kToTile);
+        tc::tma_load_2d(sbase + s * kToStage + kToMid, &tmRes, fb, 0, t * kToTile);
+      }
+    }
+  } else {
+    const int w = warp - 1;                           // channel chunk 0..7
+    const int ctid = threadIdx.x - 32;                // 0..255
+    float sc[8], sh[8], w0[8], w1[8], w2[8];
+    {
+      const F8 a = load8(p.scale + w * 8), b = load8(p.shift + w * 8);
+      const F8 x0 = load8(p.w3 + w * 8), x1 = load8(p.w3 + 64 + w * 8), x2 = load8(p.w3 + 128 + w * 8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { sc[e] = a.v[e]; sh[e] = b.v[e]; w0[e] = x0.v[e]; w1[e] = x1.v[e]; w2[e] = x2.v[e]; }
+    }
+    const float bb0 = p.b3[0], bb1 = p.b3[1], bb2 = p.b3[2];
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
+      const uint32_t s = it % kToStages;
+      const uint32_t tile = sbase + s * kToStage;
+      const uint32_t part = part_base + (it & 1u) * kToPart;
+      tc::mbar_wait(tc::smem_u32(&full[s]), (it / kToStages) & 1u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int px = lane + 32 * k;
+        uint32_t h0, h1, h2, h3;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(h0), "=r"(h1), "=r"(h2), "=r"(h3)
+                     : "r"(tile + (uint32_t)(px * 128) + ((uint32_t)(w ^ (px & 7)) << 4)));
+        const uint32_t hw[4] = {h0, h1, h2, h3};
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int e2 = 0; e2 < 4; ++e2) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[e2]));
+          const float a0 = fmaxf(fmaf(f.x, sc[2 * e2], sh[2 * e2]), 0.f), a1 = fmaxf(fmaf(f.y, sc[2 * e2 + 1], sh[2 * e2 + 1]), 0.f);
+          s0 = fmaf(a1, w0[2 * e2 + 1], fmaf(a0, w0[2 * e2], s0));
+          s1 = fmaf(a1, w1[2 * e2 + 1], fmaf(a0, w1[2 * e2], s1));
+          s2 = fmaf(a1, w2[2 * e2 + 1], fmaf(a0, w2[2 * e2], s2));
+        }
+        // partial[px][chunk]: 16-byte slot, chunk XOR-swizzled by the pixel so that the 8 lanes of a quarter-warp store
+        // (and the reducer later loads) conflict-free
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(part + (uint32_t)(px * 128) + ((uint32_t)(w ^ (px & 7)) << 4)),
+                     "f"(s0), "f"(s1), "f"(s2), "f"(0.f)
+                     : "memory");
+      }
+      tc::named_bar_sync(1, 256);                     // all partials of this tile are written; the tile itself is consumed
+      if (ctid < kToTile) {
+        const int px = ctid;
+        float s0 = bb0, s1 = bb1, s2 = bb2;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float a, b, d, pad;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(a), "=f"(b), "=f"(d), "=f"(pad)
+                       : "r"(part + (uint32_t)(px * 128) + ((uint32_t)(c ^ (px & 7)) << 4)));
+          s0 += a; s1 += b; s2 += d;
+        }
+        float r0, r1, r2, rpad;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r0), "=f"(r1), "=f"(r2), "=f"(rpad) : "r"(tile + kToMid + (uint32_t)(px * 16)));
+        const long long pix = (long long)t * kToTile + px;
+        if (pix < p.M) {
+          const long long b = pix / p.HW, hw = pix - b * p.HW;
+          float* o = p.out + b * 3 * p.HW + hw;
+          o[0] = s0 + r0;
+          o[p.HW] = s1 + r1;
+          o[2 * p.HW] = s2 + r2;
+        }
+      }
+      // the stage may be refilled once every compute warp is past its reads (the reducers read the residual last)
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tc::smem_u32(&empty[s]));
+    }
+  }
+  (void)gen0;
+}
+
+// returns 0 = launched, 1 = not applicable, < 0 = error
+int tail_out_fwd_tma(const float* d14, const void* mid, const float* scale, const float* shift, const float* w3, const float* b3,
+                     float* out, int B, int H, int W, cudaStream_t st) {
+  TailOutParams p;
+  p.scale = scale; p.shift = shift; p.w3 = w3; p.b3 = b3; p.out = out;
+  p.HW = 4LL * H * W;
+  p.M = p.HW * B;
+  if (p.M < 4 * kToTile) return 1;
+  const long long tiles = (p.M + kToTile - 1) / kToTile;
+  if (tiles > 0x7fffffffLL) return 1;
+  p.tiles = (int)tiles;
+  CUtensorMap tmMid, tmRes;
+  {
+    uint64_t dims[2] = {64ull, (uint64_t)p.M}, str[1] = {128ull};
+    uint32_t box[2] = {64u, (uint32_t)kToTile};
+    if (tc::encode_tensor_map_bf16(&tmMid, mid, 2, dims, str, box, 128)) return -1;        // fp16 bits, 2-byte elements
+  }
+  {
+    uint64_t dims[2] = {8ull, (uint64_t)p.M}, str[1] = {16ull};                           // fp32 x 4 per pixel = 8 two-byte units
+    uint32_t box[2] = {8u, (uint32_t)kToTile};
+    if (tc::encode_tensor_map_bf16(&tmRes, d14, 2, dims, str, box, 0)) return -1;
+  }
+  constexpr int SMEM = 1024 + kToStages * kToStage + 2 * kToPart;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tail_out_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    EUNET_REQUIRE(e == cudaSuccess, "tail_out_fwd: cudaFuncSetAttribute(%d): %s", SMEM, cudaGetErrorString(e));
+    configured = true;
+  }
+  const int grid = p.tiles < 2 * kNumSMs ? p.tiles : 2 * kNumSMs;   // two co-resident CTAs: one reduces / stores while the other streams
+  tail_out_tma_kernel<<<grid, 288, SMEM, st>>>(tmMid, tmRes, p);
+  return check_launch("tail_out_fwd(tma)");
+}
+
+}  // namespace eunet

@@ -415,6 +415,32 @@ def test_tail_bwd_fused_matches_separate_kernels(k, shape):
     assert nerr(dw, dw_ref) < 2e-5, nerr(dw, dw_ref)
 
 
+@pytest.mark.parametrize("variant", ["tma", "thread_per_pixel"])
+@pytest.mark.parametrize("shape", [(2, 8, 12), (1, 36, 20), (3, 64, 64), (1, 5, 13)])
+def test_tail_out_fwd(k, shape, variant):
+    """out = d1 + b3 + W3 . relu(mid * scale + shift) over the raw fp16 conv output (training-mode tail forward): the
+    TMA-pipelined persistent kernel (chunk-per-warp) and the thread-per-pixel kernel against torch fp32 on the same fp16 data.
+    shape = (B, H, W) of the HALF-resolution grid; the tensors live at 2H x 2W (ragged last tile for most shapes)."""
+    B, H, W = shape
+    M = B * 4 * H * W
+    g = torch.Generator(device="cuda").manual_seed(H * 31 + W)
+    mid = (torch.randn(M, 64, device="cuda", generator=g) * 2).to(torch.float16)
+    d14 = torch.randn(M, 4, device="cuda", generator=g)
+    sc, sh = torch.rand(64, device="cuda", generator=g) + 0.5, torch.randn(64, device="cuda", generator=g)
+    w3, b3 = (torch.randn(3, 64, device="cuda", generator=g) / 8).contiguous(), torch.randn(3, device="cuda", generator=g)
+    out = torch.full((B, 3, 2 * H, 2 * W), 9.0, device="cuda")
+    k.set_option("tail_out_tma", 1 if variant == "tma" else 0)
+    try:
+        k.call("eunet_tail_out_fwd", d14.data_ptr(), mid.data_ptr(), k.BF16, sc.data_ptr(), sh.data_ptr(), w3.data_ptr(), b3.data_ptr(),
+               out.data_ptr(), B, H, W)
+        torch.cuda.synchronize()
+    finally:
+        k.set_option("tail_out_tma", 1)
+    a = torch.relu(mid.float() * sc + sh)
+    want = (d14[:, :3] + b3 + a @ w3.t()).reshape(B, 2 * H, 2 * W, 3).permute(0, 3, 1, 2)
+    assert nerr(out, want) < 1e-5
+
+
 def test_pack_input_and_padded_weights(k):
     g = torch.Generator().manual_seed(4)
     x = torch.rand(2, 3, 8, 8, generator=g)
