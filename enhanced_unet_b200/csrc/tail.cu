@@ -468,6 +468,8 @@ namespace eunet {
 int g_opt_tail_out_tma = 1;
 int tail_out_fwd_tma(const float* d14, const void* mid, const float* scale, const float* shift, const float* w3, const float* b3,
                      float* out, int B, int H, int W, cudaStream_t st);
+int tail_bwd_reduce_tma(const float* dout4, const void* mid, const float* scale, const float* shift, const float* mean,
+                        const float* invstd, const float* w3, double* acc, int B, int H, int W, cudaStream_t st);
 }  // namespace eunet
 
 using namespace eunet;
@@ -515,6 +517,10 @@ int eunet_tail_bwd_reduce(const float* dout, const void* mid, int dtype, const f
                           const float* mean, const float* invstd, const float* w3, double* acc, int B, int H, int W,
                           void* stream) {
   EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "tail_bwd_reduce: bad shape");
+  if (dtype == EUNET_BF16 && g_opt_tail_out_tma) {
+    const int rc = tail_bwd_reduce_tma(dout, mid, scale, shift, mean, invstd, w3, acc, B, H, W, (cudaStream_t)stream);
+    if (rc <= 0) return rc;      // launched or failed; 1 = too small, use the ring kernel
+  }
   DISPATCH_DTYPE(dtype, tail_ring_attr((const void*)tail_bwd_reduce_kernel<TY>, Stream8<TY, kTailStages>::bytes(256) + Stream4f<kTailStages>::bytes(256));
                  tail_bwd_reduce_kernel<TY><<<rows_grid(4LL * B * H * W), 256, Stream8<TY, kTailStages>::bytes(256) + Stream4f<kTailStages>::bytes(256), (cudaStream_t)stream>>>(
                             dout, (const TY*)mid, scale, shift, mean, invstd, w3, acc, B, H, W));

@@ -171,4 +171,161 @@ int tail_out_fwd_tma(const float* d14, const void* mid, const float* scale, cons
   return check_launch("tail_out_fwd(tma)");
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Backward pass 1 over (dout4, mid) in the same style: BN sums + enhance.3 weight / bias gradients
+// (acc layout as tail_bwd_reduce_kernel: [0,64) sum g', [64,128) sum g' xhat, [128,320) dW3[k][c], [320,323) db3[k]).
+// Channel chunk per warp: the masked sums P_k = sum m g_k, Q_k = sum m g_k xc (see tail.cu) accumulate in registers over
+// all pixels a lane sees - no per-tile synchronisation at all; one shuffle tree + fp64 atomics per warp at the end.
+// ------------------------------------------------------------------------------------------------------------
+struct TailReduceParams {
+  const float* scale;
+  const float* shift;
+  const float* mean;
+  const float* invstd;
+  const float* w3;
+  double* acc;
+  long long M;
+  int tiles;
+};
+
+constexpr int kTrStages = 4;      // 4 x 18 KB = 72 KB: two CTAs per SM
+
+__global__ void __launch_bounds__(288, 2)
+tail_reduce_tma_kernel(const __grid_constant__ CUtensorMap tmMid, const __grid_constant__ CUtensorMap tmG, const TailReduceParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full[kTrStages], empty[kTrStages];
+  const uint32_t sbase = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kTrStages; ++s) { tc::mbar_init(tc::smem_u32(&full[s]), 1); tc::mbar_init(tc::smem_u32(&empty[s]), 8); }
+    tc::mbar_fence_init();
+    tc::tma_prefetch_desc(&tmMid);
+    tc::tma_prefetch_desc(&tmG);
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
+        const uint32_t s = it % kTrStages;
+        tc::mbar_wait(tc::smem_u32(&empty[s]), ((it / kTrStages) & 1u) ^ 1u);
+        const uint32_t fb = tc::smem_u32(&full[s]);
+        tc::mbar_expect_tx(fb, kToStage);
+        tc::tma_load_2d(sbase + s * kToStage, &tmMid, fb, 0, t * kToTile);
+        tc::tma_load_2d(sbase + s * kToStage + kToMid, &tmG, fb, 0, t * kToTile);   // rows past M are zero-filled: g = 0
+      }
+    }
+  } else {
+    const int w = warp - 1;                           // channel chunk 0..7
+    float sc[8], mu[8], beta[8], P[3][8], Q[3][8], db0 = 0.f, db1 = 0.f, db2 = 0.f;
+    {
+      const F8 a = load8(p.scale + w * 8), b = load8(p.shift + w * 8), m = load8(p.mean + w * 8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        sc[e] = a.v[e]; mu[e] = m.v[e];
+        beta[e] = fmaf(a.v[e], m.v[e], b.v[e]);
+        P[0][e] = P[1][e] = P[2][e] = Q[0][e] = Q[1][e] = Q[2][e] = 0.f;
+      }
+    }
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
+      const uint32_t s = it % kTrStages;
+      const uint32_t tile = sbase + s * kToStage;
+      tc::mbar_wait(tc::smem_u32(&full[s]), (it / kTrStages) & 1u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int px = lane + 32 * k;
+        uint32_t h0, h1, h2, h3;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(h0), "=r"(h1), "=r"(h2), "=r"(h3)
+                     : "r"(tile + (uint32_t)(px * 128) + ((uint32_t)(w ^ (px & 7)) << 4)));
+        float g0, g1, g2, gpad;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(g0), "=f"(g1), "=f"(g2), "=f"(gpad) : "r"(tile + kToMid + (uint32_t)(px * 16)));
+        const uint32_t hw[4] = {h0, h1, h2, h3};
+#pragma unroll
+        for (int e2 = 0; e2 < 4; ++e2) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[e2]));
+          const float v[2] = {f.x, f.y};
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int e = 2 * e2 + h;
+            const float xc = v[h] - mu[e];
+            if (fmaf(xc, sc[e], beta[e]) > 0.f) {
+              P[0][e] += g0; P[1][e] += g1; P[2][e] += g2;
+              Q[0][e] = fmaf(g0, xc, Q[0][e]); Q[1][e] = fmaf(g1, xc, Q[1][e]); Q[2][e] = fmaf(g2, xc, Q[2][e]);
+            }
+          }
+        }
+        if (w == 0) { db0 += g0; db1 += g1; db2 += g2; }
+      }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tc::smem_u32(&empty[s]));
+    }
+    // per-channel totals over the warp's 32 lanes, then the five reductions of this chunk
+    const F8 is = load8(p.invstd + w * 8), x0 = load8(p.w3 + w * 8), x1 = load8(p.w3 + 64 + w * 8), x2 = load8(p.w3 + 128 + w * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { P[k][e] = warp_sum(P[k][e]); Q[k][e] = warp_sum(Q[k][e]); }
+    }
+    if (w == 0) { db0 = warp_sum(db0); db1 = warp_sum(db1); db2 = warp_sum(db2); }
+    if (lane < 8) {
+      const int e = lane, c = w * 8 + e;
+      // select this lane's channel without dynamic register indexing
+      float p0 = 0.f, p1 = 0.f, p2 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, sce = 0.f, be = 0.f, ise = 0.f, wa = 0.f, wb = 0.f, wc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i == e) {
+          p0 = P[0][i]; p1 = P[1][i]; p2 = P[2][i]; q0 = Q[0][i]; q1 = Q[1][i]; q2 = Q[2][i];
+          sce = sc[i]; be = beta[i]; ise = is.v[i]; wa = x0.v[i]; wb = x1.v[i]; wc = x2.v[i];
+        }
+      atomicAdd(p.acc + c, (double)(wa * p0 + wb * p1 + wc * p2));
+      atomicAdd(p.acc + 64 + c, (double)(ise * (wa * q0 + wb * q1 + wc * q2)));
+      atomicAdd(p.acc + 128 + c, (double)fmaf(sce, q0, be * p0));
+      atomicAdd(p.acc + 192 + c, (double)fmaf(sce, q1, be * p1));
+      atomicAdd(p.acc + 256 + c, (double)fmaf(sce, q2, be * p2));
+    }
+    if (w == 0 && lane == 0) {
+      atomicAdd(p.acc + 320, (double)db0);
+      atomicAdd(p.acc + 321, (double)db1);
+      atomicAdd(p.acc + 322, (double)db2);
+    }
+  }
+}
+
+// returns 0 = launched, 1 = not applicable, < 0 = error
+int tail_bwd_reduce_tma(const float* dout4, const void* mid, const float* scale, const float* shift, const float* mean,
+                        const float* invstd, const float* w3, double* acc, int B, int H, int W, cudaStream_t st) {
+  TailReduceParams p;
+  p.scale = scale; p.shift = shift; p.mean = mean; p.invstd = invstd; p.w3 = w3; p.acc = acc;
+  p.M = 4LL * H * W * B;
+  if (p.M < 4 * kToTile) return 1;
+  const long long tiles = (p.M + kToTile - 1) / kToTile;
+  if (tiles > 0x7fffffffLL) return 1;
+  p.tiles = (int)tiles;
+  CUtensorMap tmMid, tmG;
+  {
+    uint64_t dims[2] = {64ull, (uint64_t)p.M}, str[1] = {128ull};
+    uint32_t box[2] = {64u, (uint32_t)kToTile};
+    if (tc::encode_tensor_map_bf16(&tmMid, mid, 2, dims, str, box, 128)) return -1;
+  }
+  {
+    uint64_t dims[2] = {8ull, (uint64_t)p.M}, str[1] = {16ull};
+    uint32_t box[2] = {8u, (uint32_t)kToTile};
+    if (tc::encode_tensor_map_bf16(&tmG, dout4, 2, dims, str, box, 0)) return -1;
+  }
+  constexpr int SMEM = 1024 + kTrStages * kToStage;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tail_reduce_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    EUNET_REQUIRE(e == cudaSuccess, "tail_bwd_reduce: cudaFuncSetAttribute(%d): %s", SMEM, cudaGetErrorString(e));
+    configured = true;
+  }
+  const int grid = p.tiles < 2 * kNumSMs ? p.tiles : 2 * kNumSMs;
+  tail_reduce_tma_kernel<<<grid, 288, SMEM, st>>>(tmMid, tmG, p);
+  return check_launch("tail_bwd_reduce(tma)");
+}
+
 }  // namespace eunet
