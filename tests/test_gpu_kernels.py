@@ -102,7 +102,7 @@ def test_maxpool_fwd_bwd(k, dtn, shape):
 
 
 @pytest.mark.parametrize("dtn", ["fp32", "bf16"])
-@pytest.mark.parametrize("shape", [(2, 64, 5, 7), (1, 16, 1, 1), (1, 8, 1, 4), (2, 128, 8, 8)])
+@pytest.mark.parametrize("shape", [(2, 64, 5, 7), (1, 16, 1, 1), (1, 8, 1, 4), (2, 128, 8, 8), (2, 64, 12, 20), (1, 128, 6, 9), (3, 192, 4, 8)])
 def test_upsample_fwd_bwd(k, dtn, shape):
     B, C, H, W = shape
     dt = DT[dtn]
