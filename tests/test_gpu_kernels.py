@@ -441,6 +441,30 @@ def test_tail_out_fwd(k, shape, variant):
     assert nerr(out, want) < 1e-5
 
 
+@pytest.mark.parametrize("case", [(64, 5000, 64, 0), (128, 3333, 192, 64), (512, 1100, 768, 256), (256, 1024, 256, 0)])
+def test_bn_bwd_reduce_on_channel_slices(k, case):
+    """bn_bwd_reduce (masked sums, predicated accumulation, one resident wave) against a torch fp64 evaluation of sum g' /
+    sum g' xhat; dact is a channel slice of a wider buffer (the concat gradient buffers), M is not a multiple of anything."""
+    C, M, ld, off = case
+    g = torch.Generator(device="cuda").manual_seed(C + M)
+    y = (torch.randn(M, C, device="cuda", generator=g) * 1.3 + 0.4).to(torch.float16)
+    buf = torch.randn(M, ld, device="cuda", generator=g).to(torch.bfloat16)
+    dact = buf[:, off:off + C]
+    mean = y.float().mean(0)
+    invstd = 1.0 / torch.sqrt(y.float().var(0, unbiased=False) + 1e-5)
+    scale = ((torch.rand(C, device="cuda", generator=g) + 0.5) * invstd).contiguous()
+    shift = (torch.randn(C, device="cuda", generator=g) * 0.3 - mean * scale).contiguous()
+    sums = torch.zeros(2 * C, dtype=torch.float64, device="cuda")
+    k.call("eunet_bn_bwd_reduce", dact.data_ptr(), ld, y.data_ptr(), C, k.BF16, M, C, scale.data_ptr(), shift.data_ptr(),
+           mean.data_ptr(), invstd.data_ptr(), sums.data_ptr())
+    torch.cuda.synchronize()
+    yd, dd = y.double(), dact.double()
+    mask = (yd * scale.double() + shift.double()) > 0
+    gp = torch.where(mask, dd, torch.zeros_like(dd))
+    want = torch.cat([gp.sum(0), (gp * (yd - mean.double()) * invstd.double()).sum(0)])
+    assert nerr(sums, want) < 2e-5, nerr(sums, want)
+
+
 def test_pack_input_and_padded_weights(k):
     g = torch.Generator().manual_seed(4)
     x = torch.rand(2, 3, 8, 8, generator=g)
