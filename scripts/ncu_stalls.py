@@ -20,8 +20,8 @@ for path in sys.argv[1:]:
         seen.add(key)
         g = lambda k: d[idx[k]] if k in idx else "?"
         print(f"--- {name} grid {d[idx['Grid Size']]} block {d[idx['Block Size']]}")
-        print(f"    time {g('gpu__time_duration.sum')} {units[idx['gpu__time_duration.sum']]}  dram rd {g('dram__bytes_read.sum')} wr {g('dram__bytes_write.sum')} "
-              f"{units[idx['dram__bytes_read.sum']]}  dram% {g('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')}")
+        print(f"    time {g('gpu__time_duration.sum')} {units[idx['gpu__time_duration.sum']]}  dram rd {g('dram__bytes_read.sum')} {units[idx['dram__bytes_read.sum']]} "
+              f"wr {g('dram__bytes_write.sum')} {units[idx['dram__bytes_write.sum']]}  dram% {g('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')}")
         print(f"    issue_active% {g('smsp__issue_active.avg.pct_of_peak_sustained_active')}  warps_active% {g('sm__warps_active.avg.pct_of_peak_sustained_active')} "
               f"regs {g('launch__registers_per_thread')}  l1tex% {g('l1tex__throughput.avg.pct_of_peak_sustained_elapsed')} lts% {g('lts__throughput.avg.pct_of_peak_sustained_elapsed')} "
               f"sm% {g('sm__throughput.avg.pct_of_peak_sustained_elapsed')}")
