@@ -21,7 +21,6 @@ struct WgradHaloParams {
   float* dw;
   int B, H, W, Cin, Cout;
   int blocks_x, blocks_y, tiles, tiles_per_split, ci_chunks;
-  int debug_skip_store;
 };
 
 template <int STAGES>
@@ -111,7 +110,7 @@ conv3x3_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
         uint32_t raw[32];
         tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(pr * 64 + c0), raw);
         tc::tmem_ld_wait();
-        if (live && !p.debug_skip_store) {
+        if (live) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int co = co0 + c0 + i;
@@ -238,7 +237,6 @@ static int conv3x3_wgrad16_halo(const void* x, int ldx, const void* dy, int lddy
   if (tiles > 0x7fffffffLL) return 1;
   p.tiles = (int)tiles;
   p.ci_chunks = 1;
-  p.debug_skip_store = 0;
   const int co_tiles = (Cout + 63) / 64;
   int splits = kNumSMs / co_tiles;          // one CTA per SM (177 KB of stages each)
   if (splits > p.tiles) splits = p.tiles;
@@ -290,7 +288,6 @@ int conv3x3_wgrad_halo_bf16(const void* x, int ldx, const void* dy, int lddy, fl
   if (tiles > 0x7fffffffLL) return 1;
   p.tiles = (int)tiles;
   p.ci_chunks = Cin / 64;
-  p.debug_skip_store = (g_opt_conv_halo == 3);
   const int co_tiles = (Cout + 63) / 64;
   const int cols = p.ci_chunks * co_tiles;
   int splits = (2 * kNumSMs) / cols;   // cols * splits <= 2 CTAs per SM: never spill into a third, nearly empty wave
