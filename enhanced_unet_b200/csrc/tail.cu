@@ -468,6 +468,7 @@ namespace eunet {
 int g_opt_tail_out_tma = 1;
 int tail_out_fwd_tma(const float* d14, const void* mid, const float* scale, const float* shift, const float* w3, const float* b3,
                      float* out, int B, int H, int W, cudaStream_t st);
+int tail_dec1_fwd_tma(const void* d2, int ldd2, const float* w1, const float* b1, float* z4, long long M, cudaStream_t st);
 int tail_bwd_reduce_tma(const float* dout4, const void* mid, const float* scale, const float* shift, const float* mean,
                         const float* invstd, const float* w3, double* acc, int B, int H, int W, cudaStream_t st);
 }  // namespace eunet
@@ -479,6 +480,10 @@ extern "C" {
 int eunet_tail_dec1_fwd(const void* d2, int ldd2, int dtype, const float* w1, const float* b1, float* z4, long long M,
                         void* stream) {
   EUNET_REQUIRE(M > 0 && ldd2 >= 64 && (ldd2 & 7) == 0, "tail_dec1_fwd: bad shape M=%lld ld=%d", M, ldd2);
+  if (dtype == EUNET_BF16 && g_opt_tail_out_tma) {
+    const int rc = tail_dec1_fwd_tma(d2, ldd2, w1, b1, z4, M, (cudaStream_t)stream);
+    if (rc <= 0) return rc;      // launched or failed; 1 = too small, 8-lanes-per-pixel kernel below
+  }
   DISPATCH_DTYPE(dtype, tail_dec1_fwd_kernel<T><<<rows_grid(M), 256, 0, (cudaStream_t)stream>>>((const T*)d2, ldd2, w1, b1, z4, M));
   return check_launch("tail_dec1_fwd");
 }

@@ -37,6 +37,9 @@ struct TailOutParams {
   int tiles;
 };
 
+// DEC1 = true: the same streaming layout for z = dec1(d2) (1x1, 64 -> 3, models.py:212, evaluated at HxW): bf16 input rows
+// (any row stride), no affine / ReLU / residual, output fp32 [pixels][4] (z4) instead of NCHW planes.
+template <bool DEC1>
 __global__ void __launch_bounds__(288, 2)
 tail_out_tma_kernel(const __grid_constant__ CUtensorMap tmMid, const __grid_constant__ CUtensorMap tmRes, const TailOutParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -61,9 +64,9 @@ tail_out_tma_kernel(const __grid_constant__ CUtensorMap tmMid, const __grid_cons
         const uint32_t s = it % kToStages;
         tc::mbar_wait(tc::smem_u32(&empty[s]), ((it / kToStages) & 1u) ^ 1u);
         const uint32_t fb = tc::smem_u32(&full[s]);
-        tc::mbar_expect_tx(fb, kToStage);             // out-of-range rows of the last tile are zero-filled, bytes still count
+        tc::mbar_expect_tx(fb, DEC1 ? kToMid : kToStage);   // out-of-range rows of the last tile are zero-filled, bytes still count
         tc::tma_load_2d(sbase + s * kToStage, &tmMid, fb, 0, t * kToTile);
-        tc::tma_load_2d(sbase + s * kToStage + kToMid, &tmRes, fb, 0, t * kToTile);
+        if (!DEC1) tc::tma_load_2d(sbase + s * kToStage + kToMid, &tmRes, fb, 0, t * kToTile);
       }
     }
   } else {
@@ -71,10 +74,14 @@ tail_out_tma_kernel(const __grid_constant__ CUtensorMap tmMid, const __grid_cons
     const int ctid = threadIdx.x - 32;                // 0..255
     float sc[8], sh[8], w0[8], w1[8], w2[8];
     {
-      const F8 a = load8(p.scale + w * 8), b = load8(p.shift + w * 8);
       const F8 x0 = load8(p.w3 + w * 8), x1 = load8(p.w3 + 64 + w * 8), x2 = load8(p.w3 + 128 + w * 8);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { sc[e] = a.v[e]; sh[e] = b.v[e]; w0[e] = x0.v[e]; w1[e] = x1.v[e]; w2[e] = x2.v[e]; }
+      for (int e = 0; e < 8; ++e) { sc[e] = 1.f; sh[e] = 0.f; w0[e] = x0.v[e]; w1[e] = x1.v[e]; w2[e] = x2.v[e]; }
+      if (!DEC1) {
+        const F8 a = load8(p.scale + w * 8), b = load8(p.shift + w * 8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { sc[e] = a.v[e]; sh[e] = b.v[e]; }
+      }
     }
     const float bb0 = p.b3[0], bb1 = p.b3[1], bb2 = p.b3[2];
     uint32_t it = 0;
@@ -94,8 +101,15 @@ tail_out_tma_kernel(const __grid_constant__ CUtensorMap tmMid, const __grid_cons
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int e2 = 0; e2 < 4; ++e2) {
-          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[e2]));
-          const float a0 = fmaxf(fmaf(f.x, sc[2 * e2], sh[2 * e2]), 0.f), a1 = fmaxf(fmaf(f.y, sc[2 * e2 + 1], sh[2 * e2 + 1]), 0.f);
+          float a0, a1;
+          if (DEC1) {      // bf16 activations, plain dot products
+            a0 = __uint_as_float(hw[e2] << 16);
+            a1 = __uint_as_float(hw[e2] & 0xffff0000u);
+          } else {         // raw fp16 conv outputs: BN affine + ReLU first
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[e2]));
+            a0 = fmaxf(fmaf(f.x, sc[2 * e2], sh[2 * e2]), 0.f);
+            a1 = fmaxf(fmaf(f.y, sc[2 * e2 + 1], sh[2 * e2 + 1]), 0.f);
+          }
           s0 = fmaf(a1, w0[2 * e2 + 1], fmaf(a0, w0[2 * e2], s0));
           s1 = fmaf(a1, w1[2 * e2 + 1], fmaf(a0, w1[2 * e2], s1));
           s2 = fmaf(a1, w2[2 * e2 + 1], fmaf(a0, w2[2 * e2], s2));
@@ -118,15 +132,19 @@ tail_out_tma_kernel(const __grid_constant__ CUtensorMap tmMid, const __grid_cons
                        : "r"(part + (uint32_t)(px * 128) + ((uint32_t)(c ^ (px & 7)) << 4)));
           s0 += a; s1 += b; s2 += d;
         }
-        float r0, r1, r2, rpad;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r0), "=f"(r1), "=f"(r2), "=f"(rpad) : "r"(tile + kToMid + (uint32_t)(px * 16)));
         const long long pix = (long long)t * kToTile + px;
-        if (pix < p.M) {
-          const long long b = pix / p.HW, hw = pix - b * p.HW;
-          float* o = p.out + b * 3 * p.HW + hw;
-          o[0] = s0 + r0;
-          o[p.HW] = s1 + r1;
-          o[2 * p.HW] = s2 + r2;
+        if (DEC1) {
+          if (pix < p.M) reinterpret_cast<float4*>(p.out)[pix] = make_float4(s0, s1, s2, 0.f);
+        } else {
+          float r0, r1, r2, rpad;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r0), "=f"(r1), "=f"(r2), "=f"(rpad) : "r"(tile + kToMid + (uint32_t)(px * 16)));
+          if (pix < p.M) {
+            const long long b = pix / p.HW, hw = pix - b * p.HW;
+            float* o = p.out + b * 3 * p.HW + hw;
+            o[0] = s0 + r0;
+            o[p.HW] = s1 + r1;
+            o[2 * p.HW] = s2 + r2;
+          }
         }
       }
       // the stage may be refilled once every compute warp is past its reads (the reducers read the residual last)
@@ -162,13 +180,41 @@ int tail_out_fwd_tma(const float* d14, const void* mid, const float* scale, cons
   constexpr int SMEM = 1024 + kToStages * kToStage + 2 * kToPart;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tail_out_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaError_t e = cudaFuncSetAttribute(tail_out_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     EUNET_REQUIRE(e == cudaSuccess, "tail_out_fwd: cudaFuncSetAttribute(%d): %s", SMEM, cudaGetErrorString(e));
     configured = true;
   }
   const int grid = p.tiles < 2 * kNumSMs ? p.tiles : 2 * kNumSMs;   // two co-resident CTAs: one reduces / stores while the other streams
-  tail_out_tma_kernel<<<grid, 288, SMEM, st>>>(tmMid, tmRes, p);
+  tail_out_tma_kernel<false><<<grid, 288, SMEM, st>>>(tmMid, tmRes, p);
   return check_launch("tail_out_fwd(tma)");
+}
+
+// z4 = dec1(d2): returns 0 = launched, 1 = not applicable, < 0 = error
+int tail_dec1_fwd_tma(const void* d2, int ldd2, const float* w1, const float* b1, float* z4, long long M, cudaStream_t st) {
+  TailOutParams p;
+  p.scale = nullptr; p.shift = nullptr; p.w3 = w1; p.b3 = b1; p.out = z4;
+  p.HW = 1;
+  p.M = M;
+  if (M < 4 * kToTile) return 1;
+  const long long tiles = (M + kToTile - 1) / kToTile;
+  if (tiles > 0x7fffffffLL) return 1;
+  p.tiles = (int)tiles;
+  CUtensorMap tmIn;
+  {
+    uint64_t dims[2] = {64ull, (uint64_t)M}, str[1] = {(uint64_t)ldd2 * 2};
+    uint32_t box[2] = {64u, (uint32_t)kToTile};
+    if (tc::encode_tensor_map_bf16(&tmIn, d2, 2, dims, str, box, 128)) return -1;
+  }
+  constexpr int SMEM = 1024 + kToStages * kToStage + 2 * kToPart;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tail_out_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    EUNET_REQUIRE(e == cudaSuccess, "tail_dec1_fwd: cudaFuncSetAttribute(%d): %s", SMEM, cudaGetErrorString(e));
+    configured = true;
+  }
+  const int grid = p.tiles < 2 * kNumSMs ? p.tiles : 2 * kNumSMs;
+  tail_out_tma_kernel<true><<<grid, 288, SMEM, st>>>(tmIn, tmIn, p);
+  return check_launch("tail_dec1_fwd(tma)");
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -465,6 +465,22 @@ def test_bn_bwd_reduce_on_channel_slices(k, case):
     assert nerr(sums, want) < 2e-5, nerr(sums, want)
 
 
+@pytest.mark.parametrize("case", [(5000, 64, 0), (777, 192, 128), (300, 64, 0)])
+def test_tail_dec1_fwd(k, case):
+    """z = dec1(d2) (1x1, 64 -> 3) on bf16 rows that may be a channel slice of a wider buffer: TMA-pipelined kernel for
+    M >= 512 pixels, the 8-lanes-per-pixel kernel below that; against torch fp32 on the same bf16 data."""
+    M, ld, off = case
+    g = torch.Generator(device="cuda").manual_seed(M)
+    buf = torch.randn(M, ld, device="cuda", generator=g).to(torch.bfloat16)
+    d2 = buf[:, off:off + 64]
+    w1, b1 = (torch.randn(3, 64, device="cuda", generator=g) / 8).contiguous(), torch.randn(3, device="cuda", generator=g)
+    z4 = torch.full((M, 4), 7.0, device="cuda")
+    k.call("eunet_tail_dec1_fwd", d2.data_ptr(), ld, k.BF16, w1.data_ptr(), b1.data_ptr(), z4.data_ptr(), M)
+    torch.cuda.synchronize()
+    want = d2.float() @ w1.t() + b1
+    assert nerr(z4[:, :3], want) < 1e-5 and torch.all(z4[:, 3] == 0)
+
+
 def test_pack_input_and_padded_weights(k):
     g = torch.Generator().manual_seed(4)
     x = torch.rand(2, 3, 8, 8, generator=g)
