@@ -469,6 +469,8 @@ int g_opt_tail_out_tma = 1;
 int tail_out_fwd_tma(const float* d14, const void* mid, const float* scale, const float* shift, const float* w3, const float* b3,
                      float* out, int B, int H, int W, cudaStream_t st);
 int tail_dec1_fwd_tma(const void* d2, int ldd2, const float* w1, const float* b1, float* z4, long long M, cudaStream_t st);
+int tail_dec1_bwd_tma(const float* dz4, const void* d2, int ldd2, void* dd2, int lddd2, const float* w1, double* acc, long long M,
+                      cudaStream_t st);
 int tail_bwd_reduce_tma(const float* dout4, const void* mid, const float* scale, const float* shift, const float* mean,
                         const float* invstd, const float* w3, double* acc, int B, int H, int W, cudaStream_t st);
 }  // namespace eunet
@@ -554,6 +556,10 @@ int eunet_tail_up_bwd(const void* dd1p, int dtype, int dd1_stride, const float* 
 int eunet_tail_dec1_bwd(const float* dz4, const void* d2, int ldd2, void* dd2, int lddd2, int dtype, const float* w1,
                         double* acc, long long M, void* stream) {
   EUNET_REQUIRE(M > 0 && ldd2 >= 64 && lddd2 >= 64, "tail_dec1_bwd: bad shape");
+  if (dtype == EUNET_BF16 && g_opt_tail_out_tma && (ldd2 & 7) == 0 && (lddd2 & 7) == 0) {
+    const int rc = tail_dec1_bwd_tma(dz4, d2, ldd2, dd2, lddd2, w1, acc, M, (cudaStream_t)stream);
+    if (rc <= 0) return rc;      // launched or failed; 1 = too small, 8-lanes-per-pixel kernel below
+  }
   DISPATCH_DTYPE(dtype, tail_dec1_bwd_kernel<T><<<rows_grid(M), 256, 0, (cudaStream_t)stream>>>(dz4, (const T*)d2, ldd2, (T*)dd2,
                                                                                                lddd2, w1, acc, M));
   return check_launch("tail_dec1_bwd");

@@ -374,4 +374,158 @@ int tail_bwd_reduce_tma(const float* dout4, const void* mid, const float* scale,
   return check_launch("tail_bwd_reduce(tma)");
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// dec1 backward in the same style: dd2[p][c] = sum_k dz[p][k] w1[k][c] (bf16, any row stride, written with a TMA tensor
+// store from a swizzled staging tile), dW1[k][c] += dz[p][k] d2[p][c] and db1[k] += dz[p][k] in registers
+// (acc layout as tail_dec1_bwd_kernel: [0,192) dW1[k][c], [192,195) db1).
+// ------------------------------------------------------------------------------------------------------------
+struct Dec1BwdParams {
+  const float* w1;
+  double* acc;
+  int tiles;
+};
+
+__global__ void __launch_bounds__(288, 2)
+tail_dec1_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmD2, const __grid_constant__ CUtensorMap tmDz,
+                         const __grid_constant__ CUtensorMap tmOut, const Dec1BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full[kToStages], empty[kToStages];
+  const uint32_t sbase = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t out_base = sbase + kToStages * kToStage;           // 2 x 16 KB staging, 1024-byte aligned
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kToStages; ++s) { tc::mbar_init(tc::smem_u32(&full[s]), 1); tc::mbar_init(tc::smem_u32(&empty[s]), 8); }
+    tc::mbar_fence_init();
+    tc::tma_prefetch_desc(&tmD2);
+    tc::tma_prefetch_desc(&tmDz);
+    tc::tma_prefetch_desc(&tmOut);
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
+        const uint32_t s = it % kToStages;
+        tc::mbar_wait(tc::smem_u32(&empty[s]), ((it / kToStages) & 1u) ^ 1u);
+        const uint32_t fb = tc::smem_u32(&full[s]);
+        tc::mbar_expect_tx(fb, kToStage);
+        tc::tma_load_2d(sbase + s * kToStage, &tmD2, fb, 0, t * kToTile);
+        tc::tma_load_2d(sbase + s * kToStage + kToMid, &tmDz, fb, 0, t * kToTile);      // rows past M: zero fill (dz = 0)
+      }
+    }
+  } else {
+    const int w = warp - 1;
+    const int ctid = threadIdx.x - 32;
+    float w0[8], w1[8], w2[8], dw0[8], dw1[8], dw2[8], db0 = 0.f, db1 = 0.f, db2 = 0.f;
+    {
+      const F8 x0 = load8(p.w1 + w * 8), x1 = load8(p.w1 + 64 + w * 8), x2 = load8(p.w1 + 128 + w * 8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { w0[e] = x0.v[e]; w1[e] = x1.v[e]; w2[e] = x2.v[e]; dw0[e] = dw1[e] = dw2[e] = 0.f; }
+    }
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
+      const uint32_t s = it % kToStages;
+      const uint32_t tile = sbase + s * kToStage;
+      const uint32_t stg = out_base + (it & 1u) * kToMid;
+      tc::mbar_wait(tc::smem_u32(&full[s]), (it / kToStages) & 1u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int px = lane + 32 * k;
+        const uint32_t off = (uint32_t)(px * 128) + ((uint32_t)(w ^ (px & 7)) << 4);
+        uint32_t h0, h1, h2, h3;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(h0), "=r"(h1), "=r"(h2), "=r"(h3) : "r"(tile + off));
+        float z0, z1, z2, zpad;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(z0), "=f"(z1), "=f"(z2), "=f"(zpad) : "r"(tile + kToMid + (uint32_t)(px * 16)));
+        const uint32_t hw[4] = {h0, h1, h2, h3};
+        float o[8];
+#pragma unroll
+        for (int e2 = 0; e2 < 4; ++e2) {
+          const float v[2] = {__uint_as_float(hw[e2] << 16), __uint_as_float(hw[e2] & 0xffff0000u)};
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int e = 2 * e2 + h;
+            o[e] = z0 * w0[e] + z1 * w1[e] + z2 * w2[e];
+            dw0[e] = fmaf(z0, v[h], dw0[e]);
+            dw1[e] = fmaf(z1, v[h], dw1[e]);
+            dw2[e] = fmaf(z2, v[h], dw2[e]);
+          }
+        }
+        if (w == 0) { db0 += z0; db1 += z1; db2 += z2; }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + off), "r"(pack_bf16x2(o[0], o[1])), "r"(pack_bf16x2(o[2], o[3])),
+                     "r"(pack_bf16x2(o[4], o[5])), "r"(pack_bf16x2(o[6], o[7]))
+                     : "memory");
+      }
+      // input stage consumed; the staged gradient tile goes out with one tensor store (rows past M are clipped).  The
+      // issuer first waits until the store of tile it-1 has finished reading its buffer, which tile it+1 overwrites.
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tc::smem_u32(&empty[s]));
+      if (ctid == 0) tc::tma_store_wait_read<0>();
+      tc::named_bar_sync(1, 256);
+      if (ctid == 0) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(&tmOut)),
+                     "r"(stg), "r"(0), "r"(t * kToTile)
+                     : "memory");
+        tc::tma_store_commit();
+      }
+    }
+    if (ctid == 0) tc::tma_store_wait<0>();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { dw0[e] = warp_sum(dw0[e]); dw1[e] = warp_sum(dw1[e]); dw2[e] = warp_sum(dw2[e]); }
+    if (w == 0) { db0 = warp_sum(db0); db1 = warp_sum(db1); db2 = warp_sum(db2); }
+    if (lane < 8) {
+      float a = 0.f, b = 0.f, c = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (e == lane) { a = dw0[e]; b = dw1[e]; c = dw2[e]; }
+      atomicAdd(p.acc + w * 8 + lane, (double)a);
+      atomicAdd(p.acc + 64 + w * 8 + lane, (double)b);
+      atomicAdd(p.acc + 128 + w * 8 + lane, (double)c);
+    }
+    if (w == 0 && lane == 0) {
+      atomicAdd(p.acc + 192, (double)db0);
+      atomicAdd(p.acc + 193, (double)db1);
+      atomicAdd(p.acc + 194, (double)db2);
+    }
+  }
+}
+
+// returns 0 = launched, 1 = not applicable, < 0 = error
+int tail_dec1_bwd_tma(const float* dz4, const void* d2, int ldd2, void* dd2, int lddd2, const float* w1, double* acc, long long M,
+                      cudaStream_t st) {
+  if (M < 4 * kToTile) return 1;
+  const long long tiles = (M + kToTile - 1) / kToTile;
+  if (tiles > 0x7fffffffLL) return 1;
+  Dec1BwdParams p;
+  p.w1 = w1; p.acc = acc; p.tiles = (int)tiles;
+  CUtensorMap tmD2, tmDz, tmOut;
+  {
+    uint64_t dims[2] = {64ull, (uint64_t)M}, str[1] = {(uint64_t)ldd2 * 2};
+    uint32_t box[2] = {64u, (uint32_t)kToTile};
+    if (tc::encode_tensor_map_bf16(&tmD2, d2, 2, dims, str, box, 128)) return -1;
+  }
+  {
+    uint64_t dims[2] = {8ull, (uint64_t)M}, str[1] = {16ull};
+    uint32_t box[2] = {8u, (uint32_t)kToTile};
+    if (tc::encode_tensor_map_bf16(&tmDz, dz4, 2, dims, str, box, 0)) return -1;
+  }
+  {
+    uint64_t dims[2] = {64ull, (uint64_t)M}, str[1] = {(uint64_t)lddd2 * 2};
+    uint32_t box[2] = {64u, (uint32_t)kToTile};
+    if (tc::encode_tensor_map_bf16(&tmOut, dd2, 2, dims, str, box, 128)) return -1;
+  }
+  constexpr int SMEM = 1024 + kToStages * kToStage + 2 * kToMid;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tail_dec1_bwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    EUNET_REQUIRE(e == cudaSuccess, "tail_dec1_bwd: cudaFuncSetAttribute(%d): %s", SMEM, cudaGetErrorString(e));
+    configured = true;
+  }
+  const int grid = p.tiles < 2 * kNumSMs ? p.tiles : 2 * kNumSMs;
+  tail_dec1_bwd_tma_kernel<<<grid, 288, SMEM, st>>>(tmD2, tmDz, tmOut, p);
+  return check_launch("tail_dec1_bwd(tma)");
+}
+
 }  // namespace eunet

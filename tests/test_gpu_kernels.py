@@ -481,6 +481,29 @@ def test_tail_dec1_fwd(k, case):
     assert nerr(z4[:, :3], want) < 1e-5 and torch.all(z4[:, 3] == 0)
 
 
+@pytest.mark.parametrize("case", [(5000, 64, 0, 64), (777, 192, 128, 72), (300, 64, 0, 64)])
+def test_tail_dec1_bwd(k, case):
+    """dec1 backward (dd2 = dz W1, dW1 = dz^T d2, db1 = sum dz) on strided bf16 rows: TMA-pipelined kernel with a TMA tensor
+    store for M >= 512 pixels, the 8-lanes-per-pixel kernel below that; against torch on the same data."""
+    M, ld, off, ldo = case
+    g = torch.Generator(device="cuda").manual_seed(M + 1)
+    buf = torch.randn(M, ld, device="cuda", generator=g).to(torch.bfloat16)
+    d2 = buf[:, off:off + 64]
+    dz4 = torch.randn(M, 4, device="cuda", generator=g)
+    dz4[:, 3] = 0
+    w1 = (torch.randn(3, 64, device="cuda", generator=g) / 8).contiguous()
+    obuf = torch.full((M, ldo), 3.0, dtype=torch.bfloat16, device="cuda")
+    dd2 = obuf[:, :64]
+    acc = torch.zeros(200, dtype=torch.float64, device="cuda")
+    k.call("eunet_tail_dec1_bwd", dz4.data_ptr(), d2.data_ptr(), ld, dd2.data_ptr(), ldo, k.BF16, w1.data_ptr(), acc.data_ptr(), M)
+    torch.cuda.synchronize()
+    assert nerr(dd2.float(), dz4[:, :3] @ w1) < 6e-3                      # bf16 output rounding
+    if ldo > 64:
+        assert torch.all(obuf[:, 64:] == 3.0)                             # neighbouring channels untouched
+    assert nerr(acc[:192].reshape(3, 64), dz4[:, :3].double().t() @ d2.double()) < 1e-5
+    assert nerr(acc[192:195], dz4[:, :3].double().sum(0)) < 1e-5
+
+
 def test_pack_input_and_padded_weights(k):
     g = torch.Generator().manual_seed(4)
     x = torch.rand(2, 3, 8, 8, generator=g)
