@@ -24,6 +24,7 @@ namespace eunet {
 int g_opt_conv_halo = 1;
 int g_opt_tma_store = 1;
 extern int g_opt_tail_out_tma;   // tail.cu: 1 (default) = TMA-pipelined tail_out_fwd
+extern int g_opt_bn_tma;         // elementwise.cu: 1 (default) = TMA-pipelined bn_apply_relu
 
 PixelTile choose_pixel_tile(int B, int H, int W, int pixels) {
   PixelTile best{};
@@ -500,6 +501,10 @@ using namespace eunet;
 extern "C" int eunet_set_option(const char* name, int value) {
   if (strcmp(name, "conv_halo") == 0) {
     g_opt_conv_halo = value;
+    return 0;
+  }
+  if (strcmp(name, "bn_tma") == 0) {
+    g_opt_bn_tma = value;
     return 0;
   }
   if (strcmp(name, "tail_out_tma") == 0) {

@@ -600,6 +600,12 @@ static int check_vec(const void* p, int ld, int C, const char* what) {
 
 }  // namespace eunet
 
+namespace eunet {
+int g_opt_bn_tma = 1;
+int bn_apply_relu_tma(const void* y, int ldy, void* out, int ldo, long long M, int C, const float* scale, const float* shift,
+                      cudaStream_t st);
+}  // namespace eunet
+
 using namespace eunet;
 
 extern "C" {
@@ -634,6 +640,10 @@ int eunet_bn_apply_relu(const void* y, int ldy, void* out, int ldo, void* pooled
     DISPATCH_DTYPE(dtype, bn_apply_relu_pool_kernel<T, TY><<<ew_grid(M / 4 * (C / 8)), 256, 0, st>>>(
                               (const TY*)y, ldy, (T*)out, ldo, (T*)pooled, ldp, B, H, W, C, scale, shift));
   } else {
+    if (dtype == EUNET_BF16 && g_opt_bn_tma) {
+      const int rc = bn_apply_relu_tma(y, ldy, out, ldo, M, C, scale, shift, st);
+      if (rc <= 0) return rc;      // launched or failed; 1 = shape not covered, ring kernel below
+    }
     EUNET_REQUIRE(C <= 2048 && 256 % (C / 8) == 0, "bn_apply_relu: C/8=%d must divide 256", C / 8);
     DISPATCH_DTYPE(dtype, bn_ring_smem_attr((const void*)bn_apply_relu_kernel<T, TY>, Stream8<TY, 6>::bytes(256));
                    const int R = 256 / (C / 8);

@@ -38,7 +38,8 @@ int eunet_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* smem_
  *   "conv_halo"    1 (default) = halo-tile persistent conv kernels where they apply; 0 = always the per-tap kernels;
  *                  2 = halo kernels for every shape they cover (tests); 5 = per-tap wgrad without row-halo X boxes
  *   "tma_store"    1 (default) = Cout = 64 halo kernels write their tile with a TMA tensor store; 0 = per-thread stores
- *   "tail_out_tma" 1 (default) = TMA-pipelined tail_out_fwd / tail_bwd_reduce; 0 = thread-per-pixel / cp.async-ring kernels */
+ *   "tail_out_tma" 1 (default) = TMA-pipelined tail_out_fwd / tail_bwd_reduce / tail_dec1_*; 0 = the cp.async-ring kernels
+ *   "bn_tma"       1 (default) = TMA load -> transform -> TMA store bn_apply_relu; 0 = the cp.async-ring kernel */
 int eunet_set_option(const char* name, int value);
 
 /* ---- metrics.py:12-58 (calculate_iou / calculate_dice / calculate_semantic_metrics) and the confusion

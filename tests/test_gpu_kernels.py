@@ -504,6 +504,33 @@ def test_tail_dec1_bwd(k, case):
     assert nerr(acc[192:195], dz4[:, :3].double().sum(0)) < 1e-5
 
 
+@pytest.mark.parametrize("case", [(64, 5000, 64, 192, 128), (128, 3333, 128, 384, 256), (512, 1100, 512, 512, 0)])
+def test_bn_apply_relu_tma_on_channel_slices(k, case):
+    """TMA load -> transform -> TMA store bn_apply_relu against the cp.async ring kernel (bit-identical) and torch; the output
+    is a channel slice of a wider buffer (skip slices of the concat buffers), M is not a multiple of the 128-pixel tile."""
+    C, M, ldy, ldo, off = case
+    g = torch.Generator(device="cuda").manual_seed(C + M)
+    y = (torch.randn(M, ldy, device="cuda", generator=g) * 1.5).to(torch.float16)
+    sc, sh = torch.rand(C, device="cuda", generator=g) + 0.5, torch.randn(C, device="cuda", generator=g)
+    outs = {}
+    for name, opt in (("tma", 1), ("ring", 0)):
+        buf = torch.full((M, ldo), 3.0, dtype=torch.bfloat16, device="cuda")
+        out = buf[:, off:off + C]
+        k.set_option("bn_tma", opt)
+        try:
+            k.call("eunet_bn_apply_relu", y.data_ptr(), ldy, out.data_ptr(), ldo, None, 0, k.BF16, 1, 1, M, C, sc.data_ptr(), sh.data_ptr())
+            torch.cuda.synchronize()
+        finally:
+            k.set_option("bn_tma", 1)
+        outs[name] = buf
+    assert torch.equal(outs["tma"], outs["ring"])
+    want = torch.relu(y[:, :C].float() * sc + sh)
+    assert nerr(outs["tma"][:, off:off + C].float(), want) < 6e-3
+    if ldo > C:
+        rest = torch.cat([outs["tma"][:, :off], outs["tma"][:, off + C:]], 1)
+        assert torch.all(rest == 3.0)
+
+
 def test_pack_input_and_padded_weights(k):
     g = torch.Generator().manual_seed(4)
     x = torch.rand(2, 3, 8, 8, generator=g)
