@@ -152,7 +152,8 @@ int eunet_tail_bwd_reduce(const float* dout4, const void* mid, int dtype, const 
 int eunet_tail_bwd_dmid(const float* dout4, const void* mid, void* dmid, int dtype, const float* scale, const float* shift,
                         const float* mean, const float* invstd, const float* w3, const double* acc, int B, int H, int W,
                         void* stream);
-/* Fused backward of the enhance head at 2Hx2W (bf16 tensor-core path): replaces eunet_tail_bwd_dmid + eunet_conv3x3_wgrad
+/* Fused backward of the enhance head at 2Hx2W (reference models.py:309-311 under loss.backward(), train_eval.py:338;
+ * bf16 tensor-core path): replaces eunet_tail_bwd_dmid + eunet_conv3x3_wgrad
  * + eunet_conv3x3_dgrad_few for enhance.0 - the 64-channel gradient dmid is formed on chip and never written:
  *   dmid = BN/ReLU backward of (mid_raw, dout4) with the sums `acc` from eunet_tail_bwd_reduce,
  *   dw_packed[co][tap][ci] += sum_p dmid[p,co] * d1p16[p+tap,ci]      (fp32 [64][9][16], caller-zeroed),
