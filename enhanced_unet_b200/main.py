@@ -31,20 +31,30 @@ def main(argv=None):
         raise SystemExit("plotting (reference visualization.py) is outside the accelerated hot path")
     if not torch.cuda.is_available():
         raise SystemExit("a CUDA device is required (there is no CPU fallback)")
-    device = "cuda"
+    # one process per GPU under torchrun (WORLD_SIZE > 1): NCCL process group, rank-local batches, gradient all-reduce
+    # inside Trainer; rank 0 evaluates and writes the results
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    if world > 1 and not torch.distributed.is_initialized():
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    device = "cuda" if world == 1 else f"cuda:{local}"
     all_results = {}
     for name in args.models:
-        train = SyntheticCellBatches(args.train_batches, args.batch, args.size, seed=1)
+        train = SyntheticCellBatches(args.train_batches, args.batch, args.size, seed=1 + 1000 * rank)
         val = SyntheticCellBatches(2, args.batch, args.size, seed=99)
         ckpt = os.path.join("checkpoints", name, "best_model.pth")
         if args.mode in ("train", "train_eval"):
             ckpt = train_model(name, "data", device, args.epochs, train_batches=train, val_batches=val, dtype=args.dtype)
-        if args.mode in ("eval", "train_eval"):
+        if args.mode in ("eval", "train_eval") and rank == 0:
             all_results[name] = evaluate_model(name, "data", device, ckpt, batches=val, dtype=args.dtype)
             print(json.dumps({name: all_results[name]}, indent=1))
-    os.makedirs("results", exist_ok=True)
-    with open(os.path.join("results", "evaluation_results.json"), "w") as f:      # reference main.py:251-279
-        json.dump(all_results, f, indent=2)
+    if rank == 0:
+        os.makedirs("results", exist_ok=True)
+        with open(os.path.join("results", "evaluation_results.json"), "w") as f:      # reference main.py:251-279
+            json.dump(all_results, f, indent=2)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
     return all_results
 
 

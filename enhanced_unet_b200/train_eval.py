@@ -18,6 +18,7 @@ import torch
 import torch.nn.functional as F
 
 from . import metrics as _metrics
+from . import parallel as _parallel
 from .lib import call, ptr
 from .models import get_model
 from .ops import combined_loss
@@ -72,6 +73,13 @@ class Trainer:
             self.optimizer, T_0=max(10, self.total_epochs // 3), T_mult=2, eta_min=1e-7)
         self.warmup_scheduler = torch.optim.lr_scheduler.LinearLR(
             self.optimizer, start_factor=0.001, end_factor=1.0, total_iters=self.warmup_epochs)
+        # data parallel (one process per GPU, torch.distributed initialised by the launcher; the reference has no
+        # distributed code): identical replicas, gradients summed across ranks during backward, averaged in the optimiser
+        self._world = _parallel.world_size()
+        self._exchange = None
+        if self._world > 1:
+            _parallel.broadcast_parameters(list(model.parameters()) + list(model.buffers()))
+            self._exchange = _parallel.GradientAllReduce(model)
 
     def _compute_combined_loss(self, logits: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         """One sample: logits [3,H,W] (or [3,2H,2W]), target [H,W] -> 2.5*focal + 2.5*dice + 1.0*tversky (183-197)."""
@@ -99,8 +107,10 @@ class Trainer:
                     gt = F.pad(gt, (0, w_pad, 0, h_pad), mode="constant", value=0)
                 loss = loss + combined_loss(outputs[i:i + 1], gt.unsqueeze(0))
             loss = loss / batch_size
-        loss.backward()
-        self.optimizer.step()          # global-norm clip (max_norm=1.0) fused into the AdamW kernel
+        loss.backward()                # world > 1: launches the bucketed gradient all-reduce as gradients are finished
+        if self._exchange is not None:
+            self._exchange.wait()
+        self.optimizer.step(grad_scale=1.0 / self._world)   # global-norm clip (max_norm=1.0) fused into the AdamW kernel
         return loss.detach()
 
     def train_epoch(self, dataloader: Iterable[Dict]) -> float:
@@ -286,6 +296,8 @@ def train_model(model_name: str, data_dir, device: str = "cuda", num_epochs: int
             print(f"  val mIoU {miou:.4f}  live {res.get('sem_live_iou', 0):.4f}  dead {res.get('sem_dead_iou', 0):.4f}")
             if miou > best_miou:
                 best_miou, best_loss = miou, loss
+                if _parallel.world_size() > 1 and torch.distributed.get_rank() != 0:
+                    continue                                                                         # rank 0's replica is checkpointed
                 torch.save({"epoch": epoch + 1, "model_state_dict": model.state_dict(),
                             "optimizer_state_dict": trainer.optimizer.state_dict(),
                             "scheduler_state_dict": trainer.scheduler.state_dict(), "best_miou": best_miou,
