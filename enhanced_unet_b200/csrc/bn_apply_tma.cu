@@ -23,6 +23,7 @@ constexpr int kBaStages = 3;
 constexpr int kBaTile = 128;
 constexpr int kBaBytes = kBaTile * 128;       // 16 KB
 
+template <bool F16>
 __global__ void __launch_bounds__(288, 2)
 bn_apply_relu_tma_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmOut, const BnApplyTmaParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -75,7 +76,7 @@ bn_apply_relu_tma_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_c
 #pragma unroll
         for (int e2 = 0; e2 < 4; ++e2) {
           const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[e2]));
-          o[e2] = pack_bf16x2(fmaxf(fmaf(f.x, sc[2 * e2], sh[2 * e2]), 0.f), fmaxf(fmaf(f.y, sc[2 * e2 + 1], sh[2 * e2 + 1]), 0.f));
+          o[e2] = pack16x2<F16>(fmaxf(fmaf(f.x, sc[2 * e2], sh[2 * e2]), 0.f), fmaxf(fmaf(f.y, sc[2 * e2 + 1], sh[2 * e2 + 1]), 0.f));
         }
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + off), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
       }
@@ -97,7 +98,7 @@ bn_apply_relu_tma_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_c
 
 // returns 0 = launched, 1 = not applicable (caller uses the ring kernel), < 0 = error
 int bn_apply_relu_tma(const void* y, int ldy, void* out, int ldo, long long M, int C, const float* scale, const float* shift,
-                      cudaStream_t st) {
+                      bool out_f16, cudaStream_t st) {
   if (C % 64 != 0 || M < 8 * kBaTile || M > 0x7fffffffLL) return 1;
   BnApplyTmaParams p;
   p.scale = scale; p.shift = shift;
@@ -119,14 +120,12 @@ int bn_apply_relu_tma(const void* y, int ldy, void* out, int ldo, long long M, i
     if (tc::encode_tensor_map_bf16(&tmOut, out, 2, dims, str, box, 128)) return -1;
   }
   constexpr int SMEM = 1024 + kBaStages * kBaBytes + 2 * kBaBytes;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(bn_apply_relu_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    EUNET_REQUIRE(e == cudaSuccess, "bn_apply_relu(tma): cudaFuncSetAttribute(%d): %s", SMEM, cudaGetErrorString(e));
-    configured = true;
-  }
+  auto kern = out_f16 ? bn_apply_relu_tma_kernel<true> : bn_apply_relu_tma_kernel<false>;
+  // set on every launch: the attribute is per device, and a process may drive more than one GPU
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+  EUNET_REQUIRE(e == cudaSuccess, "bn_apply_relu(tma): cudaFuncSetAttribute(%d): %s", SMEM, cudaGetErrorString(e));
   dim3 grid((unsigned)blocks, (unsigned)splits);
-  bn_apply_relu_tma_kernel<<<grid, 288, SMEM, st>>>(tmY, tmOut, p);
+  kern<<<grid, 288, SMEM, st>>>(tmY, tmOut, p);
   return check_launch("bn_apply_relu(tma)");
 }
 

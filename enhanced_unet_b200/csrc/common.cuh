@@ -22,7 +22,30 @@ int check_launch(const char* what);   // cudaPeekAtLastError based; sets error t
 
 constexpr int kNumSMs = 148;
 
-enum DType : int { kF32 = 0, kBF16 = 1 };
+enum DType : int { kF32 = 0, kBF16 = 1, kF16 = 2 };
+
+// dtype code -> (T = activation / gradient storage type, TY = storage type of RAW pre-BatchNorm conv outputs).
+//   EUNET_BF16: bf16 tensors, fp16 raw;  EUNET_F16: fp16 everywhere (gradients carry the power-of-two scale of
+//   eunet_grad_scale);  EUNET_F32: fp32 everywhere.
+#define EUNET_DISPATCH_DTYPE(dtype, ...)                    \
+  do {                                                      \
+    if ((dtype) == EUNET_BF16) {                            \
+      using T = __nv_bfloat16;                              \
+      using TY = __half;                                    \
+      __VA_ARGS__;                                          \
+    } else if ((dtype) == EUNET_F16) {                      \
+      using T = __half;                                     \
+      using TY = __half;                                    \
+      __VA_ARGS__;                                          \
+    } else if ((dtype) == EUNET_F32) {                      \
+      using T = float;                                      \
+      using TY = float;                                     \
+      __VA_ARGS__;                                          \
+    } else {                                                \
+      set_error("unknown dtype %d", (int)(dtype));          \
+      return -1;                                            \
+    }                                                       \
+  } while (0)
 
 // ---- element access: 8 consecutive channels as fp32, from fp32 or bf16 storage ----
 struct F8 {
@@ -92,6 +115,22 @@ __device__ __forceinline__ void store8(__half* p, const F8& r) {
   u.w = pack_f16x2(r.v[6], r.v[7]);
   *reinterpret_cast<uint4*>(p) = u;
 }
+// two 16-bit elements in one 32-bit word, F16 ? fp16 : bf16 (the TMA-staged kernels work on raw 32-bit words)
+template <bool F16> __device__ __forceinline__ void unpack16x2(uint32_t w, float& lo, float& hi) {
+  if (F16) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+    lo = f.x; hi = f.y;
+  } else {
+    lo = __uint_as_float(w << 16); hi = __uint_as_float(w & 0xffff0000u);
+  }
+}
+template <bool F16> __device__ __forceinline__ uint32_t pack16x2(float lo, float hi) {
+  return F16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
+}
+// the power-of-two gradient scale of fp16 mode: gscale = {S, 1/S} on the device, or NULL (= 1)
+__device__ __forceinline__ float gscale_fwd(const float* gscale) { return gscale ? __ldg(gscale) : 1.f; }
+__device__ __forceinline__ float gscale_inv(const float* gscale) { return gscale ? __ldg(gscale + 1) : 1.f; }
+
 __device__ __forceinline__ float to_f32(float x) { return x; }
 __device__ __forceinline__ float to_f32(__half x) { return __half2float(x); }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 x) { return __bfloat162float(x); }

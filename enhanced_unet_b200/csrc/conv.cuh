@@ -10,11 +10,12 @@ int conv3x3_fwd_f32(const float* x, int ldx, const float* w, float* y, int ldy, 
 int conv3x3_wgrad_f32(const float* x, int ldx, const float* dy, int lddy, float* dw, int B, int H, int W, int Cin, int Cout,
                       cudaStream_t st);
 
-// v2 halo-tile kernel (conv_halo.cu): 0 = launched, 1 = shape not covered (use the per-tap kernel), < 0 = error
+// v2 halo-tile kernel (conv_halo.cu); f16: operands / outputs are fp16 instead of bf16: 0 = launched, 1 = shape not covered (use the per-tap kernel), < 0 = error
 int conv3x3_fwd_halo_bf16(const void* x, int ldx, const void* w, void* y, int ldy, int B, int H, int W, int Cin, int Cout,
-                          double* stats, const float* scale, const float* shift, int relu, int out_raw, cudaStream_t st);
+                          double* stats, const float* scale, const float* shift, int relu, int out_raw, int f16, float* amax,
+                          cudaStream_t st);
 int conv3x3_wgrad_halo_bf16(const void* x, int ldx, const void* dy, int lddy, float* dw, int B, int H, int W, int Cin, int Cout,
-                            cudaStream_t st);
+                            int f16, cudaStream_t st);
 extern int g_opt_conv_halo;   // 1 (default): use the halo kernel where it applies
 extern int g_opt_tma_store;   // 1 (default): Cout = 64 halo kernels write their output tile with a TMA tensor store
 

@@ -26,6 +26,7 @@ struct DgradFewParams {
   float* dx4;
   int B, H, W;
   int blocks_x, blocks_y, items;
+  uint32_t fmt16;     // operand format of dy and the flipped filters: 1 = bf16, 0 = fp16
 };
 
 constexpr int kDfRows = 180;                 // halo tile rows: 18 x 10 pixels
@@ -81,7 +82,7 @@ conv3x3_dgrad_few_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_
     }
   } else if (warp == 1) {
     if (tc::elect_one()) {
-      constexpr uint32_t idesc = tc::make_idesc_bf16(64, kDfN, 0, 0);
+      const uint32_t idesc = tc::make_idesc_16(64, kDfN, 0, 0, p.fmt16);
       tc::mbar_wait(tc::smem_u32(&w_full), 0);
       tc::tc_fence_after();
       uint32_t it = 0;
@@ -176,14 +177,15 @@ conv3x3_dgrad_few_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_
 
 using namespace eunet;
 
-extern "C" int eunet_conv3x3_dgrad_few(const void* dy, int lddy, const void* w_packed_flip, float* dx4, int B, int H, int W,
-                                       int Cout, int cin_pad, void* stream) {
+extern "C" int eunet_conv3x3_dgrad_few(const void* dy, int lddy, const void* w_packed_flip, float* dx4, int dtype, int B, int H,
+                                       int W, int Cout, int cin_pad, void* stream) {
+  EUNET_REQUIRE(dtype == EUNET_BF16 || dtype == EUNET_F16, "conv3x3_dgrad_few: tensor-core path only (dtype %d)", dtype);
   EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "conv3x3_dgrad_few: bad shape");
   EUNET_REQUIRE(Cout == 64 && cin_pad >= 8 && cin_pad % 8 == 0, "conv3x3_dgrad_few: needs 64 gradient channels and a packed "
                 "filter of >= 8 input-channel rows (got Cout=%d, cin_pad=%d)", Cout, cin_pad);
   EUNET_REQUIRE(lddy % 8 == 0 && lddy >= 64, "conv3x3_dgrad_few: bad lddy %d", lddy);
   DgradFewParams p;
-  p.dx4 = dx4; p.B = B; p.H = H; p.W = W;
+  p.dx4 = dx4; p.B = B; p.H = H; p.W = W; p.fmt16 = dtype == EUNET_F16 ? 0u : 1u;
   p.blocks_x = (W + 7) / 8;
   p.blocks_y = (H + 15) / 16;
   const long long items = (long long)p.blocks_x * p.blocks_y * B;
@@ -203,11 +205,9 @@ extern "C" int eunet_conv3x3_dgrad_few(const void* dy, int lddy, const void* w_p
     if (tc::encode_tensor_map_bf16(&tmW, w_packed_flip, 2, dims, str, box, 128)) return -1;
   }
   constexpr int SMEM = 1024 + 8192 + kDfStages * kDfSlot + 2 * kDfSBytes;
-  static bool configured = false;
-  if (!configured) {
+  {   // set on every launch: the attribute is per device, and a process may drive more than one GPU
     cudaError_t e = cudaFuncSetAttribute(conv3x3_dgrad_few_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     EUNET_REQUIRE(e == cudaSuccess, "conv3x3_dgrad_few: cudaFuncSetAttribute(%d): %s", SMEM, cudaGetErrorString(e));
-    configured = true;
   }
   const int grid = p.items < kNumSMs ? p.items : kNumSMs;
   conv3x3_dgrad_few_kernel<<<grid, 320, SMEM, (cudaStream_t)stream>>>(tmDY, tmW, p);

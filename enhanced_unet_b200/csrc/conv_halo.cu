@@ -32,6 +32,8 @@ struct ConvHaloParams {
   const float* shift;
   int relu;
   int out_f16;
+  uint32_t fmt16;     // tensor-core operand format of x and w: 1 = bf16, 0 = fp16
+  float* amax;        // fp16 outputs: atomicMax of |y| over the stored values when it exceeds the fp16 range (may be NULL)
   // EPI = 1 (fused 2Hx2W tail, reference models.py:310-313 + 337): out = d14 + b3 + W3 . relu(acc * scale + shift)
   const float* w3;    // [3][64]
   const float* b3;    // [3]
@@ -162,7 +164,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (tc::elect_one()) {
-      constexpr uint32_t idesc = tc::make_idesc_bf16(128, BN, 0, 0);
+      const uint32_t idesc = tc::make_idesc_16(128, BN, 0, 0, p.fmt16);
       if (WRES) {
         tc::mbar_wait(tc::smem_u32(&w_full), 0);
         tc::tc_fence_after();
@@ -228,6 +230,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const int r = q * 32 + lane;                 // GEMM row inside a 128-row tile: (ty, tx) = (r / 8, r % 8)
       const int ty = r >> 3, tx = r & 7;
       const bool want_stats = p.stats != nullptr, affine = EPI == 0 && p.scale != nullptr, do_store = p.y != nullptr;
+      const bool want_amax = p.amax != nullptr && p.out_f16 != 0;
+      float amax = 0.f;
       double tot1[NCW], tot2[NCW];
 #pragma unroll
       for (int cw = 0; cw < NCW; ++cw) tot1[cw] = tot2[cw] = 0.0;
@@ -322,6 +326,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 #pragma unroll
                   for (int ee = 0; ee < 8; ++ee) o[ee] = fmaxf(o[ee], 0.f);
                 }
+                if (want_amax) {
+#pragma unroll
+                  for (int ee = 0; ee < 8; ++ee) amax = fmaxf(amax, fabsf(o[ee]));
+                }
                 uint4 u;
                 if (p.out_f16) {
                   u.x = tc::cvt_f16x2_sat(o[0], o[1]); u.y = tc::cvt_f16x2_sat(o[2], o[3]);
@@ -394,6 +402,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         }
       }
       if (TST && do_store && e == 0 && lane == 0) tc::tma_store_wait<0>();
+      // fp16 saturation is loud, not silent: the largest stored magnitude goes out only when it exceeded the fp16 range
+      if (want_amax && amax > 65504.f) atomicMax(reinterpret_cast<unsigned int*>(p.amax), __float_as_uint(amax));
       if (want_stats) {
         if (NCW == 1 && pending > 0) flush(0);
 #pragma unroll
@@ -444,11 +454,9 @@ static int launch_halo(const void* x, int ldx, const void* w, ConvHaloParams p, 
     if (tc::encode_tensor_map_bf16(&tmW, w, 2, dims, str, box, KC == 64 ? 128 : 32)) return -1;
   }
   auto kern = conv3x3_halo_kernel<KC, BN, MT, WRES, TST, EPI>;
-  static int configured = 0;
-  if (configured < smem) {
+  {   // set on every launch: the attribute is per device, and a process may drive more than one GPU
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     EUNET_REQUIRE(e == cudaSuccess, "conv3x3_halo: cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e));
-    configured = smem;
   }
   const int ntiles = p.Cout / BN;
   int per = kNumSMs / ntiles;
@@ -461,11 +469,13 @@ static int launch_halo(const void* x, int ldx, const void* w, ConvHaloParams p, 
 
 // returns 0 = launched, 1 = shape not covered (caller uses the per-tap kernel), < 0 = error
 int conv3x3_fwd_halo_bf16(const void* x, int ldx, const void* w, void* y, int ldy, int B, int H, int W, int Cin, int Cout,
-                          double* stats, const float* scale, const float* shift, int relu, int out_raw, cudaStream_t st) {
+                          double* stats, const float* scale, const float* shift, int relu, int out_raw, int f16, float* amax,
+                          cudaStream_t st) {
   ConvHaloParams p;
   p.y = y; p.ldy = ldy; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.blocks_x = p.blocks_y = p.items = 0;
-  p.stats = stats; p.scale = scale; p.shift = shift; p.relu = relu; p.out_f16 = out_raw ? 1 : 0;
+  p.stats = stats; p.scale = scale; p.shift = shift; p.relu = relu; p.out_f16 = (out_raw || f16) ? 1 : 0;
+  p.fmt16 = f16 ? 0u : 1u; p.amax = amax;
   p.w3 = p.b3 = p.d14 = nullptr; p.out = nullptr;
   if (H < 8 || W < 8) return 1;
   if (y == nullptr && !(Cin == 16 && Cout == 64)) return 1;   // statistics-only pass: only the 16 -> 64 kernel skips stores           // tiny images: the batch-folding per-tap kernel wastes less
@@ -493,11 +503,12 @@ int conv3x3_fwd_halo_bf16(const void* x, int ldx, const void* w, void* y, int ld
 // BatchNorm affine + ReLU, the 1x1 enhance.3 projection, residual and bias, straight from the TMEM accumulators.
 // mid != nullptr additionally stores the RAW fp16 convolution output (the training backward reads it).
 int conv3x3_tail_fwd_bf16(const void* x16, const void* w, void* mid, const float* scale, const float* shift, const float* w3,
-                          const float* b3, const float* d14, float* out, int B, int H, int W, cudaStream_t st) {
+                          const float* b3, const float* d14, float* out, int B, int H, int W, int f16, cudaStream_t st) {
   ConvHaloParams p;
   p.y = mid; p.ldy = 64; p.B = B; p.H = H; p.W = W; p.Cin = 16; p.Cout = 64;
   p.blocks_x = p.blocks_y = p.items = 0;
   p.stats = nullptr; p.scale = scale; p.shift = shift; p.relu = 0; p.out_f16 = 1;
+  p.fmt16 = f16 ? 0u : 1u; p.amax = nullptr;
   p.w3 = w3; p.b3 = b3; p.d14 = d14; p.out = out;
   if (H < 8 || W < 8) return 1;
   if (mid != nullptr) return launch_halo<16, 64, 4, true, true, 1>(x16, 16, w, p, st);
@@ -507,14 +518,16 @@ int conv3x3_tail_fwd_bf16(const void* x16, const void* w, void* mid, const float
 }  // namespace eunet
 
 extern "C" int eunet_conv3x3_tail_fwd(const void* d1p16, const void* w_packed, void* mid_raw, const float* scale, const float* shift,
-                                      const float* w3, const float* b3, const float* d14, float* out, int B, int H2, int W2,
-                                      void* stream) {
+                                      const float* w3, const float* b3, const float* d14, float* out, int dtype, int B, int H2,
+                                      int W2, void* stream) {
   using namespace eunet;
   EUNET_REQUIRE(B > 0 && H2 >= 8 && W2 >= 8, "conv3x3_tail_fwd: needs B > 0 and a >= 8x8 output grid (got %d, %dx%d)", B, H2, W2);
+  EUNET_REQUIRE(dtype == EUNET_BF16 || dtype == EUNET_F16, "conv3x3_tail_fwd: tensor-core path only (dtype %d)", dtype);
   EUNET_REQUIRE(d1p16 && w_packed && scale && shift && w3 && b3 && d14 && out, "conv3x3_tail_fwd: null operand");
   EUNET_REQUIRE((reinterpret_cast<uintptr_t>(d14) & 15) == 0 && (reinterpret_cast<uintptr_t>(mid_raw) & 15) == 0,
                 "conv3x3_tail_fwd: d14 / mid must be 16-byte aligned");
-  const int rc = conv3x3_tail_fwd_bf16(d1p16, w_packed, mid_raw, scale, shift, w3, b3, d14, out, B, H2, W2, (cudaStream_t)stream);
+  const int rc = conv3x3_tail_fwd_bf16(d1p16, w_packed, mid_raw, scale, shift, w3, b3, d14, out, B, H2, W2, dtype == EUNET_F16,
+                                       (cudaStream_t)stream);
   EUNET_REQUIRE(rc <= 0, "conv3x3_tail_fwd: shape not covered");
   return rc;
 }

@@ -38,6 +38,7 @@ struct TailBwdParams {
   const double* acc;  // [0,64) sum g', [64,128) sum g' xhat (tail_bwd_reduce)
   int B, H, W;
   int blocks_x, blocks_y, items;
+  uint32_t fmt16;     // operand format (d1p16, flipped filters, the dmid tile formed on chip): 1 = bf16, 0 = fp16
 };
 
 constexpr int kTbStages = 4;
@@ -107,8 +108,8 @@ tail_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmMid, const __grid_co
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (tc::elect_one()) {
-      constexpr uint32_t idesc_u = tc::make_idesc_bf16(64, 184, 0, 0);     // both K-major
-      constexpr uint32_t idesc_w = tc::make_idesc_bf16(64, 48, 1, 1);      // both MN-major
+      const uint32_t idesc_u = tc::make_idesc_16(64, 184, 0, 0, p.fmt16);     // both K-major
+      const uint32_t idesc_w = tc::make_idesc_16(64, 48, 1, 1, p.fmt16);      // both MN-major
       tc::mbar_wait(tc::smem_u32(&w_full), 0);
       tc::tc_fence_after();
       uint32_t it = 0;
@@ -244,7 +245,8 @@ tail_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmMid, const __grid_co
                 o[e] = rr;
               }
             }
-            u0 = pack_bf16x2(o[0], o[1]); u1 = pack_bf16x2(o[2], o[3]); u2 = pack_bf16x2(o[4], o[5]); u3 = pack_bf16x2(o[6], o[7]);
+            if (p.fmt16) { u0 = pack_bf16x2(o[0], o[1]); u1 = pack_bf16x2(o[2], o[3]); u2 = pack_bf16x2(o[4], o[5]); u3 = pack_bf16x2(o[6], o[7]); }
+            else { u0 = tc::cvt_f16x2_sat(o[0], o[1]); u1 = tc::cvt_f16x2_sat(o[2], o[3]); u2 = tc::cvt_f16x2_sat(o[4], o[5]); u3 = tc::cvt_f16x2_sat(o[6], o[7]); }
           }
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u0), "r"(u1), "r"(u2), "r"(u3) : "memory");
         }
@@ -282,12 +284,14 @@ using namespace eunet;
 
 extern "C" int eunet_tail_bwd_fused(const float* dout4, const void* mid_raw, const void* d1p16, const void* w_packed_flip,
                                     const float* scale, const float* shift, const float* mean, const float* invstd,
-                                    const float* w3, const double* acc, float* dx4, float* dw_packed, int B, int H2, int W2,
-                                    void* stream) {
+                                    const float* w3, const double* acc, float* dx4, float* dw_packed, int dtype, int B, int H2,
+                                    int W2, void* stream) {
   EUNET_REQUIRE(B > 0 && H2 >= 8 && W2 >= 8, "tail_bwd_fused: needs B > 0 and a >= 8x8 grid (got %d, %dx%d)", B, H2, W2);
   EUNET_REQUIRE(dout4 && mid_raw && d1p16 && w_packed_flip && scale && shift && mean && invstd && w3 && acc && dx4 && dw_packed,
                 "tail_bwd_fused: null operand");
+  EUNET_REQUIRE(dtype == EUNET_BF16 || dtype == EUNET_F16, "tail_bwd_fused: tensor-core path only (dtype %d)", dtype);
   TailBwdParams p;
+  p.fmt16 = dtype == EUNET_F16 ? 0u : 1u;
   p.dx4 = dx4; p.dw = dw_packed; p.scale = scale; p.shift = shift; p.mean = mean; p.invstd = invstd; p.w3 = w3; p.acc = acc;
   p.B = B; p.H = H2; p.W = W2;
   p.blocks_x = (W2 + 7) / 8;
@@ -320,11 +324,9 @@ extern "C" int eunet_tail_bwd_fused(const float* dout4, const void* mid_raw, con
     if (tc::encode_tensor_map_bf16(&tmW, w_packed_flip, 2, dims, str, box, 128)) return -1;
   }
   constexpr int SMEM = 1024 + 8192 + kTbStages * kTbStage + 2 * kTbSBytes;
-  static bool configured = false;
-  if (!configured) {
+  {   // set on every launch: the attribute is per device, and a process may drive more than one GPU
     cudaError_t e = cudaFuncSetAttribute(tail_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     EUNET_REQUIRE(e == cudaSuccess, "tail_bwd_fused: cudaFuncSetAttribute(%d): %s", SMEM, cudaGetErrorString(e));
-    configured = true;
   }
   const int grid = p.items < kNumSMs ? p.items : kNumSMs;
   tail_bwd_fused_kernel<<<grid, 576, SMEM, (cudaStream_t)stream>>>(tmMid, tmDout, tmX, tmW, p);

@@ -53,7 +53,9 @@ struct ConvFwdParams {
   const float* scale;
   const float* shift;
   int relu;
-  int out_f16;   // 1: store fp16 (raw pre-BN tensor), 0: store bf16 (activation / gradient)
+  int out_f16;   // 1: store fp16 (raw pre-BN tensor, or any tensor in fp16 mode), 0: store bf16 (activation / gradient)
+  uint32_t fmt16;   // tensor-core operand format of x and w: 1 = bf16, 0 = fp16
+  float* amax;   // fp16 outputs: atomicMax of |y| when it exceeds the fp16 range (may be NULL)
 };
 
 struct ConvWgradParams {
@@ -61,6 +63,7 @@ struct ConvWgradParams {
   int B, H, W, Cin, Cout;
   int bw, bh, bb, tiles_x, tiles_y;
   int tiles, tiles_per_split;
+  uint32_t fmt16;
 };
 
 // sum over the 32 lanes of a warp of 32 per-lane values; lane l ends with the total of v[l]
@@ -140,7 +143,7 @@ conv3x3_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
     if (tc::elect_one()) {
-      constexpr uint32_t idesc = tc::make_idesc_bf16(128, BN, 0, 0);
+      const uint32_t idesc = tc::make_idesc_16(128, BN, 0, 0, p.fmt16);
       for (int it = 0; it < kiters; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
@@ -167,6 +170,7 @@ conv3x3_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     __nv_bfloat16* yrow = p.y + (((long long)gb * p.H + gy) * p.W + gx) * p.ldy + n0;
     tc::mbar_wait(tc::smem_u32(&accum_bar), 0);
     tc::tc_fence_after();
+    float amax = 0.f;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += CH) {
       uint32_t raw[32];
@@ -203,6 +207,7 @@ conv3x3_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             if (p.scale != nullptr) f = fmaf(f, __ldg(p.scale + n0 + c0 + g8 * 8 + e), __ldg(p.shift + n0 + c0 + g8 * 8 + e));
             if (p.relu) f = fmaxf(f, 0.f);
             o[e] = f;
+            amax = fmaxf(amax, fabsf(f));
           }
           uint4 u;
           if (p.out_f16) {
@@ -220,6 +225,7 @@ conv3x3_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         }
       }
     }
+    if (p.amax != nullptr && p.out_f16 && amax > 65504.f) atomicMax(reinterpret_cast<unsigned int*>(p.amax), __float_as_uint(amax));
     if (p.stats != nullptr) {
       asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
       for (int c = threadIdx.x - 64; c < BN; c += 128) {
@@ -316,7 +322,7 @@ conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     }
   } else if (warp == 1) {
     if (tc::elect_one()) {
-      constexpr uint32_t idesc = tc::make_idesc_bf16(128, N, 1, 1);   // both operands MN-major
+      const uint32_t idesc = tc::make_idesc_16(128, N, 1, 1, p.fmt16);   // both operands MN-major
       constexpr uint32_t B_LAYOUT = KC == 64 ? tc::kSwizzle128 : tc::kSwizzle32;
       constexpr uint32_t B_ROW = KC * 2;            // bytes per pixel row of an X tile
       for (int it = 0; it < kiters; ++it) {
@@ -383,11 +389,9 @@ static int launch_fwd(const CUtensorMap& tmX, const CUtensorMap& tmW, const Conv
                       cudaStream_t st) {
   constexpr int SMEM = STAGES * (128 * KC * 2 + BN * KC * 2) + 1024;
   auto kern = conv3x3_fwd_tc_kernel<KC, BN, STAGES>;
-  static bool configured = false;   // per instantiation; attribute is sticky per device context
-  if (!configured) {
+  {   // set on every launch: the attribute is per device, and a process may drive more than one GPU
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     EUNET_REQUIRE(e == cudaSuccess, "conv3x3_fwd: cudaFuncSetAttribute(%d): %s", SMEM, cudaGetErrorString(e));
-    configured = true;
   }
   dim3 grid((unsigned)mtiles, (unsigned)ntiles);
   kern<<<grid, 192, SMEM, st>>>(tmX, tmW, p);
@@ -395,12 +399,13 @@ static int launch_fwd(const CUtensorMap& tmX, const CUtensorMap& tmW, const Conv
 }
 
 static int conv3x3_fwd_bf16(const void* x, int ldx, const void* w, void* y, int ldy, int B, int H, int W, int Cin, int Cout,
-                            double* stats, const float* scale, const float* shift, int relu, int out_raw, cudaStream_t st) {
+                            double* stats, const float* scale, const float* shift, int relu, int out_raw, int f16, float* amax,
+                            cudaStream_t st) {
   EUNET_REQUIRE(Cin % 16 == 0 && Cout % 16 == 0, "conv3x3_fwd(bf16): Cin=%d and Cout=%d must be multiples of 16", Cin, Cout);
   EUNET_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && ldx >= Cin && ldy >= Cout, "conv3x3_fwd(bf16): bad ld (%d, %d)", ldx, ldy);
   EUNET_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0, "conv3x3_fwd(bf16): y not 16-byte aligned");
   if (g_opt_conv_halo) {
-    const int rc = conv3x3_fwd_halo_bf16(x, ldx, w, y, ldy, B, H, W, Cin, Cout, stats, scale, shift, relu, out_raw, st);
+    const int rc = conv3x3_fwd_halo_bf16(x, ldx, w, y, ldy, B, H, W, Cin, Cout, stats, scale, shift, relu, out_raw, f16, amax, st);
     if (rc <= 0) return rc;   // launched (0) or failed (< 0); 1 = not covered, fall through to the per-tap kernel
   }
   EUNET_REQUIRE(y != nullptr, "conv3x3_fwd(bf16): y == NULL (statistics only) is implemented for 16 -> 64 channels on >= 8x8 images");
@@ -418,7 +423,8 @@ static int conv3x3_fwd_bf16(const void* x, int ldx, const void* w, void* y, int 
   p.y = (__nv_bfloat16*)y; p.ldy = ldy;
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.bw = t.bw; p.bh = t.bh; p.bb = t.bb; p.tiles_x = t.tiles_x; p.tiles_y = t.tiles_y;
-  p.stats = stats; p.scale = scale; p.shift = shift; p.relu = relu; p.out_f16 = out_raw ? 1 : 0;
+  p.stats = stats; p.scale = scale; p.shift = shift; p.relu = relu; p.out_f16 = (out_raw || f16) ? 1 : 0;
+  p.fmt16 = f16 ? 0u : 1u; p.amax = amax;
   const long long mt = t.tiles();
   const int nt = Cout / BN;
   EUNET_REQUIRE(mt <= 0x7fffffffLL, "conv3x3_fwd(bf16): too many tiles");
@@ -441,11 +447,9 @@ template <int KC, int TAPS, int STAGES, bool RH = false>
 static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDY, ConvWgradParams p, cudaStream_t st) {
   constexpr int SMEM = STAGES * (2 * 64 * 128 + (RH ? 80 * KC * 2 : TAPS * 64 * KC * 2)) + 1024;
   auto kern = conv3x3_wgrad_tc_kernel<KC, TAPS, STAGES, RH>;
-  static bool configured = false;
-  if (!configured) {
+  {   // set on every launch: the attribute is per device, and a process may drive more than one GPU
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     EUNET_REQUIRE(e == cudaSuccess, "conv3x3_wgrad: cudaFuncSetAttribute(%d): %s", SMEM, cudaGetErrorString(e));
-    configured = true;
   }
   const int co_tiles = (p.Cout + 127) / 128;
   const int zdim = (p.Cin / KC) * (9 / TAPS);
@@ -461,11 +465,11 @@ static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDY, ConvWgr
 }
 
 static int conv3x3_wgrad_bf16(const void* x, int ldx, const void* dy, int lddy, float* dw, int B, int H, int W, int Cin, int Cout,
-                              cudaStream_t st) {
+                              int f16, cudaStream_t st) {
   EUNET_REQUIRE(Cin % 16 == 0 && Cout % 64 == 0, "conv3x3_wgrad(bf16): Cin=%d must be a multiple of 16 and Cout=%d of 64", Cin, Cout);
   EUNET_REQUIRE(ldx % 8 == 0 && lddy % 8 == 0 && ldx >= Cin && lddy >= Cout, "conv3x3_wgrad(bf16): bad ld (%d, %d)", ldx, lddy);
   if (g_opt_conv_halo) {
-    const int rc = conv3x3_wgrad_halo_bf16(x, ldx, dy, lddy, dw, B, H, W, Cin, Cout, st);
+    const int rc = conv3x3_wgrad_halo_bf16(x, ldx, dy, lddy, dw, B, H, W, Cin, Cout, f16, st);
     if (rc <= 0) return rc;
   }
   const int KC = (Cin % 64 == 0) ? 64 : 16;
@@ -482,7 +486,7 @@ static int conv3x3_wgrad_bf16(const void* x, int ldx, const void* dy, int lddy, 
   }
   if (make_act_map(&tmDY, dy, lddy, Cout, B, H, W, 64, t, 128)) return -1;
   ConvWgradParams p;
-  p.dw = dw;
+  p.dw = dw; p.fmt16 = f16 ? 0u : 1u;
   p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.bw = t.bw; p.bh = t.bh; p.bb = t.bb; p.tiles_x = t.tiles_x; p.tiles_y = t.tiles_y;
   EUNET_REQUIRE(t.tiles() <= 0x7fffffffLL, "conv3x3_wgrad(bf16): too many tiles");
@@ -521,12 +525,13 @@ extern "C" int eunet_set_option(const char* name, int value) {
 
 extern "C" int eunet_conv3x3_fwd(const void* x, int ldx, const void* w_packed, void* y, int ldy, int dtype, int B, int H, int W,
                                  int Cin, int Cout, double* stats, const float* scale, const float* shift, int relu,
-                                 int out_raw, void* stream) {
+                                 int out_raw, float* amax, void* stream) {
   EUNET_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv3x3_fwd: bad shape");
   EUNET_REQUIRE((scale == nullptr) == (shift == nullptr), "conv3x3_fwd: scale and shift must be given together");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == EUNET_BF16)
-    return conv3x3_fwd_bf16(x, ldx, w_packed, y, ldy, B, H, W, Cin, Cout, stats, scale, shift, relu, out_raw, st);
+  if (dtype == EUNET_BF16 || dtype == EUNET_F16)
+    return conv3x3_fwd_bf16(x, ldx, w_packed, y, ldy, B, H, W, Cin, Cout, stats, scale, shift, relu, out_raw, dtype == EUNET_F16, amax,
+                            st);
   if (dtype == EUNET_F32) {
     EUNET_REQUIRE(Cin % 16 == 0 && Cout % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "conv3x3_fwd(f32): Cin%%16, Cout%%4, ld%%4");
     return conv3x3_fwd_f32((const float*)x, ldx, (const float*)w_packed, (float*)y, ldy, B, H, W, Cin, Cout, stats, scale, shift,
@@ -540,7 +545,8 @@ extern "C" int eunet_conv3x3_wgrad(const void* x, int ldx, const void* dy, int l
                                    int W, int Cin, int Cout, void* stream) {
   EUNET_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv3x3_wgrad: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == EUNET_BF16) return conv3x3_wgrad_bf16(x, ldx, dy, lddy, dw_packed, B, H, W, Cin, Cout, st);
+  if (dtype == EUNET_BF16 || dtype == EUNET_F16)
+    return conv3x3_wgrad_bf16(x, ldx, dy, lddy, dw_packed, B, H, W, Cin, Cout, dtype == EUNET_F16, st);
   if (dtype == EUNET_F32) {
     EUNET_REQUIRE(Cin % 4 == 0 && Cout % 4 == 0 && ldx % 4 == 0 && lddy % 4 == 0, "conv3x3_wgrad(f32): channels/ld %% 4");
     return conv3x3_wgrad_f32((const float*)x, ldx, (const float*)dy, lddy, dw_packed, B, H, W, Cin, Cout, st);

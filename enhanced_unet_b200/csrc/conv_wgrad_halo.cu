@@ -21,6 +21,7 @@ struct WgradHaloParams {
   float* dw;
   int B, H, W, Cin, Cout;
   int blocks_x, blocks_y, tiles, tiles_per_split, ci_chunks;
+  uint32_t fmt16;     // operand format of x and dy: 1 = bf16, 0 = fp16
 };
 
 template <int STAGES>
@@ -73,7 +74,7 @@ conv3x3_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
     }
   } else if (warp == 1) {
     if (tc::elect_one()) {
-      constexpr uint32_t idesc = tc::make_idesc_bf16(128, 64, 1, 1);   // both operands MN-major
+      const uint32_t idesc = tc::make_idesc_16(128, 64, 1, 1, p.fmt16);   // both operands MN-major
       for (int it = 0; it < kiters; ++it) {
         const int s = it % STAGES;
         tc::mbar_wait(tc::smem_u32(&full_bar[s]), ((uint32_t)(it / STAGES)) & 1u);
@@ -183,7 +184,7 @@ conv3x3_wgrad16_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __gri
     }
   } else if (warp == 1) {
     if (tc::elect_one()) {
-      constexpr uint32_t idesc = tc::make_idesc_bf16(64, 48, 1, 1);   // both operands MN-major
+      const uint32_t idesc = tc::make_idesc_16(64, 48, 1, 1, p.fmt16);   // both operands MN-major
       for (int it = 0; it < kiters; ++it) {
         const int s = it % STAGES;
         tc::mbar_wait(tc::smem_u32(&full_bar[s]), ((uint32_t)(it / STAGES)) & 1u);
@@ -226,11 +227,11 @@ conv3x3_wgrad16_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __gri
 }
 
 static int conv3x3_wgrad16_halo(const void* x, int ldx, const void* dy, int lddy, float* dw, int B, int H, int W, int Cout,
-                                cudaStream_t st) {
+                                int f16, cudaStream_t st) {
   constexpr int STAGES = 8;
   constexpr int SMEM = 1024 + STAGES * (6 * 1024 + 128 * 128);
   WgradHaloParams p;
-  p.dw = dw; p.B = B; p.H = H; p.W = W; p.Cin = 16; p.Cout = Cout;
+  p.dw = dw; p.B = B; p.H = H; p.W = W; p.Cin = 16; p.Cout = Cout; p.fmt16 = f16 ? 0u : 1u;
   p.blocks_x = (W + 7) / 8;
   p.blocks_y = (H + 15) / 16;
   const long long tiles = (long long)p.blocks_x * p.blocks_y * B;
@@ -257,11 +258,9 @@ static int conv3x3_wgrad16_halo(const void* x, int ldx, const void* dy, int lddy
     if (tc::encode_tensor_map_bf16(&tmDY, dy, 4, dims, str, box, 128)) return -1;
   }
   auto kern = conv3x3_wgrad16_halo_kernel<STAGES>;
-  static bool configured = false;
-  if (!configured) {
+  {   // set on every launch: the attribute is per device, and a process may drive more than one GPU
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     EUNET_REQUIRE(e == cudaSuccess, "conv3x3_wgrad16_halo: cudaFuncSetAttribute(%d): %s", SMEM, cudaGetErrorString(e));
-    configured = true;
   }
   dim3 grid((unsigned)co_tiles, (unsigned)splits);
   kern<<<grid, 192, SMEM, st>>>(tmX, tmDY, p);
@@ -270,9 +269,9 @@ static int conv3x3_wgrad16_halo(const void* x, int ldx, const void* dy, int lddy
 
 // returns 0 = launched, 1 = shape not covered, < 0 = error
 int conv3x3_wgrad_halo_bf16(const void* x, int ldx, const void* dy, int lddy, float* dw, int B, int H, int W, int Cin, int Cout,
-                            cudaStream_t st) {
+                            int f16, cudaStream_t st) {
   if (H < 8 || W < 8) return 1;
-  if (Cin == 16) return conv3x3_wgrad16_halo(x, ldx, dy, lddy, dw, B, H, W, Cout, st);
+  if (Cin == 16) return conv3x3_wgrad16_halo(x, ldx, dy, lddy, dw, B, H, W, Cout, f16, st);
   if (Cin % 64 != 0) return 1;
   // Cout a multiple of 128: the per-tap kernel (M = 128 output channels, N = 192 per MMA, two CTAs per SM, row-halo X
   // boxes) is not shared-memory-port bound and wins (measured 1.0-1.25 PF against 0.85-1.02 PF here); this kernel keeps
@@ -281,7 +280,7 @@ int conv3x3_wgrad_halo_bf16(const void* x, int ldx, const void* dy, int lddy, fl
   constexpr int STAGES = 4;
   constexpr int SMEM = 1024 + STAGES * (23 * 1024 + 128 * 128);
   WgradHaloParams p;
-  p.dw = dw; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.dw = dw; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.fmt16 = f16 ? 0u : 1u;
   p.blocks_x = (W + 7) / 8;
   p.blocks_y = (H + 15) / 16;
   const long long tiles = (long long)p.blocks_x * p.blocks_y * B;
@@ -309,11 +308,9 @@ int conv3x3_wgrad_halo_bf16(const void* x, int ldx, const void* dy, int lddy, fl
     if (tc::encode_tensor_map_bf16(&tmDY, dy, 4, dims, str, box, 128)) return -1;
   }
   auto kern = conv3x3_wgrad_halo_kernel<STAGES>;
-  static bool configured = false;
-  if (!configured) {
+  {   // set on every launch: the attribute is per device, and a process may drive more than one GPU
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     EUNET_REQUIRE(e == cudaSuccess, "conv3x3_wgrad_halo: cudaFuncSetAttribute(%d): %s", SMEM, cudaGetErrorString(e));
-    configured = true;
   }
   dim3 grid((unsigned)cols, (unsigned)splits);
   kern<<<grid, 192, SMEM, st>>>(tmX, tmDY, p);

@@ -6,21 +6,7 @@
 
 namespace eunet {
 
-#define DISPATCH_DTYPE(dtype, ...)                          \
-  do {                                                      \
-    if ((dtype) == EUNET_BF16) {                            \
-      using T = __nv_bfloat16;                              \
-      using TY = __half;                                    \
-      __VA_ARGS__;                                          \
-    } else if ((dtype) == EUNET_F32) {                      \
-      using T = float;                                      \
-      using TY = float;                                     \
-      __VA_ARGS__;                                          \
-    } else {                                                \
-      set_error("unknown dtype %d", (int)(dtype));          \
-      return -1;                                            \
-    }                                                       \
-  } while (0)
+#define DISPATCH_DTYPE EUNET_DISPATCH_DTYPE
 
 static void bn_ring_smem_attr(const void* kernel, int bytes) {
   if (bytes > 48 * 1024) (void)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -419,14 +405,15 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const T* __restrict__ dact, int ldd, const TY* __restrict__ y, int ldy, T* __restrict__ dy, int lddy,
                     long long M, int C, const float* __restrict__ scale, const float* __restrict__ shift,
                     const float* __restrict__ mean, const float* __restrict__ invstd, const double* __restrict__ sums,
-                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                    float* __restrict__ dgamma, float* __restrict__ dbeta, const float* __restrict__ gscale) {
   // block = 256 threads = G channel groups x R pixel lanes (G = C/8 divides 256): every thread keeps ONE channel
   // group, so the per-channel constants are loaded once
   const int G = C >> 3, R = 256 / G;
   if (blockIdx.x == 0) {
+    const double inv = (double)gscale_inv(gscale);     // fp16 mode: the gradients carry a power-of-two scale
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      if (dbeta) dbeta[c] = (float)sums[c];
-      if (dgamma) dgamma[c] = (float)sums[C + c];
+      if (dbeta) dbeta[c] = (float)(sums[c] * inv);
+      if (dgamma) dgamma[c] = (float)(sums[C + c] * inv);
     }
   }
   const int cg = threadIdx.x % G, r = threadIdx.x / G;
@@ -575,20 +562,49 @@ __global__ void __launch_bounds__(256) pack_weight_multi_kernel(const __grid_con
   }
 }
 
-__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Co, int Ci, int CiPad, int hilo) {
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Co, int Ci, int CiPad, int hilo,
+                                    const float* __restrict__ gscale) {
   const long long items = (long long)Co * Ci * 9;
+  const float inv = gscale_inv(gscale);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
     const int tap = (int)(i % 9);
     const int ci = (int)((i / 9) % Ci);
     const int co = (int)(i / (9LL * Ci));
     const float* row = dwp + ((long long)co * 9 + tap) * CiPad;
-    dw[i] = hilo ? row[ci] + row[3 + ci] : row[ci];   // hi/lo input split: d/dw sums the x_hi and x_lo channels
+    dw[i] = (hilo ? row[ci] + row[3 + ci] : row[ci]) * inv;   // hi/lo input split: d/dw sums the x_hi and x_lo channels
   }
 }
 
-__global__ void cast_f64_f32_kernel(const double* __restrict__ s, float* __restrict__ d, long long n) {
+__global__ void cast_f64_f32_kernel(const double* __restrict__ s, float* __restrict__ d, long long n, const float* __restrict__ gscale) {
+  const double inv = (double)gscale_inv(gscale);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    d[i] = (float)s[i];
+    d[i] = (float)(s[i] * inv);
+}
+
+// ---- fp16 mode: power-of-two gradient scale from the largest |dout| (all of backward is linear in dout) ----
+__global__ void absmax_kernel(const float* __restrict__ g, long long n, unsigned int* __restrict__ bits) {
+  float m = 0.f;
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));   // fmaxf drops NaN operands
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(g[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(bits, __float_as_uint(m));   // non-negative floats order like their bits
+}
+__global__ void grad_scale_finalize_kernel(float* __restrict__ gscale, float target) {
+  const float m = __uint_as_float(reinterpret_cast<const unsigned int*>(gscale)[2]);
+  float S = 1.f;
+  if (m > 0.f && m < 3.0e38f) {                      // zero / inf gradients: leave them unscaled
+    int e = (int)floorf(log2f(target / m));
+    e = e < -60 ? -60 : (e > 60 ? 60 : e);
+    S = exp2f((float)e);
+  }
+  gscale[0] = S;
+  gscale[1] = 1.f / S;
 }
 
 static int check_vec(const void* p, int ld, int C, const char* what) {
@@ -603,7 +619,7 @@ static int check_vec(const void* p, int ld, int C, const char* what) {
 namespace eunet {
 int g_opt_bn_tma = 1;
 int bn_apply_relu_tma(const void* y, int ldy, void* out, int ldo, long long M, int C, const float* scale, const float* shift,
-                      cudaStream_t st);
+                      bool out_f16, cudaStream_t st);
 }  // namespace eunet
 
 using namespace eunet;
@@ -640,8 +656,8 @@ int eunet_bn_apply_relu(const void* y, int ldy, void* out, int ldo, void* pooled
     DISPATCH_DTYPE(dtype, bn_apply_relu_pool_kernel<T, TY><<<ew_grid(M / 4 * (C / 8)), 256, 0, st>>>(
                               (const TY*)y, ldy, (T*)out, ldo, (T*)pooled, ldp, B, H, W, C, scale, shift));
   } else {
-    if (dtype == EUNET_BF16 && g_opt_bn_tma) {
-      const int rc = bn_apply_relu_tma(y, ldy, out, ldo, M, C, scale, shift, st);
+    if ((dtype == EUNET_BF16 || dtype == EUNET_F16) && g_opt_bn_tma) {
+      const int rc = bn_apply_relu_tma(y, ldy, out, ldo, M, C, scale, shift, dtype == EUNET_F16, st);
       if (rc <= 0) return rc;      // launched or failed; 1 = shape not covered, ring kernel below
     }
     EUNET_REQUIRE(C <= 2048 && 256 % (C / 8) == 0, "bn_apply_relu: C/8=%d must divide 256", C / 8);
@@ -670,7 +686,7 @@ int eunet_bn_bwd_reduce(const void* dact, int ldd, const void* y, int ldy, int d
 
 int eunet_bn_bwd_apply(const void* dact, int ldd, const void* y, int ldy, void* dy, int lddy, int dtype, long long M, int C,
                        const float* scale, const float* shift, const float* mean, const float* invstd, const double* sums,
-                       float* dgamma, float* dbeta, void* stream) {
+                       float* dgamma, float* dbeta, const float* gscale, void* stream) {
   if (check_vec(dact, ldd, C, "bn_bwd_apply(dact)") || check_vec(y, ldy, C, "bn_bwd_apply(y)") ||
       check_vec(dy, lddy, C, "bn_bwd_apply(dy)"))
     return -1;
@@ -679,7 +695,7 @@ int eunet_bn_bwd_apply(const void* dact, int ldd, const void* y, int ldy, void* 
   DISPATCH_DTYPE(dtype, bn_ring_smem_attr((const void*)bn_bwd_apply_kernel<T, TY>, (int)(8 * 256 * kBnStages * (sizeof(T) + sizeof(TY))));
                  bn_bwd_apply_kernel<T, TY><<<clamp_grid((M + 256 / (C / 8) - 1) / (256 / (C / 8)), 8), 256, 8 * 256 * kBnStages * (sizeof(T) + sizeof(TY)), (cudaStream_t)stream>>>(
                             (const T*)dact, ldd, (const TY*)y, ldy, (T*)dy, lddy, M, C, scale, shift, mean, invstd, sums, dgamma,
-                            dbeta));
+                            dbeta, gscale));
   return check_launch("bn_bwd_apply");
 }
 
@@ -768,16 +784,28 @@ int eunet_pack_weight3x3_multi(const void* const* w, void* const* out, const int
   return check_launch("pack_weight3x3_multi");
 }
 
-int eunet_unpack_wgrad3x3(const float* dw_packed, float* dw, int Co, int Ci, int CiPad, int hilo, void* stream) {
+int eunet_unpack_wgrad3x3(const float* dw_packed, float* dw, int Co, int Ci, int CiPad, int hilo, const float* gscale,
+                          void* stream) {
   EUNET_REQUIRE(Co > 0 && Ci > 0 && CiPad >= Ci && (!hilo || (Ci == 3 && CiPad >= 6)), "unpack_wgrad3x3: bad shape");
-  unpack_wgrad_kernel<<<ew_grid((long long)Co * Ci * 9), 256, 0, (cudaStream_t)stream>>>(dw_packed, dw, Co, Ci, CiPad, hilo);
+  unpack_wgrad_kernel<<<ew_grid((long long)Co * Ci * 9), 256, 0, (cudaStream_t)stream>>>(dw_packed, dw, Co, Ci, CiPad, hilo, gscale);
   return check_launch("unpack_wgrad3x3");
 }
 
-int eunet_cast_f64_f32(const double* src, float* dst, long long n, void* stream) {
+int eunet_cast_f64_f32(const double* src, float* dst, long long n, const float* gscale, void* stream) {
   EUNET_REQUIRE(n > 0, "cast_f64_f32: n=%lld", n);
-  cast_f64_f32_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(src, dst, n);
+  cast_f64_f32_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(src, dst, n, gscale);
   return check_launch("cast_f64_f32");
+}
+
+int eunet_grad_scale(const float* g, long long n, float target_max, float* gscale, void* stream) {
+  EUNET_REQUIRE(g && gscale && n > 0 && target_max > 0.f, "grad_scale: bad arguments");
+  EUNET_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, "grad_scale: g must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(gscale + 2, 0, 4, st);
+  EUNET_REQUIRE(e == cudaSuccess, "grad_scale: cudaMemsetAsync: %s", cudaGetErrorString(e));
+  absmax_kernel<<<clamp_grid((n / 4 + 255) / 256, 8), 256, 0, st>>>(g, n, reinterpret_cast<unsigned int*>(gscale) + 2);
+  grad_scale_finalize_kernel<<<1, 1, 0, st>>>(gscale, target_max);
+  return check_launch("grad_scale");
 }
 
 }  // extern "C"

@@ -106,6 +106,8 @@ extern "C" int eunet_fusion_gate_fwd(const float* out_main, const float* out_aux
   const int grid = clamp_grid((M + 255) / 256, 8);
   if (dtype == EUNET_BF16)
     fusion_gate_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(out_main, out_aux, p, (__nv_bfloat16*)fg16, res4, B, H, W);
+  else if (dtype == EUNET_F16)
+    fusion_gate_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>(out_main, out_aux, p, (__half*)fg16, res4, B, H, W);
   else if (dtype == EUNET_F32)
     fusion_gate_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(out_main, out_aux, p, (float*)fg16, res4, B, H, W);
   else {

@@ -63,12 +63,16 @@ loss_fwd_kernel(const float* __restrict__ logits, const long long* __restrict__ 
     float z[3], lp[3], p[3];
     load_logits<SCALE>(logits, b, h, w, H, W, z);
     softmax3(z, lp, p);
-    const int t = clamp_target(target[(long long)b * HW + i]);
+    const long long traw = target[(long long)b * HW + i];
+    const int t = clamp_target(traw);
     const float ce = -lp[t] * kCEW[t];
     const float pt = expf(-ce);
     const float u = 1.f - pt;
     const float u2 = u * u;
     acc[0] += kAlpha[t] * (u2 * u2 * u) * ce;
+    // a label outside {0,1,2} (e.g. the ignore value 255) makes the reference's F.cross_entropy raise; a kernel cannot
+    // raise, so it poisons the loss with NaN instead of silently training on a clamped label
+    if (traw < 0 || traw > 2) acc[0] = __int_as_float(0x7fc00000);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       acc[1 + c] += (t == c) ? p[c] : 0.f;

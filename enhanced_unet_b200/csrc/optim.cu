@@ -174,8 +174,9 @@ extern "C" int eunet_adamw_step(float* p, const float* g, float* m, float* v, lo
                                 float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                                 void* stream) {
   EUNET_REQUIRE(n > 0 && step >= 1, "adamw_step: n=%lld step=%d", n, step);
-  const float bc1 = 1.f - powf(beta1, (float)step);
-  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  // bias corrections in double, as torch.optim.AdamW forms them in Python floats (1 - 0.999f^step carries ~6e-5 in fp32)
+  const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
   adamw_kernel<<<clamp_grid((n + 255) / 256, 8), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, gradsq, max_norm, lr, beta1, beta2,
                                                                                  eps, weight_decay, bc1, bc2_sqrt, grad_scale);
   return check_launch("adamw_step");
@@ -198,8 +199,9 @@ extern "C" int eunet_adamw_multi(void* const* p, const void* const* g, void* con
                                  const double* gradsq, float max_norm, float lr, float beta1, float beta2, float eps,
                                  float weight_decay, int step, float grad_scale, void* stream) {
   EUNET_REQUIRE(count > 0 && step >= 1, "adamw_multi: count=%d step=%d", count, step);
-  const float bc1 = 1.f - powf(beta1, (float)step);
-  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  // bias corrections in double, as torch.optim.AdamW forms them in Python floats (1 - 0.999f^step carries ~6e-5 in fp32)
+  const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
   for (int first = 0; first < count; first += kMaxTensors) {
     TensorTable t;
     const int c = count - first < kMaxTensors ? count - first : kMaxTensors;

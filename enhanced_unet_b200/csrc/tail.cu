@@ -11,21 +11,7 @@
 
 namespace eunet {
 
-#define DISPATCH_DTYPE(dtype, ...)                          \
-  do {                                                      \
-    if ((dtype) == EUNET_BF16) {                            \
-      using T = __nv_bfloat16;                              \
-      using TY = __half;                                    \
-      __VA_ARGS__;                                          \
-    } else if ((dtype) == EUNET_F32) {                      \
-      using T = float;                                      \
-      using TY = float;                                     \
-      __VA_ARGS__;                                          \
-    } else {                                                \
-      set_error("unknown dtype %d", (int)(dtype));          \
-      return -1;                                            \
-    }                                                       \
-  } while (0)
+#define DISPATCH_DTYPE EUNET_DISPATCH_DTYPE
 
 __device__ __forceinline__ float group8_sum(float v) {
   v += __shfl_xor_sync(0xffffffffu, v, 1);
@@ -104,11 +90,13 @@ __global__ void tail_up_fwd_kernel(const float* __restrict__ z4, T* __restrict__
 }
 
 // NCHW fp32 [B,3,Ho,Wo] -> pixel-major float4 (3 channels + pad): one 16-byte load per pixel for the tail kernels
-__global__ void tail_pack3_kernel(const float* __restrict__ src, float* __restrict__ dst4, int B, long long HW) {
+__global__ void tail_pack3_kernel(const float* __restrict__ src, float* __restrict__ dst4, int B, long long HW,
+                                  const float* __restrict__ gscale) {
+  const float S = gscale_fwd(gscale);       // fp16 mode: power-of-two gradient scale (exact)
   for (int b = blockIdx.y; b < B; b += gridDim.y)
     for (long long hw = (long long)blockIdx.x * blockDim.x + threadIdx.x; hw < HW; hw += (long long)gridDim.x * blockDim.x) {
       const float* p = src + (long long)b * 3 * HW + hw;
-      reinterpret_cast<float4*>(dst4)[(long long)b * HW + hw] = make_float4(__ldg(p), __ldg(p + HW), __ldg(p + 2 * HW), 0.f);
+      reinterpret_cast<float4*>(dst4)[(long long)b * HW + hw] = make_float4(S * __ldg(p), S * __ldg(p + HW), S * __ldg(p + 2 * HW), 0.f);
     }
 }
 
@@ -380,9 +368,17 @@ __device__ __forceinline__ void load3<__nv_bfloat16>(const __nv_bfloat16* p, flo
   v[2] = __uint_as_float(t.y << 16);
 }
 
+template <>
+__device__ __forceinline__ void load3<__half>(const __half* p, float v[3]) {
+  const uint2 t = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+  v[0] = a.x; v[1] = a.y; v[2] = b.x;
+}
+
 template <typename T>
 __global__ void tail_up_bwd_kernel(const T* __restrict__ dd1p, int stride, const float* __restrict__ dout,
-                                   float* __restrict__ dz4, int B, int H, int W) {
+                                   float* __restrict__ dz4, int B, int H, int W, const float* __restrict__ gscale) {
+  const float S = gscale_fwd(gscale);       // dd1p carries the gradient scale already, dout (the caller's tensor) does not
   const int Wo = 2 * W, Ho = 2 * H;
   const long long HWo = (long long)Ho * Wo;
   for (int row = blockIdx.x; row < B * H; row += gridDim.x)
@@ -405,9 +401,9 @@ __global__ void tail_up_bwd_kernel(const T* __restrict__ dd1p, int stride, const
         load3<T>(dd1p + op * stride, v);
         const float* dp = dout + (long long)b * 3 * HWo + (long long)oy * Wo + ox;
         const float wgt = wy[r] * wx[s];
-        a0 += wgt * (v[0] + __ldg(dp));
-        a1 += wgt * (v[1] + __ldg(dp + HWo));
-        a2 += wgt * (v[2] + __ldg(dp + 2 * HWo));
+        a0 += wgt * fmaf(S, __ldg(dp), v[0]);
+        a1 += wgt * fmaf(S, __ldg(dp + HWo), v[1]);
+        a2 += wgt * fmaf(S, __ldg(dp + 2 * HWo), v[2]);
       }
     }
     reinterpret_cast<float4*>(dz4)[i] = make_float4(a0, a1, a2, 0.f);
@@ -468,9 +464,10 @@ namespace eunet {
 int g_opt_tail_out_tma = 1;
 int tail_out_fwd_tma(const float* d14, const void* mid, const float* scale, const float* shift, const float* w3, const float* b3,
                      float* out, int B, int H, int W, cudaStream_t st);
-int tail_dec1_fwd_tma(const void* d2, int ldd2, const float* w1, const float* b1, float* z4, long long M, cudaStream_t st);
-int tail_dec1_bwd_tma(const float* dz4, const void* d2, int ldd2, void* dd2, int lddd2, const float* w1, double* acc, long long M,
+int tail_dec1_fwd_tma(const void* d2, int ldd2, const float* w1, const float* b1, float* z4, long long M, bool f16,
                       cudaStream_t st);
+int tail_dec1_bwd_tma(const float* dz4, const void* d2, int ldd2, void* dd2, int lddd2, const float* w1, double* acc, long long M,
+                      bool f16, cudaStream_t st);
 int tail_bwd_reduce_tma(const float* dout4, const void* mid, const float* scale, const float* shift, const float* mean,
                         const float* invstd, const float* w3, double* acc, int B, int H, int W, cudaStream_t st);
 }  // namespace eunet
@@ -482,21 +479,21 @@ extern "C" {
 int eunet_tail_dec1_fwd(const void* d2, int ldd2, int dtype, const float* w1, const float* b1, float* z4, long long M,
                         void* stream) {
   EUNET_REQUIRE(M > 0 && ldd2 >= 64 && (ldd2 & 7) == 0, "tail_dec1_fwd: bad shape M=%lld ld=%d", M, ldd2);
-  if (dtype == EUNET_BF16 && g_opt_tail_out_tma) {
-    const int rc = tail_dec1_fwd_tma(d2, ldd2, w1, b1, z4, M, (cudaStream_t)stream);
+  if ((dtype == EUNET_BF16 || dtype == EUNET_F16) && g_opt_tail_out_tma) {
+    const int rc = tail_dec1_fwd_tma(d2, ldd2, w1, b1, z4, M, dtype == EUNET_F16, (cudaStream_t)stream);
     if (rc <= 0) return rc;      // launched or failed; 1 = too small, 8-lanes-per-pixel kernel below
   }
   DISPATCH_DTYPE(dtype, tail_dec1_fwd_kernel<T><<<rows_grid(M), 256, 0, (cudaStream_t)stream>>>((const T*)d2, ldd2, w1, b1, z4, M));
   return check_launch("tail_dec1_fwd");
 }
 
-int eunet_tail_pack3(const float* src, float* dst4, int B, int H, int W, void* stream) {
+int eunet_tail_pack3(const float* src, float* dst4, int B, int H, int W, const float* gscale, void* stream) {
   EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "tail_pack3: bad shape");
   {
     const long long HW = (long long)H * W;
     long long bx = (HW + 255) / 256, cap = ((long long)kNumSMs * 8 + B - 1) / B;
     dim3 grid((unsigned)(bx < cap ? bx : cap), (unsigned)(B < 65535 ? B : 65535));
-    tail_pack3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst4, B, HW);
+    tail_pack3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst4, B, HW, gscale);
   }
   return check_launch("tail_pack3");
 }
@@ -510,7 +507,7 @@ int eunet_tail_up_fwd(const float* z4, void* d1p, float* d14, int dtype, int B, 
 int eunet_tail_out_fwd(const float* d14, const void* mid, int dtype, const float* scale, const float* shift, const float* w3,
                        const float* b3, float* out, int B, int H, int W, void* stream) {
   EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "tail_out_fwd: bad shape");
-  if (dtype == EUNET_BF16 && g_opt_tail_out_tma) {
+  if ((dtype == EUNET_BF16 || dtype == EUNET_F16) && g_opt_tail_out_tma) {
     const int rc = tail_out_fwd_tma(d14, mid, scale, shift, w3, b3, out, B, H, W, (cudaStream_t)stream);
     if (rc <= 0) return rc;      // launched or failed; 1 = too small, use the thread-per-pixel kernel
   }
@@ -524,7 +521,7 @@ int eunet_tail_bwd_reduce(const float* dout, const void* mid, int dtype, const f
                           const float* mean, const float* invstd, const float* w3, double* acc, int B, int H, int W,
                           void* stream) {
   EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "tail_bwd_reduce: bad shape");
-  if (dtype == EUNET_BF16 && g_opt_tail_out_tma) {
+  if ((dtype == EUNET_BF16 || dtype == EUNET_F16) && g_opt_tail_out_tma) {
     const int rc = tail_bwd_reduce_tma(dout, mid, scale, shift, mean, invstd, w3, acc, B, H, W, (cudaStream_t)stream);
     if (rc <= 0) return rc;      // launched or failed; 1 = too small, use the ring kernel
   }
@@ -545,19 +542,19 @@ int eunet_tail_bwd_dmid(const float* dout, const void* mid, void* dmid, int dtyp
 }
 
 int eunet_tail_up_bwd(const void* dd1p, int dtype, int dd1_stride, const float* dout, float* dz4, int B, int H, int W,
-                      void* stream) {
+                      const float* gscale, void* stream) {
   EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "tail_up_bwd: bad shape");
   EUNET_REQUIRE(dd1_stride >= 4 && dd1_stride % 4 == 0, "tail_up_bwd: dd1_stride %d must be a multiple of 4 (>= 4)", dd1_stride);
   DISPATCH_DTYPE(dtype, tail_up_bwd_kernel<T><<<clamp_grid((long long)B * H, 16), 256, 0, (cudaStream_t)stream>>>(
-                            (const T*)dd1p, dd1_stride, dout, dz4, B, H, W));
+                            (const T*)dd1p, dd1_stride, dout, dz4, B, H, W, gscale));
   return check_launch("tail_up_bwd");
 }
 
 int eunet_tail_dec1_bwd(const float* dz4, const void* d2, int ldd2, void* dd2, int lddd2, int dtype, const float* w1,
                         double* acc, long long M, void* stream) {
   EUNET_REQUIRE(M > 0 && ldd2 >= 64 && lddd2 >= 64, "tail_dec1_bwd: bad shape");
-  if (dtype == EUNET_BF16 && g_opt_tail_out_tma && (ldd2 & 7) == 0 && (lddd2 & 7) == 0) {
-    const int rc = tail_dec1_bwd_tma(dz4, d2, ldd2, dd2, lddd2, w1, acc, M, (cudaStream_t)stream);
+  if ((dtype == EUNET_BF16 || dtype == EUNET_F16) && g_opt_tail_out_tma && (ldd2 & 7) == 0 && (lddd2 & 7) == 0) {
+    const int rc = tail_dec1_bwd_tma(dz4, d2, ldd2, dd2, lddd2, w1, acc, M, dtype == EUNET_F16, (cudaStream_t)stream);
     if (rc <= 0) return rc;      // launched or failed; 1 = too small, 8-lanes-per-pixel kernel below
   }
   DISPATCH_DTYPE(dtype, tail_dec1_bwd_kernel<T><<<rows_grid(M), 256, 0, (cudaStream_t)stream>>>(dz4, (const T*)d2, ldd2, (T*)dd2,

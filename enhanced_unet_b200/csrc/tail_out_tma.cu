@@ -39,7 +39,7 @@ struct TailOutParams {
 
 // DEC1 = true: the same streaming layout for z = dec1(d2) (1x1, 64 -> 3, models.py:212, evaluated at HxW): bf16 input rows
 // (any row stride), no affine / ReLU / residual, output fp32 [pixels][4] (z4) instead of NCHW planes.
-template <bool DEC1>
+template <bool DEC1, bool F16>
 __global__ void __launch_bounds__(288, 2)
 tail_out_tma_kernel(const __grid_constant__ CUtensorMap tmMid, const __grid_constant__ CUtensorMap tmRes, const TailOutParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -102,9 +102,8 @@ tail_out_tma_kernel(const __grid_constant__ CUtensorMap tmMid, const __grid_cons
 #pragma unroll
         for (int e2 = 0; e2 < 4; ++e2) {
           float a0, a1;
-          if (DEC1) {      // bf16 activations, plain dot products
-            a0 = __uint_as_float(hw[e2] << 16);
-            a1 = __uint_as_float(hw[e2] & 0xffff0000u);
+          if (DEC1) {      // bf16 / fp16 activations, plain dot products
+            unpack16x2<F16>(hw[e2], a0, a1);
           } else {         // raw fp16 conv outputs: BN affine + ReLU first
             const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[e2]));
             a0 = fmaxf(fmaf(f.x, sc[2 * e2], sh[2 * e2]), 0.f);
@@ -178,19 +177,18 @@ int tail_out_fwd_tma(const float* d14, const void* mid, const float* scale, cons
     if (tc::encode_tensor_map_bf16(&tmRes, d14, 2, dims, str, box, 0)) return -1;
   }
   constexpr int SMEM = 1024 + kToStages * kToStage + 2 * kToPart;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tail_out_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+  {   // set on every launch: the attribute is per device, and a process may drive more than one GPU
+    cudaError_t e = cudaFuncSetAttribute(tail_out_tma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     EUNET_REQUIRE(e == cudaSuccess, "tail_out_fwd: cudaFuncSetAttribute(%d): %s", SMEM, cudaGetErrorString(e));
-    configured = true;
   }
   const int grid = p.tiles < 2 * kNumSMs ? p.tiles : 2 * kNumSMs;   // two co-resident CTAs: one reduces / stores while the other streams
-  tail_out_tma_kernel<false><<<grid, 288, SMEM, st>>>(tmMid, tmRes, p);
+  tail_out_tma_kernel<false, false><<<grid, 288, SMEM, st>>>(tmMid, tmRes, p);
   return check_launch("tail_out_fwd(tma)");
 }
 
 // z4 = dec1(d2): returns 0 = launched, 1 = not applicable, < 0 = error
-int tail_dec1_fwd_tma(const void* d2, int ldd2, const float* w1, const float* b1, float* z4, long long M, cudaStream_t st) {
+int tail_dec1_fwd_tma(const void* d2, int ldd2, const float* w1, const float* b1, float* z4, long long M, bool f16,
+                      cudaStream_t st) {
   TailOutParams p;
   p.scale = nullptr; p.shift = nullptr; p.w3 = w1; p.b3 = b1; p.out = z4;
   p.HW = 1;
@@ -206,14 +204,14 @@ int tail_dec1_fwd_tma(const void* d2, int ldd2, const float* w1, const float* b1
     if (tc::encode_tensor_map_bf16(&tmIn, d2, 2, dims, str, box, 128)) return -1;
   }
   constexpr int SMEM = 1024 + kToStages * kToStage + 2 * kToPart;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tail_out_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+  {   // set on every launch: the attribute is per device, and a process may drive more than one GPU
+    cudaError_t e = cudaFuncSetAttribute(f16 ? tail_out_tma_kernel<true, true> : tail_out_tma_kernel<true, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     EUNET_REQUIRE(e == cudaSuccess, "tail_dec1_fwd: cudaFuncSetAttribute(%d): %s", SMEM, cudaGetErrorString(e));
-    configured = true;
   }
   const int grid = p.tiles < 2 * kNumSMs ? p.tiles : 2 * kNumSMs;
-  tail_out_tma_kernel<true><<<grid, 288, SMEM, st>>>(tmIn, tmIn, p);
+  if (f16) tail_out_tma_kernel<true, true><<<grid, 288, SMEM, st>>>(tmIn, tmIn, p);
+  else tail_out_tma_kernel<true, false><<<grid, 288, SMEM, st>>>(tmIn, tmIn, p);
   return check_launch("tail_dec1_fwd(tma)");
 }
 
@@ -363,11 +361,9 @@ int tail_bwd_reduce_tma(const float* dout4, const void* mid, const float* scale,
     if (tc::encode_tensor_map_bf16(&tmG, dout4, 2, dims, str, box, 0)) return -1;
   }
   constexpr int SMEM = 1024 + kTrStages * kToStage;
-  static bool configured = false;
-  if (!configured) {
+  {   // set on every launch: the attribute is per device, and a process may drive more than one GPU
     cudaError_t e = cudaFuncSetAttribute(tail_reduce_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     EUNET_REQUIRE(e == cudaSuccess, "tail_bwd_reduce: cudaFuncSetAttribute(%d): %s", SMEM, cudaGetErrorString(e));
-    configured = true;
   }
   const int grid = p.tiles < 2 * kNumSMs ? p.tiles : 2 * kNumSMs;
   tail_reduce_tma_kernel<<<grid, 288, SMEM, st>>>(tmMid, tmG, p);
@@ -385,6 +381,7 @@ struct Dec1BwdParams {
   int tiles;
 };
 
+template <bool F16>
 __global__ void __launch_bounds__(288, 2)
 tail_dec1_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmD2, const __grid_constant__ CUtensorMap tmDz,
                          const __grid_constant__ CUtensorMap tmOut, const Dec1BwdParams p) {
@@ -442,7 +439,8 @@ tail_dec1_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmD2, const __grid_
         float o[8];
 #pragma unroll
         for (int e2 = 0; e2 < 4; ++e2) {
-          const float v[2] = {__uint_as_float(hw[e2] << 16), __uint_as_float(hw[e2] & 0xffff0000u)};
+          float v[2];
+          unpack16x2<F16>(hw[e2], v[0], v[1]);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int e = 2 * e2 + h;
@@ -453,8 +451,8 @@ tail_dec1_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmD2, const __grid_
           }
         }
         if (w == 0) { db0 += z0; db1 += z1; db2 += z2; }
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + off), "r"(pack_bf16x2(o[0], o[1])), "r"(pack_bf16x2(o[2], o[3])),
-                     "r"(pack_bf16x2(o[4], o[5])), "r"(pack_bf16x2(o[6], o[7]))
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + off), "r"(pack16x2<F16>(o[0], o[1])), "r"(pack16x2<F16>(o[2], o[3])),
+                     "r"(pack16x2<F16>(o[4], o[5])), "r"(pack16x2<F16>(o[6], o[7]))
                      : "memory");
       }
       // input stage consumed; the staged gradient tile goes out with one tensor store (rows past M are clipped).  The
@@ -494,7 +492,7 @@ tail_dec1_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmD2, const __grid_
 
 // returns 0 = launched, 1 = not applicable, < 0 = error
 int tail_dec1_bwd_tma(const float* dz4, const void* d2, int ldd2, void* dd2, int lddd2, const float* w1, double* acc, long long M,
-                      cudaStream_t st) {
+                      bool f16, cudaStream_t st) {
   if (M < 4 * kToTile) return 1;
   const long long tiles = (M + kToTile - 1) / kToTile;
   if (tiles > 0x7fffffffLL) return 1;
@@ -517,14 +515,14 @@ int tail_dec1_bwd_tma(const float* dz4, const void* d2, int ldd2, void* dd2, int
     if (tc::encode_tensor_map_bf16(&tmOut, dd2, 2, dims, str, box, 128)) return -1;
   }
   constexpr int SMEM = 1024 + kToStages * kToStage + 2 * kToMid;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tail_dec1_bwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+  {   // set on every launch: the attribute is per device, and a process may drive more than one GPU
+    cudaError_t e = cudaFuncSetAttribute(f16 ? tail_dec1_bwd_tma_kernel<true> : tail_dec1_bwd_tma_kernel<false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     EUNET_REQUIRE(e == cudaSuccess, "tail_dec1_bwd: cudaFuncSetAttribute(%d): %s", SMEM, cudaGetErrorString(e));
-    configured = true;
   }
   const int grid = p.tiles < 2 * kNumSMs ? p.tiles : 2 * kNumSMs;
-  tail_dec1_bwd_tma_kernel<<<grid, 288, SMEM, st>>>(tmD2, tmDz, tmOut, p);
+  if (f16) tail_dec1_bwd_tma_kernel<true><<<grid, 288, SMEM, st>>>(tmD2, tmDz, tmOut, p);
+  else tail_dec1_bwd_tma_kernel<false><<<grid, 288, SMEM, st>>>(tmD2, tmDz, tmOut, p);
   return check_launch("tail_dec1_bwd(tma)");
 }
 

@@ -27,9 +27,14 @@ __host__ __device__ constexpr uint64_t make_smem_desc(uint32_t addr_bytes, uint3
 // instruction descriptor for kind::f16 with bf16 A/B and fp32 accumulate
 //   [4,6) c_format (1 = f32)  [7,10) a_format (1 = bf16)  [10,13) b_format (1 = bf16)
 //   [15] a_major (0 = K, 1 = MN)  [16] b_major  [17,23) N >> 3  [24,29) M >> 4
-__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t m, uint32_t n, uint32_t a_mn_major, uint32_t b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((n >> 3) << 17) |
+//   fmt16: operand format of BOTH A and B, 1 = bf16, 0 = fp16.  (The hardware rejects mixed fp16 x bf16 operands with an
+//   illegal-instruction fault - probed on B200, tests/test_gpu_probe.py::test_operand_formats.)
+__host__ __device__ constexpr uint32_t make_idesc_16(uint32_t m, uint32_t n, uint32_t a_mn_major, uint32_t b_mn_major, uint32_t fmt16) {
+  return (1u << 4) | (fmt16 << 7) | (fmt16 << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((n >> 3) << 17) |
          ((m >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t m, uint32_t n, uint32_t a_mn_major, uint32_t b_mn_major) {
+  return make_idesc_16(m, n, a_mn_major, b_mn_major, 1u);
 }
 
 #ifdef __CUDACC__

@@ -43,7 +43,10 @@ class _Ctx:
         self.dev = device
         self.dt = act_dtype
         self.code = lib.dtype_code(act_dtype)
-        self.raw = lib.raw_dtype(act_dtype)   # pre-BN conv outputs: fp16 in bf16 mode, fp32 in fp32 mode
+        self.raw = lib.raw_dtype(act_dtype)   # pre-BN conv outputs: fp16 in the 16-bit modes, fp32 in fp32 mode
+        self.tc = act_dtype in (torch.bfloat16, torch.float16)    # tensor-core (tcgen05) convolutions
+        self.amax: Optional[torch.Tensor] = None    # fp16 saturation monitor (1 float, sticky max of |y| beyond the fp16 range)
+        self.gs: Optional[torch.Tensor] = None      # fp16 mode, backward: {S, 1/S} gradient scale (eunet_grad_scale)
 
     def empty(self, *shape, dtype=None):
         return torch.empty(*shape, device=self.dev, dtype=dtype or self.dt)
@@ -140,18 +143,23 @@ def pack_specs(cx: _Ctx, train: bool):
 
 def conv3x3(cx: _Ctx, x: torch.Tensor, wp: torch.Tensor, y: torch.Tensor, B: int, H: int, W: int, cin: int, cout: int,
             stats: Optional[torch.Tensor] = None, scale: Optional[torch.Tensor] = None,
-            shift: Optional[torch.Tensor] = None, relu: bool = False) -> None:
+            shift: Optional[torch.Tensor] = None, relu: bool = False, cin_real: int = 0, cout_real: int = 0) -> None:
+    """``cin`` / ``cout`` are the (16-padded) channel counts the kernel runs on; ``cin_real`` (when the input is a padded
+    3-channel tensor) (``cout_real`` for a dgrad onto 3 channels) is what the ALGORITHMIC FLOP count of the launch uses (SURVEY.md §8d:
+    K = 9 * 3 = 27); such launches are tagged "k27" (HBM-roofline kernels), the others "tc" (tensor-core roofline)."""
     out_raw = int(y.dtype == cx.raw and cx.raw != cx.dt)
     assert y.dtype in (cx.dt, cx.raw) and x.dtype == cx.dt
     call("eunet_conv3x3_fwd", ptr(x), _ld(x), ptr(wp), ptr(y), _ld(y), cx.code, B, H, W, cin, cout, ptr(stats), ptr(scale),
-         ptr(shift), int(relu), out_raw, flops=2.0 * B * H * W * cout * 9 * cin)
+         ptr(shift), int(relu), out_raw, ptr(cx.amax), flops=2.0 * B * H * W * (cout_real or cout) * 9 * (cin_real or cin),
+         tag="k27" if (cin_real or cout_real) else "tc")
 
 
 class _ZeroPool:
-    """One zero-filled fp32 workspace (a single fill launch) that hands out the packed wgrad accumulators of a backward pass."""
+    """One zero-filled workspace (a single fill launch) that hands out the accumulators of a pass: packed wgrad
+    accumulators (fp32), BatchNorm statistics / backward sums (fp64), exact-zero bias gradients (fp32)."""
 
-    def __init__(self, cx: _Ctx, numel: int):
-        self.buf = cx.zeros(numel, dtype=torch.float32)
+    def __init__(self, cx: _Ctx, numel: int, dtype: torch.dtype = torch.float32):
+        self.buf = cx.zeros(numel, dtype=dtype)
         self.off = 0
 
     def take(self, *shape) -> torch.Tensor:
@@ -159,10 +167,14 @@ class _ZeroPool:
         for d in shape:
             n *= d
         if self.off + n > self.buf.numel():
-            raise RuntimeError("wgrad workspace exhausted")
+            raise RuntimeError("zero-filled workspace exhausted")
         t = self.buf[self.off:self.off + n].view(*shape)
         self.off += (n + 63) // 64 * 64
         return t
+
+
+STATS_NUMEL = 2 * (2 * sum(c for _, _, c in BLOCKS) + 64) + 64 * len(BLOCKS) * 2 + 1024   # fp64 accumulators of one pass (+ padding)
+ZERO_BIAS_NUMEL = 2 * sum(c for _, _, c in BLOCKS) + 64 + 64 * (2 * len(BLOCKS) + 1)
 
 
 def wgrad_workspace_numel() -> int:
@@ -173,17 +185,18 @@ def wgrad_workspace_numel() -> int:
 
 
 def conv3x3_wgrad(cx: _Ctx, x: torch.Tensor, dy: torch.Tensor, B: int, H: int, W: int, cin: int, cout: int,
-                  pool: Optional[_ZeroPool] = None) -> torch.Tensor:
+                  pool: Optional[_ZeroPool] = None, cin_real: int = 0) -> torch.Tensor:
     dwp = pool.take(cout, 9, cin) if pool is not None else cx.zeros(cout, 9, cin, dtype=torch.float32)
     call("eunet_conv3x3_wgrad", ptr(x), _ld(x), ptr(dy), _ld(dy), ptr(dwp), cx.code, B, H, W, cin, cout,
-         flops=2.0 * B * H * W * cout * 9 * cin)
+         flops=2.0 * B * H * W * cout * 9 * (cin_real or cin), tag="k27" if cin_real else "tc")
     return dwp
 
 
-def unpack_wgrad(dwp: torch.Tensor, co: int, ci: int, hilo: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def unpack_wgrad(dwp: torch.Tensor, co: int, ci: int, hilo: bool = False, out: Optional[torch.Tensor] = None,
+                 gscale: Optional[torch.Tensor] = None) -> torch.Tensor:
     dw = out if out is not None else torch.empty(co, ci, 3, 3, device=dwp.device, dtype=torch.float32)
     assert dw.is_contiguous() and dw.numel() == co * ci * 9 and dw.dtype == torch.float32
-    call("eunet_unpack_wgrad3x3", ptr(dwp), ptr(dw), co, ci, dwp.shape[2], int(hilo))
+    call("eunet_unpack_wgrad3x3", ptr(dwp), ptr(dw), co, ci, dwp.shape[2], int(hilo), ptr(gscale))
     return dw
 
 
@@ -198,6 +211,13 @@ class GradSink:
 
     def dst(self, name: str, shape) -> torch.Tensor:
         t = torch.empty(shape, device=self.dev, dtype=torch.float32)
+        self.grads[name] = t
+        return t
+
+    def zero_dst(self, name: str, shape, pool: "_ZeroPool") -> torch.Tensor:
+        """Destination of a gradient that is EXACTLY zero (conv bias in front of a train-mode BN): a slice of the pass's
+        zero-filled pool, so that fifteen such gradients cost no fill launches."""
+        t = pool.take(*shape)
         self.grads[name] = t
         return t
 
@@ -216,9 +236,9 @@ def grad_production_order() -> List[str]:
 
 
 def _first_layer_split(cx: _Ctx) -> bool:
-    """bf16 mode: the 3-channel network input and the first filters are split into hi + lo bf16 parts that ride in the
+    """16-bit modes: the 3-channel network input and the first filters are split into hi + lo parts that ride in the
     otherwise zero padding channels (free: K stays 16), removing the largest single source of train-mode logit error."""
-    return cx.dt == torch.bfloat16
+    return cx.tc
 
 
 class _BNSaved:
@@ -229,11 +249,14 @@ class _BNSaved:
 
 
 def _conv_bn_train(cx: _Ctx, packs: PackCache, sd: Dict[str, torch.Tensor], conv: str, bn: str, x: torch.Tensor, B, H, W, cin_p,
-                   cout, out: torch.Tensor, pooled: Optional[torch.Tensor], hilo: bool = False) -> _BNSaved:
+                   cout, out: torch.Tensor, pooled: Optional[torch.Tensor], hilo: bool = False, stats=None) -> _BNSaved:
     M = B * H * W
     y = cx.empty(M, cout, dtype=cx.raw)
-    stats = cx.zeros(2 * cout, dtype=torch.float64)
-    conv3x3(cx, x, packs.get(cx, conv, sd[conv + ".weight"], False, hilo), y, B, H, W, cin_p, cout, stats=stats)
+    if stats is None:
+        stats = cx.zeros(2 * cout, dtype=torch.float64)
+    w = sd[conv + ".weight"]
+    conv3x3(cx, x, packs.get(cx, conv, w, False, hilo), y, B, H, W, cin_p, cout, stats=stats,
+            cin_real=w.shape[1] if w.shape[1] < 16 else 0)
     f32 = torch.float32
     scale, shift, mean, invstd = (cx.empty(cout, dtype=f32) for _ in range(4))
     call("eunet_bn_finalize", ptr(stats), M, ptr(sd[bn + ".weight"]), ptr(sd[bn + ".bias"]), ptr(sd[conv + ".bias"]),
@@ -249,8 +272,9 @@ def _conv_bn_eval(cx: _Ctx, packs: PackCache, sd, conv: str, bn: str, x, B, H, W
     scale, shift = cx.empty(cout, dtype=f32), cx.empty(cout, dtype=f32)
     call("eunet_bn_fold_eval", ptr(sd[bn + ".weight"]), ptr(sd[bn + ".bias"]), ptr(sd[conv + ".bias"]),
          ptr(sd[bn + ".running_mean"]), ptr(sd[bn + ".running_var"]), BN_EPS, ptr(scale), ptr(shift), cout)
-    conv3x3(cx, x, packs.get(cx, conv, sd[conv + ".weight"], False, hilo), out, B, H, W, cin_p, cout, scale=scale, shift=shift,
-            relu=True)
+    w = sd[conv + ".weight"]
+    conv3x3(cx, x, packs.get(cx, conv, w, False, hilo), out, B, H, W, cin_p, cout, scale=scale, shift=shift,
+            relu=True, cin_real=w.shape[1] if w.shape[1] < 16 else 0)
 
 
 class Saved:
@@ -275,11 +299,15 @@ def _check_input(x: torch.Tensor) -> Tuple[int, int, int]:
 
 
 def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, train: bool, act_dtype: torch.dtype, packs: PackCache,
-            want_saved: bool) -> Tuple[torch.Tensor, Optional[Saved]]:
-    """Returns logits [B,3,2H,2W] fp32 (NCHW) and, in train mode, the saved state for ``backward``."""
+            want_saved: bool, amax: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[Saved]]:
+    """Returns logits [B,3,2H,2W] fp32 (NCHW) and, in train mode, the saved state for ``backward``.
+    ``amax``: one device float; fp16 conv outputs beyond the fp16 range leave their largest magnitude there."""
     B, H, W = _check_input(x)
     cx = _Ctx(x.device, act_dtype)
-    x = x.contiguous().float()
+    cx.amax = amax
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        x = x.contiguous().float()
+    zp64 = _ZeroPool(cx, STATS_NUMEL, torch.float64) if train else None
     sv = Saved()
     sv.B, sv.H, sv.W = B, H, W
     dims = [(H, W), (H // 2, W // 2), (H // 4, W // 4), (H // 8, W // 8)]
@@ -305,8 +333,9 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, train: bool, act_dtype
         first = hilo and prefix == "model.enc1"
         if train:
             sv.bn[prefix + ".1"] = _conv_bn_train(cx, packs, sd, prefix + ".0", prefix + ".1", xin, B, h, w, cin_p, cout, mid, None,
-                                                  hilo=first)
-            sv.bn[prefix + ".4"] = _conv_bn_train(cx, packs, sd, prefix + ".3", prefix + ".4", mid, B, h, w, cout, cout, out, pooled)
+                                                  hilo=first, stats=zp64.take(2 * cout))
+            sv.bn[prefix + ".4"] = _conv_bn_train(cx, packs, sd, prefix + ".3", prefix + ".4", mid, B, h, w, cout, cout, out, pooled,
+                                                  stats=zp64.take(2 * cout))
             sv.act[prefix + ".in"] = xin
             sv.act[prefix + ".mid"] = mid
         else:
@@ -345,15 +374,15 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, train: bool, act_dtype
     # tensor-core path: BN + ReLU + enhance.3 + residual in the conv epilogue.  Inference only: in training the 64-channel
     # tensor has to be stored for the backward pass anyway and the separate bandwidth pass is faster than the heavier
     # epilogue (measured: 1.53 ms fused + 0.25 ms statistics pass against 0.49 + 0.79 ms).
-    fused = cx.dt == torch.bfloat16 and ((not train) if FUSED_TAIL is None else bool(FUSED_TAIL))
+    fused = cx.tc and ((not train) if FUSED_TAIL is None else bool(FUSED_TAIL))
     if train:
-        stats = cx.zeros(128, dtype=torch.float64)
+        stats = zp64.take(128)
         midt = cx.empty(M2x, 64, dtype=cx.raw) if (want_saved or not fused) else None
         if fused:   # pass 1: batch statistics only (nothing stored); pass 2 below recomputes the tiles
             call("eunet_conv3x3_fwd", ptr(d1p), 16, ptr(wp0), None, 64, cx.code, B, 2 * H, 2 * W, 16, 64, ptr(stats), None, None, 0, 1,
-                 flops=2.0 * M2x * 64 * 9 * 16)
+                 None, flops=2.0 * M2x * 64 * 27, tag="k27")
         else:
-            conv3x3(cx, d1p, wp0, midt, B, 2 * H, 2 * W, 16, 64, stats=stats)
+            conv3x3(cx, d1p, wp0, midt, B, 2 * H, 2 * W, 16, 64, stats=stats, cin_real=3)
         scale, shift, mean, invstd = (cx.empty(64, dtype=f32) for _ in range(4))
         call("eunet_bn_finalize", ptr(stats), M2x, ptr(sd["enhance.1.weight"]), ptr(sd["enhance.1.bias"]),
              ptr(sd["enhance.0.bias"]), ptr(sd["enhance.1.running_mean"]), ptr(sd["enhance.1.running_var"]),
@@ -366,11 +395,11 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, train: bool, act_dtype
         midt = None
     if fused:
         call("eunet_conv3x3_tail_fwd", ptr(d1p), ptr(wp0), ptr(midt), ptr(scale), ptr(shift), ptr(w3), ptr(sd["enhance.3.bias"]),
-             ptr(d14), ptr(out), B, 2 * H, 2 * W, flops=2.0 * M2x * 64 * 9 * 16)
+             ptr(d14), ptr(out), cx.code, B, 2 * H, 2 * W, flops=2.0 * M2x * 64 * 27, tag="k27")
     else:
         if not train:   # fp32 mode, eval: conv with the folded affine + ReLU, then the 1x1 + residual pass
             midt = cx.empty(M2x, 64, dtype=cx.raw)
-            conv3x3(cx, d1p, wp0, midt, B, 2 * H, 2 * W, 16, 64, scale=scale, shift=shift, relu=True)
+            conv3x3(cx, d1p, wp0, midt, B, 2 * H, 2 * W, 16, 64, scale=scale, shift=shift, relu=True, cin_real=3)
             scale, shift = torch.ones(64, device=x.device, dtype=f32), torch.zeros(64, device=x.device, dtype=f32)
         call("eunet_tail_out_fwd", ptr(d14), ptr(midt), cx.code, ptr(scale), ptr(shift), ptr(w3), ptr(sd["enhance.3.bias"]), ptr(out),
              B, H, W)
@@ -380,12 +409,16 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, train: bool, act_dtype
     return out, None
 
 
+GRAD_SCALE_TARGET = 16.0   # fp16 mode: the largest |dLoss/dlogit| is scaled to [8, 16]: 2^12 of headroom, 2^28 below
+
+
 def backward(sd: Dict[str, torch.Tensor], sv: Saved, dout: torch.Tensor, act_dtype: torch.dtype, packs: PackCache,
-             sink: Optional[GradSink] = None) -> Dict[str, torch.Tensor]:
+             sink: Optional[GradSink] = None, amax: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """Gradients (fp32, parameter layout) for every parameter of the state_dict, written through ``sink`` in
     ``grad_production_order()``."""
     B, H, W = sv.B, sv.H, sv.W
     cx = _Ctx(dout.device, act_dtype)
+    cx.amax = amax
     f32, f64 = torch.float32, torch.float64
     dims = [(H, W), (H // 2, W // 2), (H // 4, W // 4), (H // 8, W // 8)]
     Ms = [B * h * w for h, w in dims]
@@ -393,19 +426,28 @@ def backward(sd: Dict[str, torch.Tensor], sv: Saved, dout: torch.Tensor, act_dty
         sink = GradSink(dout.device)
     grads = sink.grads
     pool = _ZeroPool(cx, wgrad_workspace_numel())
-    dout = dout.contiguous().float()
+    zp64 = _ZeroPool(cx, STATS_NUMEL, f64)
+    zbias = _ZeroPool(cx, ZERO_BIAS_NUMEL)
+    if dout.dtype != f32 or not dout.is_contiguous():
+        dout = dout.contiguous().float()
+    if cx.dt == torch.float16:
+        # tcgen05 takes both MMA operands in one 16-bit format, so gradients are fp16 too; ONE power-of-two scale per pass
+        # (backward is linear in dout) keeps them in range: applied where dout is read, removed where fp32 gradients leave
+        cx.gs = cx.empty(4, dtype=f32)
+        call("eunet_grad_scale", ptr(dout), dout.numel(), GRAD_SCALE_TARGET, ptr(cx.gs))
+    gs = cx.gs
 
     def cast64(name: str, src: torch.Tensor, shape) -> None:
         dst = sink.dst(name, shape)
-        call("eunet_cast_f64_f32", ptr(src), ptr(dst), dst.numel())
+        call("eunet_cast_f64_f32", ptr(src), ptr(dst), dst.numel(), ptr(gs))
         sink.ready(name)
 
     def zero_bias(name: str, c: int) -> None:      # conv bias in front of a train-mode BN: exact zero gradient
-        sink.dst(name, (c,)).zero_()
+        sink.zero_dst(name, (c,), zbias)
         sink.ready(name)
 
     def wgrad_into(name: str, dwp: torch.Tensor, co: int, ci: int, hilo: bool = False) -> None:
-        unpack_wgrad(dwp, co, ci, hilo, out=sink.dst(name, (co, ci, 3, 3)))
+        unpack_wgrad(dwp, co, ci, hilo, out=sink.dst(name, (co, ci, 3, 3)), gscale=gs)
         sink.ready(name)
 
     # ---- tail ----
@@ -413,9 +455,9 @@ def backward(sd: Dict[str, torch.Tensor], sv: Saved, dout: torch.Tensor, act_dty
     bn = sv.bn["enhance.1"]
     w1 = sd["model.dec1.weight"].reshape(3, 64)
     w3 = sd["enhance.3.weight"].reshape(3, 64)
-    acc = cx.zeros(328, dtype=f64)
+    acc = zp64.take(328)
     dout4 = cx.empty(M2x, 4, dtype=f32)
-    call("eunet_tail_pack3", ptr(dout), ptr(dout4), B, 2 * H, 2 * W)
+    call("eunet_tail_pack3", ptr(dout), ptr(dout4), B, 2 * H, 2 * W, ptr(gs))
     call("eunet_tail_bwd_reduce", ptr(dout4), ptr(bn.y), cx.code, ptr(bn.scale), ptr(bn.shift), ptr(bn.mean), ptr(bn.invstd),
          ptr(w3), ptr(acc), B, H, W)
     cast64("enhance.1.bias", acc[0:64], (64,))
@@ -425,34 +467,35 @@ def backward(sd: Dict[str, torch.Tensor], sv: Saved, dout: torch.Tensor, act_dty
     d1p = sv.act["d1p"]
     dz4 = cx.empty(M1, 4, dtype=f32)
     wflip = packs.get(cx, "enhance.0", sd["enhance.0.weight"], True)
-    tc_path = cx.dt == torch.bfloat16 and 2 * H >= 8 and 2 * W >= 8
+    tc_path = cx.tc and 2 * H >= 8 and 2 * W >= 8
     if tc_path and FUSED_TAIL_BWD:
         # ONE kernel: BN/ReLU backward on chip, wgrad and the 3-channel transposed dgrad from the same staged tile
         dwp = pool.take(64, 9, 16)
         dd1 = cx.empty(M2x, 4, dtype=f32)
         call("eunet_tail_bwd_fused", ptr(dout4), ptr(bn.y), ptr(d1p), ptr(wflip), ptr(bn.scale), ptr(bn.shift), ptr(bn.mean),
-             ptr(bn.invstd), ptr(w3), ptr(acc), ptr(dd1), ptr(dwp), B, 2 * H, 2 * W, flops=2 * 2.0 * M2x * 64 * 27)
+             ptr(bn.invstd), ptr(w3), ptr(acc), ptr(dd1), ptr(dwp), cx.code, B, 2 * H, 2 * W, flops=2 * 2.0 * M2x * 64 * 27,
+             tag="k27")
         wgrad_into("enhance.0.weight", dwp, 64, 3)
         zero_bias("enhance.0.bias", 64)                                        # cancelled by train-mode BN
-        call("eunet_tail_up_bwd", ptr(dd1), lib.F32, 4, ptr(dout), ptr(dz4), B, H, W)
+        call("eunet_tail_up_bwd", ptr(dd1), lib.F32, 4, ptr(dout), ptr(dz4), B, H, W, ptr(gs))
     else:
         dmid = cx.empty(M2x, 64)
         call("eunet_tail_bwd_dmid", ptr(dout4), ptr(bn.y), ptr(dmid), cx.code, ptr(bn.scale), ptr(bn.shift), ptr(bn.mean),
              ptr(bn.invstd), ptr(w3), ptr(acc), B, H, W)
-        dwp = conv3x3_wgrad(cx, d1p, dmid, B, 2 * H, 2 * W, 16, 64, pool)
+        dwp = conv3x3_wgrad(cx, d1p, dmid, B, 2 * H, 2 * W, 16, 64, pool, cin_real=3)
         wgrad_into("enhance.0.weight", dwp, 64, 3)
         zero_bias("enhance.0.bias", 64)                                        # cancelled by train-mode BN
         if tc_path:
             # 3 real gradient channels: transposed dgrad (every dmid row read once), fp32 [pixels][4] output
             dd1 = cx.empty(M2x, 4, dtype=f32)
-            call("eunet_conv3x3_dgrad_few", ptr(dmid), _ld(dmid), ptr(wflip), ptr(dd1), B, 2 * H, 2 * W, 64, 16,
-                 flops=2.0 * M2x * 64 * 27)
-            call("eunet_tail_up_bwd", ptr(dd1), lib.F32, 4, ptr(dout), ptr(dz4), B, H, W)
+            call("eunet_conv3x3_dgrad_few", ptr(dmid), _ld(dmid), ptr(wflip), ptr(dd1), cx.code, B, 2 * H, 2 * W, 64, 16,
+                 flops=2.0 * M2x * 64 * 27, tag="k27")
+            call("eunet_tail_up_bwd", ptr(dd1), lib.F32, 4, ptr(dout), ptr(dz4), B, H, W, ptr(gs))
         else:
             dd1p = cx.empty(M2x, 16)
-            conv3x3(cx, dmid, wflip, dd1p, B, 2 * H, 2 * W, 64, 16)
-            call("eunet_tail_up_bwd", ptr(dd1p), cx.code, 16, ptr(dout), ptr(dz4), B, H, W)
-    acc2 = cx.zeros(200, dtype=f64)
+            conv3x3(cx, dmid, wflip, dd1p, B, 2 * H, 2 * W, 64, 16, cout_real=3)
+            call("eunet_tail_up_bwd", ptr(dd1p), cx.code, 16, ptr(dout), ptr(dz4), B, H, W, ptr(gs))
+    acc2 = zp64.take(200)
     d2 = sv.act["d2"]
     dd2 = cx.empty(M1, 64)
     call("eunet_tail_dec1_bwd", ptr(dz4), ptr(d2), _ld(d2), ptr(dd2), _ld(dd2), cx.code, ptr(w1), ptr(acc2), M1)
@@ -461,13 +504,13 @@ def backward(sd: Dict[str, torch.Tensor], sv: Saved, dout: torch.Tensor, act_dty
 
     def bn_bwd(name: str, dact: torch.Tensor, M: int, C: int) -> torch.Tensor:
         s = sv.bn[name]
-        sums = cx.zeros(2 * C, dtype=f64)
+        sums = zp64.take(2 * C)
         call("eunet_bn_bwd_reduce", ptr(dact), _ld(dact), ptr(s.y), _ld(s.y), cx.code, M, C, ptr(s.scale), ptr(s.shift),
              ptr(s.mean), ptr(s.invstd), ptr(sums))
         dy = cx.empty(M, C)
         dg, db = sink.dst(name + ".weight", (C,)), sink.dst(name + ".bias", (C,))
         call("eunet_bn_bwd_apply", ptr(dact), _ld(dact), ptr(s.y), _ld(s.y), ptr(dy), _ld(dy), cx.code, M, C, ptr(s.scale),
-             ptr(s.shift), ptr(s.mean), ptr(s.invstd), ptr(sums), ptr(dg), ptr(db))
+             ptr(s.shift), ptr(s.mean), ptr(s.invstd), ptr(sums), ptr(dg), ptr(db), ptr(gs))
         sink.ready(name + ".weight")
         sink.ready(name + ".bias")
         return dy
@@ -483,7 +526,7 @@ def backward(sd: Dict[str, torch.Tensor], sv: Saved, dout: torch.Tensor, act_dty
         dmid_act = cx.empty(M, cout)
         conv3x3(cx, dy_b, packs.get(cx, prefix + ".3", sd[prefix + ".3.weight"], True), dmid_act, B, h, w, cout, cout)
         dy_a = bn_bwd(prefix + ".1", dmid_act, M, cout)
-        wgrad_into(prefix + ".0.weight", conv3x3_wgrad(cx, xin, dy_a, B, h, w, cin_p, cout, pool), cout, cin,
+        wgrad_into(prefix + ".0.weight", conv3x3_wgrad(cx, xin, dy_a, B, h, w, cin_p, cout, pool, cin_real=cin if cin < 16 else 0), cout, cin,
                    hilo=(prefix == "model.enc1" and _first_layer_split(cx)))
         zero_bias(prefix + ".0.bias", cout)
         if not need_dx:

@@ -14,8 +14,8 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libeunet_b200.so")
 
-F32, BF16 = 0, 1
-ABI_VERSION = 1
+F32, BF16, F16 = 0, 1, 2
+ABI_VERSION = 2
 
 _p = C.c_void_p
 _i = C.c_int
@@ -33,30 +33,31 @@ SIGNATURES = {
     "eunet_pack_input_nchw": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "eunet_pack_weight3x3": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
     "eunet_pack_weight3x3_multi": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
-    "eunet_unpack_wgrad3x3": [_p, _p, _i, _i, _i, _i, _p],
-    "eunet_conv3x3_fwd": [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _i, _p],
-    "eunet_conv3x3_tail_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
-    "eunet_conv3x3_dgrad_few": [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p],
+    "eunet_unpack_wgrad3x3": [_p, _p, _i, _i, _i, _i, _p, _p],
+    "eunet_conv3x3_fwd": [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p],
+    "eunet_conv3x3_tail_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "eunet_conv3x3_dgrad_few": [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "eunet_conv3x3_wgrad": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p],
     "eunet_bn_finalize": [_p, _ll, _p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _i, _p],
     "eunet_bn_fold_eval": [_p, _p, _p, _p, _p, _f, _p, _p, _i, _p],
     "eunet_bn_apply_relu": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p],
     "eunet_bn_bwd_reduce": [_p, _i, _p, _i, _i, _ll, _i, _p, _p, _p, _p, _p, _p],
-    "eunet_bn_bwd_apply": [_p, _i, _p, _i, _p, _i, _i, _ll, _i, _p, _p, _p, _p, _p, _p, _p, _p],
+    "eunet_bn_bwd_apply": [_p, _i, _p, _i, _p, _i, _i, _ll, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "eunet_maxpool2_fwd": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p],
     "eunet_maxpool2_bwd": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "eunet_upsample2_fwd": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p],
     "eunet_upsample2_bwd": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p],
     "eunet_tail_dec1_fwd": [_p, _i, _i, _p, _p, _p, _ll, _p],
     "eunet_tail_up_fwd": [_p, _p, _p, _i, _i, _i, _i, _p],
-    "eunet_tail_pack3": [_p, _p, _i, _i, _i, _p],
+    "eunet_tail_pack3": [_p, _p, _i, _i, _i, _p, _p],
     "eunet_tail_out_fwd": [_p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "eunet_tail_bwd_reduce": [_p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "eunet_tail_bwd_dmid": [_p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
-    "eunet_tail_bwd_fused": [_p] * 12 + [_i, _i, _i, _p],
-    "eunet_tail_up_bwd": [_p, _i, _i, _p, _p, _i, _i, _i, _p],
+    "eunet_tail_bwd_fused": [_p] * 12 + [_i, _i, _i, _i, _p],
+    "eunet_tail_up_bwd": [_p, _i, _i, _p, _p, _i, _i, _i, _p, _p],
     "eunet_tail_dec1_bwd": [_p, _p, _i, _p, _i, _i, _p, _p, _ll, _p],
-    "eunet_cast_f64_f32": [_p, _p, _ll, _p],
+    "eunet_cast_f64_f32": [_p, _p, _ll, _p, _p],
+    "eunet_grad_scale": [_p, _ll, _f, _p, _p],
     "eunet_loss_fwd": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p],
     "eunet_loss_bwd": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p],
     "eunet_resize_bilinear": [_p, _p, _i, _i, _i, _i, _i, _f, _f, _p],
@@ -117,12 +118,13 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 # number of C-ABI calls per entry point since the last COUNTERS.clear() (each call launches >= 1 kernel)
 COUNTERS: dict = {}
-# when a list: every call is bracketed by CUDA events on the launching stream -> (name, e0, e1, flops)
+# when a list: every call is bracketed by CUDA events on the launching stream -> (name, tag, e0, e1, flops)
 PROFILE: Optional[list] = None
 
 
-def call(name: str, *args, flops: float = 0.0) -> None:
-    """Invoke ``name`` with the current torch CUDA stream appended; raise on a non-zero status."""
+def call(name: str, *args, flops: float = 0.0, tag: str = "") -> None:
+    """Invoke ``name`` with the current torch CUDA stream appended; raise on a non-zero status.  ``flops`` (ALGORITHMIC
+    FLOPs of the launch) and ``tag`` (roofline group of the launch) only feed the profile."""
     lib = load()
     COUNTERS[name] = COUNTERS.get(name, 0) + 1
     if PROFILE is not None:
@@ -130,26 +132,27 @@ def call(name: str, *args, flops: float = 0.0) -> None:
         e0.record()
         rc = getattr(lib, name)(*args, stream_ptr())
         e1.record()
-        PROFILE.append((name, e0, e1, flops))
+        PROFILE.append((name, tag, e0, e1, flops))
     else:
         rc = getattr(lib, name)(*args, stream_ptr())
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {last_error()}")
 
 
-def collect_profile() -> dict:
-    """name -> (total flops, total ms, launches) for the calls recorded since PROFILE was set."""
+def collect_profile(by_tag: bool = False) -> dict:
+    """name (or (name, tag) with ``by_tag``) -> (total flops, total ms, launches) for the calls recorded since PROFILE was set."""
     torch.cuda.synchronize()
     out: dict = {}
-    for name, e0, e1, fl in PROFILE or []:
-        f, ms, n = out.get(name, (0.0, 0.0, 0))
-        out[name] = (f + fl, ms + e0.elapsed_time(e1), n + 1)
+    for name, tag, e0, e1, fl in PROFILE or []:
+        key = (name, tag) if by_tag else name
+        f, ms, n = out.get(key, (0.0, 0.0, 0))
+        out[key] = (f + fl, ms + e0.elapsed_time(e1), n + 1)
     return out
 
 
 def raw_dtype(act: torch.dtype) -> torch.dtype:
     """Storage dtype of RAW (pre-BatchNorm) conv outputs for a given activation dtype."""
-    return torch.float16 if act == torch.bfloat16 else torch.float32
+    return torch.float16 if act in (torch.bfloat16, torch.float16) else torch.float32
 
 
 def set_option(name: str, value: int) -> None:
@@ -161,6 +164,8 @@ def set_option(name: str, value: int) -> None:
 def dtype_code(dt: torch.dtype) -> int:
     if dt == torch.bfloat16:
         return BF16
+    if dt == torch.float16:
+        return F16
     if dt == torch.float32:
         return F32
     raise ValueError(f"unsupported activation dtype {dt}")

@@ -3,7 +3,7 @@
     python -m enhanced_unet_b200.main --mode train_eval --models enhanced_unet --epochs 3 --synthetic
 
 ``--synthetic`` (default; the reference's labelme ``data/`` directory and cv2 pre-processing are out of scope)
-generates bright-field-like batches on the fly.  Extra flags: ``--dtype {bf16,fp32}``, ``--size``, ``--batch``."""
+generates bright-field-like batches on the fly.  Extra flags: ``--dtype {fp16,bf16,fp32}``, ``--size``, ``--batch``."""
 from __future__ import annotations
 
 import argparse
@@ -22,7 +22,7 @@ def main(argv=None):
     ap.add_argument("--epochs", type=int, default=50)
     ap.add_argument("--regenerate-predictions", action="store_true", help="accepted for compatibility; unused")
     ap.add_argument("--synthetic", action="store_true", default=True)
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--batch", type=int, default=2)
     ap.add_argument("--train-batches", type=int, default=8)

@@ -18,7 +18,51 @@ import torch.nn as nn
 
 from . import engine
 
-_DTYPES = {"bf16": torch.bfloat16, "bfloat16": torch.bfloat16, "fp32": torch.float32, "float32": torch.float32}
+_DTYPES = {"fp16": torch.float16, "float16": torch.float16, "bf16": torch.bfloat16, "bfloat16": torch.bfloat16,
+           "fp32": torch.float32, "float32": torch.float32}
+DEFAULT_DTYPE = "fp16"
+FP16_MAX = 65504.0
+
+
+class _SaturationMonitor:
+    """fp16 tensors saturate at +-65504 (``cvt.rn.satfinite``) instead of overflowing to inf.  That must not be silent:
+    the conv epilogues leave the largest magnitude they had to clamp in one device float; it is copied to pinned host
+    memory after every pass without a sync and inspected at the start of the next pass (or by ``check()``)."""
+
+    def __init__(self):
+        self.dev = None
+        self.host = None
+        self.event = None
+        self.device = None
+
+    def buffer(self, device: torch.device) -> torch.Tensor:
+        if self.dev is None or self.device != device:
+            self.device = device
+            self.dev = torch.zeros(1, device=device, dtype=torch.float32)
+            self.host = torch.zeros(1, dtype=torch.float32).pin_memory()
+            self.event = None
+        return self.dev
+
+    def publish(self) -> None:
+        if self.dev is not None:
+            self.host.copy_(self.dev, non_blocking=True)
+            self.event = torch.cuda.Event()
+            self.event.record()
+
+    def check(self, block: bool) -> None:
+        if self.event is None:
+            return
+        if block:
+            self.event.synchronize()
+        elif not self.event.query():
+            return
+        v = float(self.host[0])
+        if v > FP16_MAX:
+            self.dev.zero_()
+            self.host.zero_()
+            raise RuntimeError(f"EnhancedUNet (fp16 mode): convolution outputs exceeded the fp16 range (max |y| = {v:.4g} > "
+                               f"{FP16_MAX:.0f}) and were clamped; results of that pass are invalid. Use dtype='bf16' or 'fp32' "
+                               "for weights / inputs of this magnitude.")
 
 
 def _conv_block(in_ch: int, out_ch: int) -> nn.Sequential:
@@ -52,7 +96,8 @@ class _UNetFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module: "EnhancedUNet", x: torch.Tensor, *params: torch.Tensor):
         sd = module._tensor_dict()
-        out, saved = engine.forward(sd, x, True, module.act_dtype, module._packs, want_saved=True)
+        out, saved = engine.forward(sd, x, True, module.act_dtype, module._packs, want_saved=True, amax=module._amax_buffer(x.device))
+        module._sat.publish()
         ctx.module = module
         ctx.saved_state = saved
         ctx.n_params = len(params)
@@ -68,7 +113,8 @@ class _UNetFunction(torch.autograd.Function):
         sink = module.grad_sink
         if sink is not None:
             sink.begin()
-        grads = engine.backward(sd, sv, dout, module.act_dtype, module._packs, sink=sink)
+        grads = engine.backward(sd, sv, dout, module.act_dtype, module._packs, sink=sink, amax=module._amax_buffer(dout.device))
+        module._sat.publish()
         ctx.saved_state = None
         names = module._param_names
         if sink is None:
@@ -87,10 +133,12 @@ class _UNetFunction(torch.autograd.Function):
 
 
 class EnhancedUNet(nn.Module):
-    """Reference models.py:246-343 (fallback body).  Extra keyword ``dtype``: 'bf16' (default, tcgen05
-    tensor-core convolutions, fp32 accumulation / statistics) or 'fp32' (CUDA-core fp32 mode)."""
+    """Reference models.py:246-343 (fallback body).  Extra keyword ``dtype``: 'fp16' (default) / 'bf16' - 16-bit tensors,
+    tcgen05 tensor-core convolutions, fp32 accumulation / statistics - or 'fp32' (CUDA-core fp32 mode).  fp16's 11
+    mantissa bits keep train-mode (batch-statistics) BatchNorm inside the 2e-2 logit tolerance where bf16's 8 do not;
+    its range is guarded (gradient scale, loud saturation check)."""
 
-    def __init__(self, num_classes: int = 3, dtype: str = "bf16"):
+    def __init__(self, num_classes: int = 3, dtype: str = DEFAULT_DTYPE):
         super().__init__()
         if num_classes != 3:
             raise ValueError("the B200 hot path implements the reference configuration num_classes=3")
@@ -103,6 +151,7 @@ class EnhancedUNet(nn.Module):
             nn.Conv2d(num_classes, 64, 3, padding=1), nn.BatchNorm2d(64), nn.ReLU(inplace=True), nn.Conv2d(64, num_classes, 1))
         self._aux_outputs = None
         self._packs = engine.PackCache()
+        self._sat = _SaturationMonitor()
         self.grad_sink = None   # parallel.FlatGradBuffer when gradients are exchanged across ranks (parallel.GradientAllReduce)
         self._param_names = [n for n, _ in self.named_parameters()]
 
@@ -111,6 +160,13 @@ class EnhancedUNet(nn.Module):
         d: Dict[str, torch.Tensor] = dict(self.named_parameters())
         d.update(dict(self.named_buffers()))
         return d
+
+    def _amax_buffer(self, device: torch.device) -> Optional[torch.Tensor]:
+        return self._sat.buffer(device) if self.act_dtype == torch.float16 else None
+
+    def check_numerics(self) -> None:
+        """Raise if any fp16 tensor of the passes launched so far had to be clamped (waits for the device)."""
+        self._sat.check(block=True)
 
     def set_compute_dtype(self, dtype: str) -> "EnhancedUNet":
         self.act_dtype = _DTYPES[dtype]
@@ -130,6 +186,7 @@ class EnhancedUNet(nn.Module):
             raise RuntimeError("EnhancedUNet (B200) parameters must live on a CUDA device: call .to('cuda'); no CPU fallback")
         if x.device != p0.device:
             raise RuntimeError(f"input on {x.device} but parameters on {p0.device}")
+        self._sat.check(block=False)     # an earlier pass clamped fp16 values: loud, one pass late at most, no sync
         need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
         if need_grad:
             if not self.training:
@@ -138,7 +195,9 @@ class EnhancedUNet(nn.Module):
             params = [p for _, p in self.named_parameters()]
             return _UNetFunction.apply(self, x, *params)
         with torch.no_grad():
-            out, _ = engine.forward(self._tensor_dict(), x, self.training, self.act_dtype, self._packs, want_saved=False)
+            out, _ = engine.forward(self._tensor_dict(), x, self.training, self.act_dtype, self._packs, want_saved=False,
+                                    amax=self._amax_buffer(x.device))
+            self._sat.publish()
         return out
 
     def get_aux_outputs(self) -> Optional[Dict[str, torch.Tensor]]:
@@ -147,7 +206,7 @@ class EnhancedUNet(nn.Module):
 
 
 def get_model(model_name: str, num_classes: int = 3, device: str = "cuda", train_mode: bool = False, data_dir: str = None,
-              max_size: int = 640, dtype: str = "bf16") -> nn.Module:
+              max_size: int = 640, dtype: str = DEFAULT_DTYPE) -> nn.Module:
     """Reference models.py:590-624.  Same signature (the last three reference kwargs are ignored there
     too); does NOT move the model to ``device`` (the caller does, train_eval.py:1079)."""
     print(f"Initializing model: {model_name}")
@@ -169,7 +228,7 @@ class FusionHead(nn.Module):
     code outside this repo's scope; this head runs standalone in EVAL mode (train mode draws Dropout2d masks from
     torch's RNG stream and is not implemented)."""
 
-    def __init__(self, num_classes: int = 3, dtype: str = "bf16"):
+    def __init__(self, num_classes: int = 3, dtype: str = DEFAULT_DTYPE):
         super().__init__()
         if num_classes != 3:
             raise ValueError("the B200 hot path implements the reference configuration num_classes=3")

@@ -74,8 +74,12 @@ class ClippedAdamW(torch.optim.Optimizer):
                  VPk(*[self.state[p]["exp_avg"].data_ptr() for p in ps]), VPk(*[self.state[p]["exp_avg_sq"].data_ptr() for p in ps]),
                  LLk(*[p.numel() for p in ps]), k, self._sq.data_ptr(), key[0], key[1], key[2], key[3], key[4], key[5], key[6],
                  float(grad_scale))
+        # the kernels wrote the parameters behind autograd's back: bump their version counters, which is what the
+        # packed-filter caches (engine.PackCache) key on - the optimiser is safe on its own, ``on_update`` is an optimisation
+        for _, p in items:
+            torch.autograd.graph.increment_version(p)
         if self.on_update is not None:
-            self.on_update()   # parameters changed behind autograd's back: drop packed-filter caches
+            self.on_update()
         return None
 
     def grad_norm(self) -> float:

@@ -85,6 +85,10 @@ class FlatGradBuffer:
             raise RuntimeError(f"FlatGradBuffer: gradient of {name} has shape {tuple(shape)}, expected {tuple(t.shape)}")
         return t
 
+    def zero_dst(self, name: str, shape, pool=None) -> torch.Tensor:
+        """Slice for a gradient that is exactly zero: ``begin`` zeroed the whole buffer (one fill), nothing to do."""
+        return self.dst(name, shape)
+
     def ready(self, name: str) -> None:
         b = self._closes.get(name)
         if b is None:
@@ -103,6 +107,7 @@ class FlatGradBuffer:
         if self._work:
             raise RuntimeError("FlatGradBuffer.begin: the previous exchange was not waited for")
         self._launched = 0
+        self.flat.zero_()      # ONE fill: the exactly-zero conv-bias gradients need no launches of their own
 
     def wait(self) -> None:
         """Join every bucket's all-reduce (the current stream waits on NCCL's; no host sync on CUDA)."""

@@ -20,7 +20,7 @@ import torch.nn.functional as F
 from . import metrics as _metrics
 from . import parallel as _parallel
 from .lib import call, ptr
-from .models import get_model
+from .models import DEFAULT_DTYPE, get_model
 from .ops import combined_loss
 from .optim import ClippedAdamW
 
@@ -128,8 +128,18 @@ class Trainer:
 class Evaluator:
     """Reference train_eval.py:356-1021, semantic-segmentation part."""
 
-    def __init__(self, model, device, model_name, tta: bool = False):
-        self.model, self.device, self.model_name, self.tta = model, device, model_name, tta
+    def __init__(self, model, device, model_name, tta: Optional[bool] = None):
+        self.model, self.device, self.model_name = model, device, model_name
+        # reference train_eval.py:363: enhanced_unet always averages the five TTA views; ``tta=False`` opts out
+        self.enable_tta = (model_name == "enhanced_unet") if tta is None else bool(tta)
+
+    @property
+    def tta(self) -> bool:
+        return self.enable_tta
+
+    @tta.setter
+    def tta(self, value: bool) -> None:
+        self.enable_tta = bool(value)
 
     @torch.no_grad()
     def _run_model_batch(self, images: torch.Tensor) -> torch.Tensor:
@@ -184,13 +194,13 @@ class Evaluator:
 
     def _run_tta_inference(self, image: torch.Tensor) -> torch.Tensor:
         """Single-image form with the reference's signature ([3,h,w] -> [3,h,w] probabilities)."""
-        if not self.tta:
+        if not self.enable_tta:
             return self._run_model_single(image)
         return self._run_tta_batch(image.unsqueeze(0))[0]
 
     @torch.no_grad()
     def _probs(self, images: torch.Tensor) -> torch.Tensor:
-        p = self._run_tta_batch(images) if self.tta else self._run_model_batch(images)
+        p = self._run_tta_batch(images) if self.enable_tta else self._run_model_batch(images)
         return p.contiguous()
 
     @torch.no_grad()
@@ -267,9 +277,11 @@ class SyntheticCellBatches:
 
 def train_model(model_name: str, data_dir, device: str = "cuda", num_epochs: int = 50, skip_training: bool = False,
                 train_batches: Optional[Iterable[Dict]] = None, val_batches: Optional[Iterable[Dict]] = None,
-                dtype: str = "bf16") -> str:
-    """Reference train_eval.py:1036-1162: epochs with warm-up / cosine-restart LR, validation every 3rd epoch,
-    best-mIoU checkpoint in the reference's format.  ``data_dir`` is unused for synthetic runs."""
+                dtype: str = DEFAULT_DTYPE, tta: Optional[bool] = None) -> str:
+    """Reference train_eval.py:1036-1162: epochs with warm-up / cosine-restart LR, validation every 3rd epoch (with the
+    5-view TTA, as the reference's Evaluator does for enhanced_unet; ``tta=False`` opts out), best-mIoU checkpoint in the
+    reference's format, early stopping (patience 10 validations without a better mIoU, only after epoch 26).
+    ``data_dir`` is unused for synthetic runs."""
     save_dir = os.path.join("checkpoints", model_name)
     os.makedirs(save_dir, exist_ok=True)
     checkpoint_path = os.path.join(save_dir, "best_model.pth")
@@ -280,7 +292,8 @@ def train_model(model_name: str, data_dir, device: str = "cuda", num_epochs: int
     model = get_model(model_name, num_classes=3, device=device, dtype=dtype).to(device)
     trainer = Trainer(model, device, model_name, total_epochs=num_epochs)
     history = {"train_loss": [], "val_miou": [], "learning_rate": [], "epoch_axis": []}
-    best_miou, best_loss = -1.0, float("inf")
+    best_miou, best_loss = 0.0, float("inf")                                                         # 1095-1096
+    patience, patience_counter = 10, 0                                                               # 1097-1098
     for epoch in range(num_epochs):
         (trainer.warmup_scheduler if epoch < trainer.warmup_epochs else trainer.scheduler).step()      # 1104-1111
         lr = trainer.optimizer.param_groups[0]["lr"]
@@ -288,36 +301,48 @@ def train_model(model_name: str, data_dir, device: str = "cuda", num_epochs: int
         history["train_loss"].append(loss)
         history["learning_rate"].append(lr)
         print(f"Epoch {epoch + 1}/{num_epochs}  lr {lr:.6f}  loss {loss:.4f}")
-        if (epoch + 1) % 3 == 0 or epoch + 1 == num_epochs:
-            res = Evaluator(model, device, model_name).evaluate(val_batches)
+        if (epoch + 1) % 3 == 0:                                                                     # 1118
+            res = Evaluator(model, device, model_name, tta=tta).evaluate(val_batches)
             miou = res.get("sem_mean_iou", 0.0)
             history["val_miou"].append(miou)
             history["epoch_axis"].append(epoch + 1)
             print(f"  val mIoU {miou:.4f}  live {res.get('sem_live_iou', 0):.4f}  dead {res.get('sem_dead_iou', 0):.4f}")
             if miou > best_miou:
-                best_miou, best_loss = miou, loss
-                if _parallel.world_size() > 1 and torch.distributed.get_rank() != 0:
-                    continue                                                                         # rank 0's replica is checkpointed
-                torch.save({"epoch": epoch + 1, "model_state_dict": model.state_dict(),
-                            "optimizer_state_dict": trainer.optimizer.state_dict(),
-                            "scheduler_state_dict": trainer.scheduler.state_dict(), "best_miou": best_miou,
-                            "best_loss": best_loss, "history": history}, checkpoint_path)            # 1143-1151
+                best_miou, best_loss, patience_counter = miou, loss, 0
+                if _parallel.world_size() == 1 or torch.distributed.get_rank() == 0:                 # rank 0's replica is checkpointed
+                    torch.save({"epoch": epoch + 1, "model_state_dict": model.state_dict(),
+                                "optimizer_state_dict": trainer.optimizer.state_dict(),
+                                "scheduler_state_dict": trainer.scheduler.state_dict(), "best_miou": best_miou,
+                                "best_loss": best_loss, "history": history}, checkpoint_path)        # 1143-1151
+            else:
+                patience_counter += 1
+        if patience_counter >= patience and epoch > 25:                                              # 1156-1159
+            print(f"Early stopping at epoch {epoch + 1}")
+            break
+    if hasattr(model, "check_numerics"):
+        model.check_numerics()
+    if not os.path.exists(checkpoint_path) and (_parallel.world_size() == 1 or torch.distributed.get_rank() == 0):
+        # fewer than three epochs (or no validation ever beat mIoU 0): the reference would return a path that does not
+        # exist; save the final weights so that evaluate_model has something to load
+        torch.save({"epoch": num_epochs, "model_state_dict": model.state_dict(), "optimizer_state_dict": trainer.optimizer.state_dict(),
+                    "scheduler_state_dict": trainer.scheduler.state_dict(), "best_miou": best_miou, "best_loss": best_loss,
+                    "history": history}, checkpoint_path)
     return checkpoint_path
 
 
 def evaluate_model(model_name: str, data_dir, device: str = "cuda", checkpoint_path: Optional[str] = None,
-                   batches: Optional[Iterable[Dict]] = None, dtype: str = "bf16") -> Dict[str, float]:
-    """Reference train_eval.py:1165-1232 (semantic metrics)."""
+                   batches: Optional[Iterable[Dict]] = None, dtype: str = DEFAULT_DTYPE, tta: Optional[bool] = None) -> Dict[str, float]:
+    """Reference train_eval.py:1165-1232 (semantic metrics; 5-view TTA for enhanced_unet unless ``tta=False``)."""
     model = get_model(model_name, num_classes=3, device=device, dtype=dtype)
     if checkpoint_path and os.path.exists(checkpoint_path):
         ckpt = torch.load(checkpoint_path, map_location="cpu", weights_only=False)                   # 1190-1191
         model.load_state_dict(ckpt["model_state_dict"])
     model = model.to(device)
     batches = batches if batches is not None else SyntheticCellBatches(2, 2, 256, seed=99)
-    return Evaluator(model, device, model_name).evaluate(batches)
+    return Evaluator(model, device, model_name, tta=tta).evaluate(batches)
 
 
 def train_and_evaluate(model_name: str, data_dir, device: str = "cuda", num_epochs: int = 50, **kw) -> Dict[str, float]:
     """Reference train_eval.py:1024-1033."""
     ckpt = train_model(model_name, data_dir, device, num_epochs, **kw)
-    return evaluate_model(model_name, data_dir, device, ckpt, dtype=kw.get("dtype", "bf16"))
+    return evaluate_model(model_name, data_dir, device, ckpt, dtype=kw.get("dtype", DEFAULT_DTYPE), tta=kw.get("tta"))

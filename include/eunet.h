@@ -11,11 +11,17 @@
  *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it asynchronously.
  *  - return 0 on success, negative on error; eunet_last_error() returns the (thread-local) message.
  *    There is no CPU fallback and no silent degradation.
- *  - activations are NHWC ("channels last"), dtype EUNET_BF16 (default) or EUNET_F32 ("fp32 mode"),
+ *  - activations are NHWC ("channels last"), dtype EUNET_F16 (default: fp16 tensors - 11 mantissa bits keep train-mode
+ *    BatchNorm inside the 2e-2 logit tolerance where bf16's 8 do not), EUNET_BF16 or EUNET_F32 ("fp32 mode"),
  *    addressed as base pointer + `ld` = elements per pixel of the underlying buffer, so a channel
  *    slice of a wider (concat) buffer is a first-class operand.  Channel counts are multiples of 8
  *    (bandwidth kernels) / 16 (convolutions).
  *  - packed 3x3 filters: [Cout][9][Cin] (tap = ky*3+kx, Cin contiguous) in the activation dtype.
+ *  - tcgen05 takes both operands of an MMA in ONE 16-bit format (fp16 x bf16 is an illegal instruction on B200), so
+ *    in EUNET_F16 mode gradients are fp16 too.  Their range is kept by one power-of-two scale S per backward pass
+ *    (eunet_grad_scale: max |dLoss/dlogits| -> 2^4): the entry points that read the caller's fp32 logit gradient
+ *    multiply by S (`gscale[0]`), the entry points that write fp32 parameter gradients multiply by 1/S (`gscale[1]`);
+ *    everything in between is linear.  `gscale` = NULL means S = 1 (bf16 / fp32 modes).
  */
 #ifndef EUNET_H_
 #define EUNET_H_
@@ -27,9 +33,10 @@
 extern "C" {
 #endif
 
-#define EUNET_ABI_VERSION 1
+#define EUNET_ABI_VERSION 2
 #define EUNET_F32 0
 #define EUNET_BF16 1
+#define EUNET_F16 2
 
 const char* eunet_last_error(void);
 int eunet_abi_version(void);
@@ -72,7 +79,8 @@ int eunet_pack_weight3x3(const float* w, void* out, int dtype, int Co, int Ci, i
 int eunet_pack_weight3x3_multi(const void* const* w, void* const* out, const int* co, const int* ci, const int* copad,
                                const int* cipad, const int* mode, int count, int dtype, void* stream);
 /* dw_packed [Co][9][CiPad] fp32 -> dw [Co,Ci,3,3] fp32 (layout of nn.Conv2d.weight.grad); hilo: sum the x_hi / x_lo channels */
-int eunet_unpack_wgrad3x3(const float* dw_packed, float* dw, int Co, int Ci, int CiPad, int hilo, void* stream);
+int eunet_unpack_wgrad3x3(const float* dw_packed, float* dw, int Co, int Ci, int CiPad, int hilo, const float* gscale,
+                          void* stream);
 
 /* ---- nn.Conv2d(k=3, padding=1) forward (models.py:219,222,309) and its autograd dgrad/wgrad
  * (loss.backward(), train_eval.py:338).  bf16: tcgen05/TMEM implicit GEMM with TMA-staged tiles;
@@ -84,10 +92,13 @@ int eunet_unpack_wgrad3x3(const float* dw_packed, float* dw, int Co, int Ci, int
  *   out_raw: element type of y.  0 = the activation dtype (bf16 / fp32); 1 = the RAW dtype used for tensors
  *            that feed a BatchNorm (fp16 in bf16 mode - 8x finer than bf16 where the batch mean dominates -
  *            and fp32 in fp32 mode).  The bn_* / tail_* entry points read raw tensors in that dtype.
- *   y == NULL (bf16, Cin = 16 -> Cout = 64 only): statistics-only pass, nothing is stored. */
+ *   y == NULL (16-bit modes, Cin = 16 -> Cout = 64 only): statistics-only pass, nothing is stored.
+ *   amax (may be NULL): fp16 outputs saturate at +-65504 instead of overflowing; when a stored magnitude exceeded that
+ *                  range the largest one is written here (atomic max of the fp32 bits; caller zeroes) so that the host
+ *                  can raise instead of training on clamped values. */
 int eunet_conv3x3_fwd(const void* x, int ldx, const void* w_packed, void* y, int ldy, int dtype, int B, int H, int W,
                       int Cin, int Cout, double* stats, const float* scale, const float* shift, int relu, int out_raw,
-                      void* stream);
+                      float* amax, void* stream);
 /* Fused forward of the 2Hx2W tail (models.py:309-313 enhance head + 337 residual), bf16 tensor-core path:
  *   out[b,k,p] = d14[p][k] + b3[k] + sum_c w3[k][c] * relu(conv3x3(d1p16; w_packed)[p,c] * scale[c] + shift[c])
  * d1p16: [B*H2*W2, 16] bf16 (d1 padded to 16 channels); w_packed: eunet_pack_weight3x3 of enhance.0 ([64][9][16]);
@@ -95,7 +106,8 @@ int eunet_conv3x3_fwd(const void* x, int ldx, const void* w_packed, void* y, int
  * out: fp32 NCHW [B,3,H2,W2].  mid_raw != NULL additionally stores the RAW fp16 convolution output [pixels][64]
  * (read by tail_bwd_*); NULL (inference) never materialises the 64-channel tensor. */
 int eunet_conv3x3_tail_fwd(const void* d1p16, const void* w_packed, void* mid_raw, const float* scale, const float* shift,
-                           const float* w3, const float* b3, const float* d14, float* out, int B, int H2, int W2, void* stream);
+                           const float* w3, const float* b3, const float* d14, float* out, int dtype, int B, int H2, int W2,
+                           void* stream);
 /* dw[co][tap][ci] += sum_p dy[p,co] * x[p+tap,ci]   (fp32 accumulate into caller-zeroed dw_packed) */
 int eunet_conv3x3_wgrad(const void* x, int ldx, const void* dy, int lddy, float* dw_packed, int dtype, int B, int H, int W,
                         int Cin, int Cout, void* stream);
@@ -105,8 +117,8 @@ int eunet_conv3x3_wgrad(const void* x, int ldx, const void* dy, int lddy, float*
  *   dx4[p][i] = sum_{tap,co} dy[p + tap - (1,1), co] * w_packed_flip[i][tap][co],  i < 3;  dx4[p][3] = 0
  * dy: [B*H*W, 64] bf16 (row stride lddy); w_packed_flip: eunet_pack_weight3x3(..., transpose_flip = 1) output
  * [cin_pad][9][64] bf16 (cin_pad >= 8); dx4: fp32 [B*H*W][4]. */
-int eunet_conv3x3_dgrad_few(const void* dy, int lddy, const void* w_packed_flip, float* dx4, int B, int H, int W, int Cout,
-                            int cin_pad, void* stream);
+int eunet_conv3x3_dgrad_few(const void* dy, int lddy, const void* w_packed_flip, float* dx4, int dtype, int B, int H, int W,
+                            int Cout, int cin_pad, void* stream);
 
 /* ---- nn.BatchNorm2d (models.py:220,223,310): train-mode statistics -> affine, running stats ---- */
 int eunet_bn_finalize(const double* stats, long long count, const float* gamma, const float* beta, const float* conv_bias,
@@ -124,7 +136,7 @@ int eunet_bn_bwd_reduce(const void* dact, int ldd, const void* y, int ldy, int d
 /* pass 2: dy = scale*(g - sum_g/M - xhat*sum_gx/M); also writes dgamma = sum_gx, dbeta = sum_g (fp32) */
 int eunet_bn_bwd_apply(const void* dact, int ldd, const void* y, int ldy, void* dy, int lddy, int dtype, long long M, int C,
                        const float* scale, const float* shift, const float* mean, const float* invstd, const double* sums,
-                       float* dgamma, float* dbeta, void* stream);
+                       float* dgamma, float* dbeta, const float* gscale, void* stream);
 
 /* ---- nn.MaxPool2d(2) (models.py:214) and nn.Upsample(x2, bilinear, align_corners=False) (models.py:215) ---- */
 int eunet_maxpool2_fwd(const void* x, int ldx, void* out, int ldo, int dtype, int B, int H, int W, int C, void* stream);
@@ -141,7 +153,7 @@ int eunet_tail_dec1_fwd(const void* d2, int ldd2, int dtype, const float* w1 /*[
 /* d1 = up(z): d1p = activation-dtype copy padded to 16 channels (conv input), d14 = fp32 [4M][4] copy (residual; may be NULL) */
 int eunet_tail_up_fwd(const float* z4, void* d1p /*[B,2H,2W,16]*/, float* d14, int dtype, int B, int H, int W, void* stream);
 /* NCHW fp32 [B,3,H,W] -> pixel-major [B*H*W][4] fp32 (the gradient of the logits as the tail backward kernels read it) */
-int eunet_tail_pack3(const float* src, float* dst4, int B, int H, int W, void* stream);
+int eunet_tail_pack3(const float* src, float* dst4, int B, int H, int W, const float* gscale, void* stream);
 int eunet_tail_out_fwd(const float* d14, const void* mid /*[B,2H,2W,64]*/, int dtype, const float* scale, const float* shift,
                        const float* w3 /*[3][64]*/, const float* b3, float* out /*[B,3,2H,2W]*/, int B, int H, int W,
                        void* stream);
@@ -160,15 +172,18 @@ int eunet_tail_bwd_dmid(const float* dout4, const void* mid, void* dmid, int dty
  *   dx4[p][i] = sum_{tap,co} dmid[p+tap-(1,1),co] * w_packed_flip[i][tap][co], i < 3   (fp32 [pixels][4]). */
 int eunet_tail_bwd_fused(const float* dout4, const void* mid_raw, const void* d1p16, const void* w_packed_flip,
                          const float* scale, const float* shift, const float* mean, const float* invstd, const float* w3,
-                         const double* acc, float* dx4, float* dw_packed, int B, int H2, int W2, void* stream);
+                         const double* acc, float* dx4, float* dw_packed, int dtype, int B, int H2, int W2, void* stream);
 /* dd1p: gradient w.r.t. d1, `dd1_stride` elements of `dtype` per pixel of which the first 3 are read
  * (16 = the padded conv3x3 dgrad output; 4 with dtype fp32 = eunet_conv3x3_dgrad_few's dx4) */
 int eunet_tail_up_bwd(const void* dd1p /*[B,2H,2W,dd1_stride]*/, int dtype, int dd1_stride, const float* dout, float* dz4,
-                      int B, int H, int W, void* stream);
+                      int B, int H, int W, const float* gscale, void* stream);
 int eunet_tail_dec1_bwd(const float* dz4, const void* d2, int ldd2, void* dd2, int lddd2, int dtype, const float* w1,
                         double* acc /*[192 + 3]*/, long long M, void* stream);
-/* double accumulators -> fp32 parameter gradients */
-int eunet_cast_f64_f32(const double* src, float* dst, long long n, void* stream);
+/* double accumulators -> fp32 parameter gradients (times gscale[1] when gscale != NULL) */
+int eunet_cast_f64_f32(const double* src, float* dst, long long n, const float* gscale, void* stream);
+/* fp16 mode: gscale[0] = S = 2^floor(log2(target_max / max|g|)), gscale[1] = 1/S (S = 1 for an all-zero or non-finite g);
+ * gscale: 4 floats of device memory ([2] is scratch).  g: the fp32 gradient of the logits (loss.backward()). */
+int eunet_grad_scale(const float* g, long long n, float target_max, float* gscale, void* stream);
 
 /* ---- loss (train_eval.py:37-60 FocalLoss, 134-157 dice_loss, 159-181 tversky_loss, 183-197 combined,
  * 261-337 per-sample loop, 306-310 logit resize == 2x2 mean) ---- */

@@ -34,11 +34,10 @@ def test_grad_production_order_covers_every_parameter_once():
 
 def test_pack_specs_and_wgrad_workspace():
     from enhanced_unet_b200 import engine
-    cx = engine._Ctx.__new__(engine._Ctx)
-    cx.dt = torch.bfloat16
+    cx = engine._Ctx(torch.device("cpu"), torch.float16)
     train, infer = engine.pack_specs(cx, True), engine.pack_specs(cx, False)
     assert len(infer) == 15 and len(train) == 29                                      # no dgrad operand for enc1.0
-    assert ("model.enc1.0", False, True) in train                                     # hi/lo split of the first layer in bf16 mode
+    assert ("model.enc1.0", False, True) in train                                     # hi/lo split of the first layer in the 16-bit modes
     assert ("model.enc1.0", True, False) not in train and ("enhance.0", True, False) in train
     need = 64 * 9 * 16 + sum(co * 9 * ((ci + 15) // 16 * 16) + co * 9 * co for _, ci, co in engine.BLOCKS)
     assert engine.wgrad_workspace_numel() >= need

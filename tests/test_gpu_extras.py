@@ -98,7 +98,7 @@ def test_clipped_adamw_matches_torch_adamw_with_clip():
     assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
 
 
-@pytest.mark.parametrize("dtype,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+@pytest.mark.parametrize("dtype,tol", [("fp32", 1e-4), ("fp16", 2e-2), ("bf16", 2e-2)])
 def test_fusion_head_matches_reference_fixture(golden_dir, dtype, tol):
     """Secondary path a10: the in-file fusion blocks of the smp body, eval mode, against the fixture produced by
     re-instantiating the reference's own nn.Sequential blocks (oracle/make_golden.py:fusion_case)."""
@@ -199,7 +199,7 @@ def test_resize_bilinear_matches_torch(case):
     assert float((got - want).abs().max()) <= 2e-6
 
 
-@pytest.mark.parametrize("dtype,tol", [("fp32", 2e-5), ("bf16", 4e-3)])
+@pytest.mark.parametrize("dtype,tol", [("fp32", 2e-5), ("fp16", 1e-3), ("bf16", 4e-3)])
 def test_tta_inference_matches_reference_fixture(golden_dir, dtype, tol):
     """Evaluator._run_tta_inference (train_eval.py:419-453): base + 2 flips + 0.75x / 1.25x views, against the reference."""
     import oracle
