@@ -30,7 +30,7 @@ def broadcast_parameters(tensors: Iterable[torch.Tensor], src: int = 0, group=No
 class FlatGradBuffer:
     """ONE flat fp32 gradient buffer laid out in the order backward FINISHES gradients
     (``engine.grad_production_order()``: tail, dec2, dec3, dec4, enc4 ... enc1), cut into buckets of at most
-    ``bucket_bytes`` at parameter boundaries.  It is the ``engine.GradSink`` of the data-parallel path: the backward
+    ``bucket_bytes`` at parameter boundaries (and after every parameter named in ``close_after``).  It is the ``engine.GradSink`` of the data-parallel path: the backward
     kernels write every gradient straight into its slice (``dst``), and ``ready`` launches the asynchronous SUM
     all-reduce of a bucket the moment its last gradient has been enqueued - NCCL runs it on its own stream behind
     an event, so the exchange overlaps the rest of backward (the level-0/1 encoder blocks, i.e. most of its time).
@@ -39,7 +39,7 @@ class FlatGradBuffer:
 
     Works on any device (gloo on CPU in the tests); holds no CUDA-specific state."""
 
-    def __init__(self, named_shapes: Sequence, device, bucket_bytes: int = 8 << 20, group=None):
+    def __init__(self, named_shapes: Sequence, device, bucket_bytes: int = 8 << 20, group=None, close_after: Sequence[str] = ()):
         self.group = group
         self.dev = torch.device(device)
         self.names: List[str] = [n for n, _ in named_shapes]
@@ -61,12 +61,16 @@ class FlatGradBuffer:
             hi = self.offsets[n] + torch.Size(self.shapes[n]).numel()
             nxt = self.names[i + 1] if i + 1 < len(self.names) else None
             nxt_hi = (self.offsets[nxt] + torch.Size(self.shapes[nxt]).numel()) if nxt else None
-            if nxt is None or (nxt_hi - lo) * 4 > bucket_bytes:
+            if nxt is None or (nxt_hi - lo) * 4 > bucket_bytes or n in close_after:
                 self._closes[n] = len(self.buckets)
                 self.buckets.append((lo, hi))
                 lo = hi
         self._work: List = []
         self._launched = 0
+
+    # Encoder levels finish ~35 % / ~15 % of backward before its end: closing a bucket after each of them sends their
+    # gradients on their way then, so that only enc1's 154 KB (the last bucket) is exchanged after the last kernel.
+    LEVEL_ENDS = ("model.enc3.0.bias", "model.enc2.0.bias")
 
     @classmethod
     def for_model(cls, model: torch.nn.Module, bucket_bytes: int = 8 << 20, group=None) -> "FlatGradBuffer":
@@ -76,7 +80,7 @@ class FlatGradBuffer:
         if set(order) != set(params):
             raise RuntimeError("FlatGradBuffer: the model's parameters do not match the hot path's production order")
         dev = next(iter(params.values())).device
-        return cls([(n, params[n].shape) for n in order], dev, bucket_bytes, group)
+        return cls([(n, params[n].shape) for n in order], dev, bucket_bytes, group, close_after=cls.LEVEL_ENDS)
 
     # ---- engine.GradSink protocol ----
     def dst(self, name: str, shape) -> torch.Tensor:

@@ -5,7 +5,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,driver_version,memory.total --format=csv > gpurun_out/gpu_info.txt 2>&1
 status=0
-for f in tests/test_gpu_probe.py tests/test_gpu_kernels.py tests/test_gpu_model.py tests/test_gpu_extras.py "$@"; do
+for f in tests/test_gpu_probe.py tests/test_gpu_kernels.py tests/test_gpu_model.py tests/test_gpu_extras.py tests/test_gpu_parallel.py "$@"; do
   name=$(basename "$f" .py)
   echo "=== $f"
   timeout 900 python -m pytest "$f" -q -rA -m gpu --maxfail=25 --no-header -p no:cacheprovider > "gpurun_out/${name}.log" 2>&1

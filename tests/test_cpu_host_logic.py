@@ -30,6 +30,11 @@ def test_grad_production_order_covers_every_parameter_once():
         assert buf.grads[n].shape == p.shape and buf.grads[n].is_contiguous()
     with pytest.raises(RuntimeError):
         buf.dst("model.enc1.0.weight", (1, 2, 3))
+    # buckets close at the ends of encoder levels 3 and 2: only enc1's gradients (154 KB) are exchanged after the last kernel
+    ends = [[n for n in buf.names if lo <= buf.offsets[n] < hi][-1] for lo, hi in buf.buckets]
+    assert "model.enc3.0.bias" in ends and "model.enc2.0.bias" in ends and ends[-1] == "model.enc1.0.bias"
+    lo, hi = buf.buckets[-1]
+    assert all(n.startswith("model.enc1.") for n in buf.names if lo <= buf.offsets[n] < hi) and (hi - lo) * 4 < 160 * 1024
 
 
 def test_pack_specs_and_wgrad_workspace():

@@ -246,3 +246,71 @@ def test_host_batch_prefetcher_round_trips():
         assert torch.equal(x.cpu(), hx) and torch.equal(t.cpu(), ht)
     with pytest.raises(RuntimeError):
         pf.get()
+
+
+def test_five_step_trajectory_matches_reference_optimiser():
+    """Multi-step parity of the FULL training step (reference train_eval.py:236-353: forward -> combined loss -> backward ->
+    clip_grad_norm_(1.0) -> AdamW -> BatchNorm running statistics), fp32 mode, five steps of ``Trainer.train_step`` against
+    the oracle port driven by ``torch.optim.AdamW`` + ``clip_grad_norm_``.
+
+    What can and cannot agree: AdamW's first steps are sign-like (update = lr * m / (sqrt(v) + eps)), so an element whose
+    gradient is smaller than the fp32 summation-order difference of two correct implementations can move by 2 * lr in
+    opposite directions; parameters are therefore compared by relative L2 and by the cosine of the 5-step update, the
+    loss of every step (which sees all of it) at 1e-3.  The conv biases in front of a train-mode BatchNorm are excluded:
+    their true gradient is zero, the reference random-walks them on fp32 rounding noise (+-lr per step), this path keeps
+    them still - they cancel in training and enter eval only through running_mean, which is compared without them."""
+    import re
+    import oracle
+    from enhanced_unet_b200.models import EnhancedUNet
+    from enhanced_unet_b200.train_eval import Trainer
+    pre_bn_bias = re.compile(r"^(model\.(enc|dec)[1234]\.(0|3)|enhance\.0)\.bias$")
+    lr, steps = 1e-3, 5
+    sd = oracle.make_state_dict(5, randomize_bn=False)
+    xs = [oracle.make_input(2, 64, 64, 30 + i) for i in range(steps)]
+    ts = [oracle.make_target(2, 64, 64, 40 + i) for i in range(steps)]
+    # ---- reference side (CPU oracle + torch optimiser)
+    params = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in sd.items()}
+    plist = [p for p in params.values() if p.requires_grad]
+    opt = torch.optim.AdamW(plist, lr=lr, weight_decay=1e-4, betas=(0.9, 0.999))
+    ref_losses = []
+    for x, t in zip(xs, ts):
+        opt.zero_grad()
+        y, nb = oracle.unet_forward(params, x, train=True)
+        loss = oracle.batch_loss(y, t)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(plist, 1.0)
+        opt.step()
+        params.update(nb)
+        ref_losses.append(float(loss))
+    # ---- this repo
+    m = EnhancedUNet(3, dtype="fp32")
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    tr = Trainer(m, "cuda", "enhanced_unet", total_epochs=50)
+    for g in tr.optimizer.param_groups:
+        g["lr"] = lr
+    losses = [float(tr.train_step(x, [t[0], t[1]])) for x, t in zip(xs, ts)]
+    for k, (a, b) in enumerate(zip(losses, ref_losses)):
+        assert abs(a - b) <= 1e-3 * abs(b), (k, a, b)
+    new = m.state_dict()
+    worst_p, worst_c, worst_s = 0.0, 1.0, 0.0
+    for name, ref in params.items():
+        got = new[name].detach().cpu()
+        if name.endswith("num_batches_tracked"):
+            assert int(got) == steps == int(ref), name
+        elif "running_" in name:
+            ref_t, got_t = ref.double(), got.double()
+            # running_mean carries the conv bias, which the reference random-walks by +-lr per step (see the docstring)
+            tol = 1e-4 + (steps * lr / max(float(ref_t.abs().max()), 1e-12) if name.endswith("running_mean") else 0.0)
+            e = float((got_t - ref_t).abs().max() / ref_t.abs().max())
+            worst_s = max(worst_s, e if name.endswith("running_var") else 0.0)
+            assert e <= tol, (name, e, tol)
+        elif not pre_bn_bias.match(name):
+            p0 = sd[name].double()
+            dr, dg = ref.detach().double() - p0, got.double() - p0
+            rel = float((got.double() - ref.detach().double()).norm() / ref.detach().double().norm())
+            cos = float((dr * dg).sum() / (dr.norm() * dg.norm() + 1e-300))
+            worst_p, worst_c = max(worst_p, rel), min(worst_c, cos)
+            assert rel <= 2e-3 and cos >= 0.97, (name, rel, cos)
+    print(f"[trajectory] losses {['%.5f' % v for v in losses]} vs {['%.5f' % v for v in ref_losses]}; worst parameter relL2 "
+          f"{worst_p:.2e}, worst update cosine {worst_c:.4f}, worst running_var err {worst_s:.2e}")
