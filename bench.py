@@ -482,16 +482,24 @@ def main_gpu(args):
         barrier()
         return maxrank(e0.elapsed_time(e1))
 
+    # One GPU: the whole step is ONE CUDA-graph launch (graph.GraphedTrainStep: the public API for a fixed-shape training
+    # loop).  N > 1: the eager step - the NCCL exchange launched from inside backward is not captured.
+    gstep = None
+    run_step = step
+    if world == 1 and not args.no_graph:
+        from enhanced_unet_b200.graph import GraphedTrainStep
+        gstep = GraphedTrainStep(model, opt, BATCH, RES, RES, warmup_steps=2, example=(x_dev, t_dev))
+        run_step = gstep
     for _ in range(args.warmup):
-        step(x_dev, t_dev)
+        run_step(x_dev, t_dev)
     lib.COUNTERS.clear()
     clk = ClockSampler(local)
     if rank == 0:          # one nvidia-smi poller per job, not one per rank
         with clk:
-            ms = timed(lambda: step(x_dev, t_dev), args.steps)
+            ms = timed(lambda: run_step(x_dev, t_dev), args.steps)
     else:
-        ms = timed(lambda: step(x_dev, t_dev), args.steps)
-    launches = sum(lib.COUNTERS.values())
+        ms = timed(lambda: run_step(x_dev, t_dev), args.steps)
+    launches = gstep.launches_per_step * args.steps if gstep is not None else sum(lib.COUNTERS.values())
     value = world * BATCH * args.steps / (ms / 1e3)
     model.check_numerics()
 
@@ -507,7 +515,7 @@ def main_gpu(args):
             x, t = pf.get()
             if i + 1 < n:
                 pf.submit(x_host, t_host)
-            float(step(x, t).detach())
+            float(run_step(x, t).detach())
 
     e2e_run(min(2, max(1, args.warmup)))
     barrier()
@@ -623,6 +631,8 @@ def main_gpu(args):
                                        "fwd + focal/dice/tversky loss + bwd + clip + AdamW",
                            "global_batch": BATCH * world, "resolution": RES, "parallelism": f"dp{world}",
                            "l2": "working set (>5 GB of activations per step) far exceeds the 126 MB L2; no flush needed",
+                           "launch": ("one CUDA graph per step (graph.GraphedTrainStep), %d kernels-launching C-ABI calls captured" % gstep.launches_per_step)
+                                     if gstep is not None else "eager: one C-ABI call per kernel",
                            "conv_tflop_per_step": conv_flops_train(BATCH, RES) / 1e12},
                 "clocks": clk.summary(),
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
@@ -643,6 +653,7 @@ def main():
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16", "fp32"], help="compute mode of the product path")
     ap.add_argument("--no-cpu", action="store_true", help="skip the bounded CPU baseline leg")
     ap.add_argument("--no-stock", action="store_true", help="skip the stock-PyTorch comparator block")
+    ap.add_argument("--no-graph", action="store_true", help="one GPU: launch the step kernel by kernel instead of as one CUDA graph")
     ap.add_argument("--quick", action="store_true", help="training line only (no inference / comparator / CPU blocks): profiling runs")
     args = ap.parse_args()
     if args.impl == "reference":

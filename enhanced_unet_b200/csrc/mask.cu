@@ -145,7 +145,58 @@ resize_bilinear_kernel(const float* __restrict__ src, float* __restrict__ dst, i
     d[i] = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
   }
 }
+
+// F.pad(x, (0, w_pad, 0, h_pad), mode='reflect') on planar fp32 [planes][H][W] -> [planes][Hp][Wp] (train_eval.py:249-253,
+// 400-406: pad to multiples of 32 at the bottom / right).  Reflection without repeating the edge: index Hp > i >= H reads
+// 2 (H - 1) - i.
+__global__ void __launch_bounds__(256)
+reflect_pad_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int W, int Hp, int Wp) {
+  const long long plane = blockIdx.y;
+  const float* s = src + plane * (long long)H * W;
+  float* d = dst + plane * (long long)Hp * Wp;
+  const long long n = (long long)Hp * Wp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(i / Wp), x = (int)(i % Wp);
+    const int sy = y < H ? y : 2 * (H - 1) - y, sx = x < W ? x : 2 * (W - 1) - x;
+    d[i] = __ldg(s + (long long)sy * W + sx);
+  }
+}
+
+// Mean of the five TTA views of Evaluator._run_tta_inference (train_eval.py:419-453) in ONE pass: the horizontally /
+// vertically flipped views are un-flipped by index (no flipped copies), summed in the reference's order and divided by 5.
+__global__ void __launch_bounds__(256)
+tta_combine_kernel(const float* __restrict__ p0, const float* __restrict__ ph, const float* __restrict__ pv,
+                   const float* __restrict__ pa, const float* __restrict__ pb, float* __restrict__ out, int H, int W) {
+  const long long off = (long long)blockIdx.y * H * W;
+  const long long n = (long long)H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(i / W), x = (int)(i % W);
+    float v = __ldg(p0 + off + i);
+    v += __ldg(ph + off + (long long)y * W + (W - 1 - x));
+    v += __ldg(pv + off + (long long)(H - 1 - y) * W + x);
+    v += __ldg(pa + off + i);
+    v += __ldg(pb + off + i);
+    out[off + i] = v / 5.0f;
+  }
+}
 }  // namespace eunet
+
+extern "C" int eunet_reflect_pad(const float* src, float* dst, int planes, int H, int W, int Hp, int Wp, void* stream) {
+  using namespace eunet;
+  EUNET_REQUIRE(planes > 0 && planes <= 65535 && H > 0 && W > 0 && Hp >= H && Wp >= W, "reflect_pad: bad shape");
+  EUNET_REQUIRE(Hp - H < H && Wp - W < W, "reflect_pad: padding (%d, %d) must be smaller than the image (%d, %d)", Hp - H, Wp - W, H, W);
+  reflect_pad_kernel<<<img_grid((long long)Hp * Wp, planes), 256, 0, (cudaStream_t)stream>>>(src, dst, H, W, Hp, Wp);
+  return check_launch("reflect_pad");
+}
+
+extern "C" int eunet_tta_combine(const float* p_base, const float* p_hflip, const float* p_vflip, const float* p_s075,
+                                 const float* p_s125, float* out, int planes, int H, int W, void* stream) {
+  using namespace eunet;
+  EUNET_REQUIRE(planes > 0 && planes <= 65535 && H > 0 && W > 0, "tta_combine: bad shape");
+  EUNET_REQUIRE(p_base && p_hflip && p_vflip && p_s075 && p_s125 && out, "tta_combine: null operand");
+  tta_combine_kernel<<<img_grid((long long)H * W, planes), 256, 0, (cudaStream_t)stream>>>(p_base, p_hflip, p_vflip, p_s075, p_s125, out, H, W);
+  return check_launch("tta_combine");
+}
 
 extern "C" int eunet_resize_bilinear(const float* src, float* dst, int planes, int Hin, int Win, int Hout, int Wout, float ratio_h,
                                      float ratio_w, void* stream) {

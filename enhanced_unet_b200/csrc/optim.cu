@@ -106,9 +106,25 @@ __device__ __forceinline__ void adamw_elem(float& p, float g, float& m, float& v
   p = pi;
 }
 
+// CUDA-graph friendly step bookkeeping: the step counter and the learning rate live in device memory, so a captured
+// training step advances on every replay.  hyper[0] = lr (written by the host), state[0] = step (incremented here);
+// out = {lr, 1 - beta1^step, sqrt(1 - beta2^step), step}.
+__global__ void adamw_prepare_kernel(int* __restrict__ step, const float* __restrict__ lr, float beta1, float beta2,
+                                     float* __restrict__ out) {
+  const int s = *step + 1;
+  *step = s;
+  out[0] = *lr;
+  out[1] = (float)(1.0 - pow((double)beta1, (double)s));
+  out[2] = (float)sqrt(1.0 - pow((double)beta2, (double)s));
+  out[3] = (float)s;
+}
+
 __global__ void __launch_bounds__(256)
 adamw_multi_kernel(const __grid_constant__ TensorTable t, const double* __restrict__ gradsq, float max_norm, float lr, float beta1,
-                   float beta2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale) {
+                   float beta2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale, const float* __restrict__ hyper) {
+  if (hyper != nullptr) {      // device-resident {lr, bc1, bc2_sqrt} (adamw_prepare_kernel)
+    lr = hyper[0]; bc1 = hyper[1]; bc2_sqrt = hyper[2];
+  }
   float clip = 1.f;
   if (gradsq != nullptr && max_norm > 0.f) {
     const float norm = (float)sqrt(*gradsq) * fabsf(grad_scale);
@@ -195,10 +211,16 @@ extern "C" int eunet_sumsq_multi(const void* const* g, const long long* n, int c
   return 0;
 }
 
+extern "C" int eunet_adamw_prepare(int* step_dev, const float* lr_dev, float beta1, float beta2, float* hyper_out, void* stream) {
+  EUNET_REQUIRE(step_dev && lr_dev && hyper_out, "adamw_prepare: null operand");
+  adamw_prepare_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, lr_dev, beta1, beta2, hyper_out);
+  return check_launch("adamw_prepare");
+}
+
 extern "C" int eunet_adamw_multi(void* const* p, const void* const* g, void* const* m, void* const* v, const long long* n, int count,
                                  const double* gradsq, float max_norm, float lr, float beta1, float beta2, float eps,
-                                 float weight_decay, int step, float grad_scale, void* stream) {
-  EUNET_REQUIRE(count > 0 && step >= 1, "adamw_multi: count=%d step=%d", count, step);
+                                 float weight_decay, int step, float grad_scale, const float* hyper_dev, void* stream) {
+  EUNET_REQUIRE(count > 0 && (step >= 1 || hyper_dev != nullptr), "adamw_multi: count=%d step=%d", count, step);
   // bias corrections in double, as torch.optim.AdamW forms them in Python floats (1 - 0.999f^step carries ~6e-5 in fp32)
   const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
   const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
@@ -207,7 +229,7 @@ extern "C" int eunet_adamw_multi(void* const* p, const void* const* g, void* con
     const int c = count - first < kMaxTensors ? count - first : kMaxTensors;
     if (fill_table(t, p, g, m, v, n, first, c)) return -1;
     adamw_multi_kernel<<<clamp_grid(t.cstart[c], 8), 256, 0, (cudaStream_t)stream>>>(t, gradsq, max_norm, lr, beta1, beta2, eps,
-                                                                                    weight_decay, bc1, bc2_sqrt, grad_scale);
+                                                                                    weight_decay, bc1, bc2_sqrt, grad_scale, hyper_dev);
     if (check_launch("adamw_multi")) return -2;
   }
   return 0;

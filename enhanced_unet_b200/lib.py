@@ -62,12 +62,15 @@ SIGNATURES = {
     "eunet_loss_bwd": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p],
     "eunet_resize_bilinear": [_p, _p, _i, _i, _i, _i, _i, _f, _f, _p],
     "eunet_softmax_probs": [_p, _p, _i, _i, _i, _i, _p],
+    "eunet_reflect_pad": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "eunet_tta_combine": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "eunet_probs_to_mask": [_p, _p, _p, _i, _i, _i, _p],
     "eunet_fusion_gate_fwd": [_p, _p, _p, _p, _i, _p, _i, _i, _i, _p],
     "eunet_fusion_out_fwd": [_p, _p, _p, _i, _i, _i, _p],
     "eunet_sumsq": [_p, _ll, _p, _p],
     "eunet_sumsq_multi": [_p, _p, _i, _p, _p],
-    "eunet_adamw_multi": [_p, _p, _p, _p, _p, _i, _p, _f, _f, _f, _f, _f, _f, _i, _f, _p],
+    "eunet_adamw_multi": [_p, _p, _p, _p, _p, _i, _p, _f, _f, _f, _f, _f, _f, _i, _f, _p, _p],
+    "eunet_adamw_prepare": [_p, _p, _f, _f, _p, _p],
     "eunet_adamw_step": [_p, _p, _p, _p, _ll, _p, _f, _f, _f, _f, _f, _f, _i, _f, _p],
     "eunet_probe_umma": [_p, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p, _p, _i, _p],
 }

@@ -44,13 +44,15 @@ class _SaturationMonitor:
         return self.dev
 
     def publish(self) -> None:
+        if torch.cuda.is_current_stream_capturing():
+            return          # inside a CUDA-graph capture: graph.GraphedTrainStep publishes after each replay
         if self.dev is not None:
             self.host.copy_(self.dev, non_blocking=True)
             self.event = torch.cuda.Event()
             self.event.record()
 
     def check(self, block: bool) -> None:
-        if self.event is None:
+        if self.event is None or torch.cuda.is_current_stream_capturing():
             return
         if block:
             self.event.synchronize()

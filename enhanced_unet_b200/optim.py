@@ -23,6 +23,38 @@ class ClippedAdamW(torch.optim.Optimizer):
         super().__init__(params, defaults)
         self.on_update = on_update
         self._sq: Optional[torch.Tensor] = None
+        # device-resident step counter / learning rate (``graph.GraphedTrainStep``): a captured step must advance on replay
+        self._dev_state: Optional[dict] = None
+
+    def enable_device_state(self) -> dict:
+        """Keep the step counter and the learning rate in device memory (needed when ``step`` is captured into a CUDA
+        graph).  Requires one parameter group and a common step count.  The python-side ``state[p]['step']`` keeps being
+        advanced by whoever replays the graph (``sync_steps``) so that ``state_dict()`` stays in the torch AdamW layout."""
+        if len(self.param_groups) != 1:
+            raise RuntimeError("device-resident optimiser state needs exactly one parameter group")
+        ps = [p for p in self.param_groups[0]["params"]]
+        steps = {int(self.state[p]["step"]) for p in ps if len(self.state[p])}
+        if len(steps) > 1:
+            raise RuntimeError("device-resident optimiser state needs a common step count")
+        dev = ps[0].device
+        self._dev_state = {"step": torch.tensor([steps.pop() if steps else 0], dtype=torch.int32, device=dev),
+                           "lr": torch.tensor([float(self.param_groups[0]["lr"])], dtype=torch.float32, device=dev),
+                           "hyper": torch.zeros(4, dtype=torch.float32, device=dev), "lr_host": float(self.param_groups[0]["lr"])}
+        return self._dev_state
+
+    def push_lr(self) -> None:
+        """Copy a learning rate changed by a scheduler into the device-resident value (no-op when unchanged)."""
+        ds = self._dev_state
+        if ds is not None and float(self.param_groups[0]["lr"]) != ds["lr_host"]:
+            ds["lr_host"] = float(self.param_groups[0]["lr"])
+            ds["lr"].fill_(ds["lr_host"])
+
+    def sync_steps(self, n: int = 1) -> None:
+        """Advance the python-side step counters by ``n`` replays of a captured step."""
+        for g in self.param_groups:
+            for p in g["params"]:
+                if len(self.state[p]):
+                    self.state[p]["step"] = int(self.state[p]["step"]) + n
 
     def _all_params(self):
         for g in self.param_groups:
@@ -66,6 +98,13 @@ class ClippedAdamW(torch.optim.Optimizer):
                 runs[-1][1].append(i)
             else:
                 runs.append((key, [i]))
+        hyper = None
+        if self._dev_state is not None:
+            if len(runs) != 1:
+                raise RuntimeError("device-resident optimiser state needs all parameters in one run (same hyper-parameters / step)")
+            ds = self._dev_state
+            call("eunet_adamw_prepare", ds["step"].data_ptr(), ds["lr"].data_ptr(), runs[0][0][2], runs[0][0][3], ds["hyper"].data_ptr())
+            hyper = ds["hyper"].data_ptr()
         for key, idxs in runs:
             k = len(idxs)
             VPk, LLk = ctypes.c_void_p * k, ctypes.c_longlong * k
@@ -73,7 +112,7 @@ class ClippedAdamW(torch.optim.Optimizer):
             call("eunet_adamw_multi", VPk(*[p.data_ptr() for p in ps]), VPk(*[grads[i].data_ptr() for i in idxs]),
                  VPk(*[self.state[p]["exp_avg"].data_ptr() for p in ps]), VPk(*[self.state[p]["exp_avg_sq"].data_ptr() for p in ps]),
                  LLk(*[p.numel() for p in ps]), k, self._sq.data_ptr(), key[0], key[1], key[2], key[3], key[4], key[5], key[6],
-                 float(grad_scale))
+                 float(grad_scale), hyper)
         # the kernels wrote the parameters behind autograd's back: bump their version counters, which is what the
         # packed-filter caches (engine.PackCache) key on - the optimiser is safe on its own, ``on_update`` is an optimisation
         for _, p in items:

@@ -48,10 +48,24 @@ class FocalLoss(torch.nn.Module):
 
 
 def _pad32(images: torch.Tensor):
+    """Reflect-pad [B,C,h,w] at the bottom / right to multiples of 32 (train_eval.py:249-253 / 400-406) on the pad kernel."""
     h, w = images.shape[-2:]
     h_pad, w_pad = (32 - h % 32) % 32, (32 - w % 32) % 32
     if h_pad or w_pad:
-        images = F.pad(images, (0, w_pad, 0, h_pad), mode="reflect")    # train_eval.py:249-253 / 400-406
+        if not images.is_cuda:
+            raise RuntimeError("_pad32 runs on CUDA tensors (no CPU fallback)")
+        if h_pad >= h or w_pad >= w:
+            raise RuntimeError(f"reflect padding ({h_pad}, {w_pad}) must be smaller than the image ({h}, {w})")   # as F.pad
+        src = images.contiguous().float()
+        b, c = src.shape[:2]
+        out = torch.empty(b, c, h + h_pad, w + w_pad, device=src.device, dtype=torch.float32)
+        done, planes = 0, b * c
+        sv, ov = src.view(planes, h, w), out.view(planes, h + h_pad, w + w_pad)
+        while done < planes:
+            k = min(65535, planes - done)
+            call("eunet_reflect_pad", ptr(sv[done:]), ptr(ov[done:]), k, h, w, h + h_pad, w + w_pad)
+            done += k
+        images = out
     return images, h_pad, w_pad
 
 
@@ -183,14 +197,22 @@ class Evaluator:
         """Reference _run_tta_inference (train_eval.py:419-453) for a batch: mean of the base view, the horizontal and
         vertical flips (index remaps) and the 0.75x / 1.25x bilinear views resized back to the input size."""
         images = images.to(self.device)
-        h, w = images.shape[-2:]
-        p = self._run_model_batch(images)
-        p = p + self._run_model_batch(images.flip(-1)).flip(-1)
-        p = p + self._run_model_batch(images.flip(-2)).flip(-2)
+        b, _, h, w = images.shape
+        views = [self._run_model_batch(images).contiguous(),
+                 self._run_model_batch(images.flip(-1)).contiguous(),        # un-flipped by index inside the combine kernel
+                 self._run_model_batch(images.flip(-2)).contiguous()]
         for scale in (0.75, 1.25):
             scaled = self._resize(images, scale_factor=scale)
-            p = p + self._resize(self._run_model_batch(scaled), size=(h, w))
-        return p / 5.0
+            views.append(self._resize(self._run_model_batch(scaled), size=(h, w)))
+        out = torch.empty(b, 3, h, w, device=views[0].device, dtype=torch.float32)
+        done, planes = 0, b * 3
+        vs = [v.view(planes, h, w) for v in views]
+        ov = out.view(planes, h, w)
+        while done < planes:
+            k = min(65535, planes - done)
+            call("eunet_tta_combine", *[ptr(v[done:]) for v in vs], ptr(ov[done:]), k, h, w)
+            done += k
+        return out
 
     def _run_tta_inference(self, image: torch.Tensor) -> torch.Tensor:
         """Single-image form with the reference's signature ([3,h,w] -> [3,h,w] probabilities)."""

@@ -202,6 +202,13 @@ int eunet_softmax_probs(const float* logits, float* probs /*[B,3,H,W]*/, int B, 
  * exactly as ATen forms it: (float)(1.0 / scale_factor) when a scale factor was given, (float)in / out for size=. */
 int eunet_resize_bilinear(const float* src, float* dst, int planes, int Hin, int Win, int Hout, int Wout, float ratio_h,
                           float ratio_w, void* stream);
+/* F.pad(x, (0, Wp - W, 0, Hp - H), mode='reflect') on planar fp32 [planes][H][W] -> [planes][Hp][Wp]: the pad to multiples
+ * of 32 in front of the model (train_eval.py:249-253 training, 400-406 inference). */
+int eunet_reflect_pad(const float* src, float* dst, int planes, int H, int W, int Hp, int Wp, void* stream);
+/* mean of the five TTA views (train_eval.py:419-453) on planar fp32 [planes][H][W]: p_hflip / p_vflip are the
+ * probabilities of the horizontally / vertically flipped INPUT as the model returned them (un-flipped here by index). */
+int eunet_tta_combine(const float* p_base, const float* p_hflip, const float* p_vflip, const float* p_s075, const float* p_s125,
+                      float* out, int planes, int H, int W, void* stream);
 /* argmax + threshold cascade + the two global pixel-ratio filters, per image; mask uint8 [B,H,W];
  * counts int32 [B][2] = (live, dead) pixel counts after the cascade and before the ratio filters (overwritten) */
 int eunet_probs_to_mask(const float* probs, unsigned char* mask, int* counts, int B, int H, int W, void* stream);
@@ -226,7 +233,12 @@ int eunet_adamw_step(float* p, const float* g, float* m, float* v, long long n, 
 int eunet_sumsq_multi(const void* const* g, const long long* n, int count, double* out, void* stream);
 int eunet_adamw_multi(void* const* p, const void* const* g, void* const* m, void* const* v, const long long* n, int count,
                       const double* gradsq, float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay,
-                      int step, float grad_scale, void* stream);
+                      int step, float grad_scale, const float* hyper_dev /* NULL, or eunet_adamw_prepare's output */,
+                      void* stream);
+/* CUDA-graph friendly bookkeeping: *step_dev += 1; hyper_out = {*lr_dev, 1 - beta1^step, sqrt(1 - beta2^step), step}.
+ * With hyper_dev != NULL eunet_adamw_multi takes lr and the bias corrections from there instead of its arguments, so a
+ * captured training step (enhanced_unet_b200/graph.py) advances correctly on every replay. */
+int eunet_adamw_prepare(int* step_dev, const float* lr_dev, float beta1, float beta2, float* hyper_out /*[4]*/, void* stream);
 
 /* ---- bring-up / verification: UMMA + TMA probe (tests/test_gpu_probe.py) ---- */
 int eunet_probe_umma(const void* a, int a_rows, int a_cols, int a_box_rows, int a_box_cols, int a_swizzle, const void* b,
