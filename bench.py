@@ -376,7 +376,7 @@ def inference_block(model, dev, world: int, rank: int, peaks: dict, reps: int = 
         assert int(cm.sum()) == b * res * res
         gflop = conv_flops_fwd(total, res) / 1e9
         out[key] = {"images_per_s": round(total / ms * 1e3, 1), "ms_per_batch": round(ms, 2), "images": total, "resolution": res,
-                    "images_per_forward_call": sub, "conv_tflops": round(gflop / ms, 1), "frac_of_tensor_peak": round(gflop / ms / peak_tf, 3)}
+                    "images_per_forward_call": sub, "conv_tflops": round(gflop / ms, 1), "frac_of_tensor_peak": round(gflop / ms / (peak_tf * world), 3)}
         del x, gt
         torch.cuda.empty_cache()
     model.check_numerics()
