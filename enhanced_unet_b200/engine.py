@@ -259,7 +259,7 @@ def _conv_bn_train(cx: _Ctx, packs: PackCache, sd: Dict[str, torch.Tensor], conv
             cin_real=w.shape[1] if w.shape[1] < 16 else 0)
     f32 = torch.float32
     scale, shift, mean, invstd = (cx.empty(cout, dtype=f32) for _ in range(4))
-    call("eunet_bn_finalize", ptr(stats), M, ptr(sd[bn + ".weight"]), ptr(sd[bn + ".bias"]), ptr(sd[conv + ".bias"]),
+    call("eunet_bn_finalize", ptr(stats), M, ptr(sd[bn + ".weight"]), ptr(sd[bn + ".bias"]), ptr(sd.get(conv + ".bias")),
          ptr(sd[bn + ".running_mean"]), ptr(sd[bn + ".running_var"]), ptr(sd[bn + ".num_batches_tracked"]), BN_MOMENTUM, BN_EPS,
          ptr(scale), ptr(shift), ptr(mean), ptr(invstd), cout)
     call("eunet_bn_apply_relu", ptr(y), _ld(y), ptr(out), _ld(out), ptr(pooled), _ld(pooled) if pooled is not None else 0,
@@ -606,3 +606,154 @@ def fusion_forward(sd: Dict[str, torch.Tensor], out_main: torch.Tensor, out_aux:
     out = torch.empty(B, 3, H, W, device=out_main.device, dtype=f32)
     call("eunet_fusion_out_fwd", ptr(z4), ptr(res4), ptr(out), B, H, W)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# fusion blocks of the smp body (reference models.py:276-302, 320-328) in TRAINING mode + backward
+# ---------------------------------------------------------------------------------------------
+FUSION_HEAD = (("fusion_head.0", "fusion_head.1", 6, 256, 0), ("fusion_head.4", "fusion_head.5", 256, 128, 1),
+               ("fusion_head.8", "fusion_head.9", 128, 64, None))     # (conv, bn, Cin, Cout, index of the Dropout2d factor after it)
+
+
+def _gate_blob(sd: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """HOST blob of the small gate / residual filters (kernel parameter block): w0[3][6][9], w3[6][3], wr[3][6], br[3]."""
+    blob = torch.cat([sd["attention_gate.0.weight"].detach().float().cpu().reshape(-1),
+                      sd["attention_gate.3.weight"].detach().float().cpu().reshape(-1),
+                      sd["fusion_residual.weight"].detach().float().cpu().reshape(-1),
+                      sd["fusion_residual.bias"].detach().float().cpu().reshape(-1)]).contiguous()
+    assert blob.numel() == 201
+    return blob
+
+
+class FusionSaved:
+    def __init__(self):
+        self.B = self.H = self.W = 0
+        self.t: Dict[str, torch.Tensor] = {}
+        self.bn: Dict[str, _BNSaved] = {}
+        self.scales = None
+
+
+def fusion_train_forward(sd: Dict[str, torch.Tensor], out_main: torch.Tensor, out_aux: torch.Tensor, act_dtype: torch.dtype,
+                         packs: PackCache, scales, amax: Optional[torch.Tensor] = None):
+    """Training-mode forward of the fusion blocks; ``scales`` = (s1 [B,256], s2 [B,128]) fp32 Dropout2d factors
+    (keep / (1 - p)).  Returns (out [B,3,H,W] fp32, saved state for ``fusion_backward``)."""
+    import ctypes
+    B, _, H, W = out_main.shape
+    cx = _Ctx(out_main.device, act_dtype)
+    cx.amax = amax
+    f32 = torch.float32
+    M = B * H * W
+    main, aux = out_main.contiguous().float(), out_aux.contiguous().float()
+    blob = _gate_blob(sd)
+    bp = ctypes.c_void_p(blob.data_ptr())
+    zp64 = _ZeroPool(cx, 2 * (3 + 6 + 256 + 128 + 64) + 64 * 8, torch.float64)
+    sv = FusionSaved()
+    sv.B, sv.H, sv.W, sv.scales = B, H, W, scales
+
+    def finalize(stats, bn, C):
+        c = cx.empty(4 * C, dtype=f32)        # {scale, shift, mean, invstd}
+        call("eunet_bn_finalize", ptr(stats), M, ptr(sd[bn + ".weight"]), ptr(sd[bn + ".bias"]), None, ptr(sd[bn + ".running_mean"]),
+             ptr(sd[bn + ".running_var"]), ptr(sd[bn + ".num_batches_tracked"]), BN_MOMENTUM, BN_EPS, ptr(c[0:C]), ptr(c[C:2 * C]),
+             ptr(c[2 * C:3 * C]), ptr(c[3 * C:4 * C]), C)
+        return c
+
+    a1 = cx.empty(M, 4, dtype=f32)
+    st1 = zp64.take(6)
+    call("eunet_fusion_gate_conv_fwd", ptr(main), ptr(aux), bp, ptr(a1), ptr(st1), B, H, W)
+    bn1 = finalize(st1, "attention_gate.1", 3)
+    a2 = cx.empty(M, 8, dtype=f32)
+    st2 = zp64.take(12)
+    call("eunet_fusion_gate_mid_fwd", ptr(a1), ptr(bn1[0:3]), ptr(bn1[3:6]), bp, ptr(a2), ptr(st2), M)
+    bn2 = finalize(st2, "attention_gate.4", 6)
+    fg16 = cx.empty(M, 16)
+    res4 = cx.empty(M, 4, dtype=f32)
+    call("eunet_fusion_gate_apply_fwd", ptr(main), ptr(aux), ptr(a2), ptr(bn2[0:6]), ptr(bn2[6:12]), bp, ptr(fg16), cx.code, ptr(res4),
+         B, H, W)
+    sv.t.update(main=main, aux=aux, a1=a1, a2=a2, bn1=bn1, bn2=bn2)
+    h, cin_p = fg16, 16
+    for conv, bn, cin, cout, drop in FUSION_HEAD:
+        nxt = cx.empty(M, cout)
+        sv.bn[bn] = _conv_bn_train(cx, packs, sd, conv, bn, h, B, H, W, cin_p, cout, nxt, None, stats=zp64.take(2 * cout))
+        if drop is not None:
+            sc = scales[drop].contiguous().float()
+            assert sc.shape == (B, cout)
+            call("eunet_channel_scale", ptr(nxt), _ld(nxt), ptr(sc), cx.code, B, H * W, cout)
+        sv.t[conv + ".in"] = h
+        h, cin_p = nxt, cout
+    sv.t["h3"] = h
+    z4 = cx.empty(M, 4, dtype=f32)
+    w11 = sd["fusion_head.11.weight"].reshape(3, 64)
+    call("eunet_tail_dec1_fwd", ptr(h), _ld(h), cx.code, ptr(w11), ptr(sd["fusion_head.11.bias"]), ptr(z4), M)
+    out = torch.empty(B, 3, H, W, device=main.device, dtype=f32)
+    call("eunet_fusion_out_fwd", ptr(z4), ptr(res4), ptr(out), B, H, W)
+    return out, sv
+
+
+def fusion_backward(sd: Dict[str, torch.Tensor], sv: FusionSaved, dout: torch.Tensor, act_dtype: torch.dtype, packs: PackCache,
+                    amax: Optional[torch.Tensor] = None):
+    """Returns (dmain, daux, {parameter name: fp32 gradient}) for ``fusion_train_forward``."""
+    import ctypes
+    B, H, W = sv.B, sv.H, sv.W
+    cx = _Ctx(dout.device, act_dtype)
+    cx.amax = amax
+    f32, f64 = torch.float32, torch.float64
+    M = B * H * W
+    dout = dout.contiguous().float()
+    if cx.dt == torch.float16:
+        cx.gs = cx.empty(4, dtype=f32)
+        call("eunet_grad_scale", ptr(dout), dout.numel(), GRAD_SCALE_TARGET, ptr(cx.gs))
+    gs = cx.gs
+    grads: Dict[str, torch.Tensor] = {}
+    zp64 = _ZeroPool(cx, 2 * (256 + 128 + 64) + 200 + 219 + 64 * 8, f64)
+    pool = _ZeroPool(cx, 256 * 9 * 16 + 128 * 9 * 256 + 64 * 9 * 128 + 256)
+
+    def cast64(name, src, shape):
+        dst = torch.empty(shape, device=dout.device, dtype=f32)
+        call("eunet_cast_f64_f32", ptr(src), ptr(dst), dst.numel(), ptr(gs))
+        grads[name] = dst
+
+    dout4 = cx.empty(M, 4, dtype=f32)
+    call("eunet_tail_pack3", ptr(dout), ptr(dout4), B, H, W, ptr(gs))
+    h3 = sv.t["h3"]
+    acc2 = zp64.take(200)
+    dact = cx.empty(M, 64)
+    w11 = sd["fusion_head.11.weight"].reshape(3, 64)
+    call("eunet_tail_dec1_bwd", ptr(dout4), ptr(h3), _ld(h3), ptr(dact), _ld(dact), cx.code, ptr(w11), ptr(acc2), M)
+    cast64("fusion_head.11.weight", acc2[0:192], (3, 64, 1, 1))
+    cast64("fusion_head.11.bias", acc2[192:195], (3,))
+    for conv, bn, cin, cout, drop in reversed(FUSION_HEAD):
+        cin_p = _pad16(cin)
+        if drop is not None:     # gradient through Dropout2d: the same per-(sample, channel) factor
+            sc = sv.scales[drop].contiguous().float()
+            call("eunet_channel_scale", ptr(dact), _ld(dact), ptr(sc), cx.code, B, H * W, cout)
+        s = sv.bn[bn]
+        sums = zp64.take(2 * cout)
+        call("eunet_bn_bwd_reduce", ptr(dact), _ld(dact), ptr(s.y), _ld(s.y), cx.code, M, cout, ptr(s.scale), ptr(s.shift), ptr(s.mean),
+             ptr(s.invstd), ptr(sums))
+        dy = cx.empty(M, cout)
+        dg, db = torch.empty(cout, device=dout.device, dtype=f32), torch.empty(cout, device=dout.device, dtype=f32)
+        call("eunet_bn_bwd_apply", ptr(dact), _ld(dact), ptr(s.y), _ld(s.y), ptr(dy), _ld(dy), cx.code, M, cout, ptr(s.scale),
+             ptr(s.shift), ptr(s.mean), ptr(s.invstd), ptr(sums), ptr(dg), ptr(db), ptr(gs))
+        grads[bn + ".weight"], grads[bn + ".bias"] = dg, db
+        xin = sv.t[conv + ".in"]
+        dwp = conv3x3_wgrad(cx, xin, dy, B, H, W, cin_p, cout, pool, cin_real=cin if cin < 16 else 0)
+        grads[conv + ".weight"] = unpack_wgrad(dwp, cout, cin, gscale=gs)
+        dx = cx.empty(M, cin_p)
+        conv3x3(cx, dy, packs.get(cx, conv, sd[conv + ".weight"], True), dx, B, H, W, cout, cin_p, cout_real=cin if cin < 16 else 0)
+        dact = dx
+    blob = _gate_blob(sd)
+    acc = zp64.take(219)
+    dz1, dz2 = cx.empty(M, 4, dtype=f32), cx.empty(M, 8, dtype=f32)
+    dmain, daux = torch.empty(B, 3, H, W, device=dout.device, dtype=f32), torch.empty(B, 3, H, W, device=dout.device, dtype=f32)
+    t = sv.t
+    call("eunet_fusion_gate_bwd", ptr(t["main"]), ptr(t["aux"]), ptr(t["a1"]), ptr(t["a2"]), ptr(t["bn1"]), ptr(t["bn2"]), ptr(dact),
+         cx.code, ptr(dout4), ctypes.c_void_p(blob.data_ptr()), ptr(dz1), ptr(dz2), ptr(acc), ptr(dmain), ptr(daux), ptr(gs), B, H, W)
+    cast64("attention_gate.4.bias", acc[0:6], (6,))
+    cast64("attention_gate.4.weight", acc[6:12], (6,))
+    cast64("fusion_residual.weight", acc[12:30], (3, 6, 1, 1))
+    cast64("fusion_residual.bias", acc[30:33], (3,))
+    cast64("attention_gate.1.bias", acc[33:36], (3,))
+    cast64("attention_gate.1.weight", acc[36:39], (3,))
+    cast64("attention_gate.3.weight", acc[39:57], (6, 3, 1, 1))
+    cast64("attention_gate.0.weight", acc[57:219], (3, 6, 3, 3))
+    return dmain, daux, grads

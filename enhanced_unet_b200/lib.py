@@ -67,6 +67,11 @@ SIGNATURES = {
     "eunet_probs_to_mask": [_p, _p, _p, _i, _i, _i, _p],
     "eunet_fusion_gate_fwd": [_p, _p, _p, _p, _i, _p, _i, _i, _i, _p],
     "eunet_fusion_out_fwd": [_p, _p, _p, _i, _i, _i, _p],
+    "eunet_fusion_gate_conv_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "eunet_fusion_gate_mid_fwd": [_p, _p, _p, _p, _p, _p, _ll, _p],
+    "eunet_fusion_gate_apply_fwd": [_p, _p, _p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _p],
+    "eunet_fusion_gate_bwd": [_p] * 7 + [_i] + [_p] * 8 + [_i, _i, _i, _p],
+    "eunet_channel_scale": [_p, _i, _p, _i, _i, _ll, _i, _p],
     "eunet_sumsq": [_p, _ll, _p, _p],
     "eunet_sumsq_multi": [_p, _p, _i, _p, _p],
     "eunet_adamw_multi": [_p, _p, _p, _p, _p, _i, _p, _f, _f, _f, _f, _f, _f, _i, _f, _p, _p],

@@ -222,13 +222,43 @@ def get_model(model_name: str, num_classes: int = 3, device: str = "cuda", train
     return model
 
 
+class _FusionFunction(torch.autograd.Function):
+    """Training-mode fusion blocks as one autograd node (fixed kernel schedules in engine.py)."""
+
+    @staticmethod
+    def forward(ctx, module: "FusionHead", out_main, out_aux, s1, s2, *params):
+        sd = dict(module.named_parameters())
+        sd.update(dict(module.named_buffers()))
+        out, saved = engine.fusion_train_forward(sd, out_main, out_aux, module.act_dtype, module._packs, (s1, s2),
+                                                 amax=module._amax_buffer(out_main.device))
+        module._sat.publish()
+        ctx.module, ctx.saved_state = module, saved
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        module, sv = ctx.module, ctx.saved_state
+        if sv is None:
+            raise RuntimeError("FusionHead backward called twice (saved activations were released)")
+        sd = dict(module.named_parameters())
+        sd.update(dict(module.named_buffers()))
+        dmain, daux, grads = engine.fusion_backward(sd, sv, dout, module.act_dtype, module._packs, amax=module._amax_buffer(dout.device))
+        module._sat.publish()
+        ctx.saved_state = None
+        return (None, dmain, daux, None, None) + tuple(grads[n] for n, _ in module.named_parameters())
+
+
 class FusionHead(nn.Module):
     """The in-file fusion blocks of the reference's smp body (models.py:276-302, 320-328): attention gate,
     fusion head and residual 1x1 over ``cat([out_main, out_aux])``.  Same sub-module names / indices as the
     reference, so the ``attention_gate.*``, ``fusion_head.*`` and ``fusion_residual.*`` entries of a reference
     checkpoint load directly.  The two smp branches that feed it (UnetPlusPlus / DeepLabV3Plus) are third-party
-    code outside this repo's scope; this head runs standalone in EVAL mode (train mode draws Dropout2d masks from
-    torch's RNG stream and is not implemented)."""
+    code outside this repo's scope; this head runs standalone, forward and backward, in eval and in training mode.
+
+    Training mode: batch-statistics BatchNorm (running statistics updated), Dropout2d (models.py:290, 294) as
+    per-(sample, channel) factors keep / (1 - p).  ``forward(out_main, out_aux, dropout_scales=(s1 [B,256], s2 [B,128]))``
+    takes the draw from the caller (parity tests hand over the reference's own draw); without it the factors are drawn
+    with torch's device generator ([B, C] tensors - bookkeeping, not arithmetic of the path)."""
 
     def __init__(self, num_classes: int = 3, dtype: str = DEFAULT_DTYPE):
         super().__init__()
@@ -249,19 +279,33 @@ class FusionHead(nn.Module):
             nn.Conv2d(64, num_classes, kernel_size=1))
         self.fusion_residual = nn.Conv2d(num_classes * 2, num_classes, kernel_size=1)
         self._packs = engine.PackCache()
+        self._sat = _SaturationMonitor()
 
     def _apply(self, fn, *args, **kwargs):
         r = super()._apply(fn, *args, **kwargs)
         self._packs.clear()
         return r
 
-    def forward(self, out_main: torch.Tensor, out_aux: torch.Tensor) -> torch.Tensor:
-        if self.training:
-            raise NotImplementedError("FusionHead runs in eval mode only (Dropout2d RNG parity is out of scope)")
+    def _amax_buffer(self, device: torch.device) -> Optional[torch.Tensor]:
+        return self._sat.buffer(device) if self.act_dtype == torch.float16 else None
+
+    def check_numerics(self) -> None:
+        self._sat.check(block=True)
+
+    def forward(self, out_main: torch.Tensor, out_aux: torch.Tensor, dropout_scales=None) -> torch.Tensor:
         if not (out_main.is_cuda and out_aux.is_cuda):
             raise RuntimeError("FusionHead (B200) runs on CUDA tensors only; there is no CPU fallback")
         if out_main.shape != out_aux.shape or out_main.dim() != 4 or out_main.shape[1] != 3:
             raise RuntimeError(f"FusionHead expects two [B,3,H,W] tensors, got {tuple(out_main.shape)} / {tuple(out_aux.shape)}")
+        self._sat.check(block=False)
+        if self.training:
+            b, dev = out_main.shape[0], out_main.device
+            if dropout_scales is None:
+                dropout_scales = tuple(torch.bernoulli(torch.full((b, c), 1.0 - p, device=dev)) / (1.0 - p) for c, p in ((256, 0.2), (128, 0.15)))
+            s1, s2 = (s.to(dev, torch.float32).contiguous() for s in dropout_scales)
+            if s1.shape != (b, 256) or s2.shape != (b, 128):
+                raise RuntimeError(f"dropout_scales must be ([B,256], [B,128]), got {tuple(s1.shape)} / {tuple(s2.shape)}")
+            return _FusionFunction.apply(self, out_main, out_aux, s1, s2, *[p for _, p in self.named_parameters()])
         with torch.no_grad():
             sd = dict(self.named_parameters())
             sd.update(dict(self.named_buffers()))

@@ -222,6 +222,33 @@ int eunet_fusion_gate_fwd(const float* out_main, const float* out_aux, const flo
                           float* res4, int B, int H, int W, void* stream);
 int eunet_fusion_out_fwd(const float* z4, const float* res4, float* out, int B, int H, int W, void* stream);
 
+/* ---- the same blocks in TRAINING mode (batch-statistics BatchNorm, Dropout2d) and their backward (models.py:276-302,
+ * 320-328 under loss.backward()).  The head's 3x3 convolutions / BatchNorms / 1x1 use the generic entry points above; the
+ * attention gate has its own passes because each of its two BatchNorms needs whole-batch statistics before it applies:
+ *   gate_conv_fwd : a1 [M][4] fp32 = conv3x3(cat[main, aux]; w0); stats = {sum[3], sumsq[3]} (double, caller zeroes)
+ *   gate_mid_fwd  : a2 [M][8] fp32 = conv1x1(gelu(a1 * scale1 + shift1); w3); stats = {sum[6], sumsq[6]}
+ *   gate_apply_fwd: fg = cat[main, aux] * sigmoid(a2 * scale2 + shift2) -> fg16 (dtype, 16 channels), res4 = fusion_residual(fg)
+ *   gate_bwd      : gradient of all of it.  Inputs: dfg16 (gradient w.r.t. the gated features from the head's first
+ *                   convolution, dtype, first 6 of 16 channels) and dout4 (gradient of the block output, pixel-major fp32 x4:
+ *                   the residual path).  bn1 / bn2: {scale, shift, mean, invstd} of the two gate BatchNorms (device).
+ *                   acc (double[219], caller zeroes): [0,6) dbeta2, [6,12) dgamma2, [12,30) dWr[3][6], [30,33) dbr,
+ *                   [33,36) dbeta1, [36,39) dgamma1, [39,57) dW3[6][3], [57,219) dW0[3][6][3][3].
+ *                   dmain / daux: fp32 NCHW gradients w.r.t. the two inputs (times gscale[1] when gscale != NULL).
+ * `gate_w`: HOST pointer to 201 floats {w0[3][6][9], w3[6][3], wr[3][6], br[3]}.
+ * channel_scale: x[b, pixel, c] *= scale_bc[b][c] in place - Dropout2d with keep / (1 - p) factors, and its backward. */
+int eunet_fusion_gate_conv_fwd(const float* out_main, const float* out_aux, const float* gate_w, float* a1, double* stats, int B,
+                               int H, int W, void* stream);
+int eunet_fusion_gate_mid_fwd(const float* a1, const float* scale1, const float* shift1, const float* gate_w, float* a2,
+                              double* stats, long long M, void* stream);
+int eunet_fusion_gate_apply_fwd(const float* out_main, const float* out_aux, const float* a2, const float* scale2,
+                                const float* shift2, const float* gate_w, void* fg16, int dtype, float* res4, int B, int H, int W,
+                                void* stream);
+int eunet_fusion_gate_bwd(const float* out_main, const float* out_aux, const float* a1, const float* a2, const float* bn1,
+                          const float* bn2, const void* dfg16, int dtype, const float* dout4, const float* gate_w, float* dz1,
+                          float* dz2, double* acc, float* dmain, float* daux, const float* gscale, int B, int H, int W,
+                          void* stream);
+int eunet_channel_scale(void* x, int ld, const float* scale_bc, int dtype, int B, long long HW, int C, void* stream);
+
 /* ---- optimiser step (train_eval.py:120, 341-343): global-norm clip + AdamW over flat fp32 buffers ---- */
 int eunet_sumsq(const float* g, long long n, double* out /*scalar, accumulates; caller zeroes*/, void* stream);
 int eunet_adamw_step(float* p, const float* g, float* m, float* v, long long n, const double* gradsq /*scalar*/,

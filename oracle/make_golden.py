@@ -201,6 +201,58 @@ def fusion_case(ref_models):
     print("fusion ysum", y.sum().item())
 
 
+def fusion_train_case(ref_models):
+    """The same three blocks in TRAINING mode (batch-statistics BatchNorm, Dropout2d drawing from torch's global RNG) and
+    their autograd backward.  The per-(sample, channel) Dropout2d factors the reference drew are read back through forward
+    hooks, so that the oracle / the CUDA path can be handed the identical draw."""
+    import torch.nn as nn
+    nc, fc = 3, 6
+    gate = nn.Sequential(nn.Conv2d(fc, fc // 2, 3, padding=1, bias=False), nn.BatchNorm2d(fc // 2), nn.GELU(),
+                         nn.Conv2d(fc // 2, fc, 1, bias=False), nn.BatchNorm2d(fc), nn.Sigmoid())
+    head = nn.Sequential(nn.Conv2d(nc * 2, 256, 3, padding=1, bias=False), nn.BatchNorm2d(256), nn.ReLU(inplace=True),
+                         nn.Dropout2d(0.2), nn.Conv2d(256, 128, 3, padding=1, bias=False), nn.BatchNorm2d(128),
+                         nn.ReLU(inplace=True), nn.Dropout2d(0.15), nn.Conv2d(128, 64, 3, padding=1, bias=False),
+                         nn.BatchNorm2d(64), nn.ReLU(inplace=True), nn.Conv2d(64, nc, 1))
+    res = nn.Conv2d(nc * 2, nc, 1)
+    sd = make_fusion_state_dict(0)
+    gate.load_state_dict({k[len("attention_gate."):]: v for k, v in sd.items() if k.startswith("attention_gate.")})
+    head.load_state_dict({k[len("fusion_head."):]: v for k, v in sd.items() if k.startswith("fusion_head.")})
+    res.load_state_dict({k[len("fusion_residual."):]: v for k, v in sd.items() if k.startswith("fusion_residual.")})
+    gate.train(); head.train(); res.train()
+    scales = {}
+
+    def hook(name):
+        def fn(mod, inp, out):
+            x = inp[0].detach()
+            idx = x.abs().flatten(2).argmax(2, keepdim=True)             # a non-zero element of every (b, c) plane
+            xi, oi = x.flatten(2).gather(2, idx), out.detach().flatten(2).gather(2, idx)
+            scales[name] = torch.where(xi != 0, oi / xi, torch.zeros_like(xi)).squeeze(2)
+        return fn
+
+    head[3].register_forward_hook(hook("s1"))
+    head[7].register_forward_hook(hook("s2"))
+    g = torch.Generator().manual_seed(21)
+    a = torch.randn(2, 3, 32, 40, generator=g).requires_grad_(True)
+    b = torch.randn(2, 3, 32, 40, generator=g).requires_grad_(True)
+    dout = torch.randn(2, 3, 32, 40, generator=g)
+    torch.manual_seed(5)
+    f = torch.cat([a, b], 1)
+    f = f * gate(f)
+    y = head(f) + res(f)
+    (y * dout).sum().backward()
+    out = dict(main=a.detach().numpy(), aux=b.detach().numpy(), dout=dout.numpy(), out=y.detach().numpy(),
+               dmain=a.grad.numpy(), daux=b.grad.numpy(), s1=scales["s1"].numpy(), s2=scales["s2"].numpy())
+    for prefix, mod in (("attention_gate", gate), ("fusion_head", head), ("fusion_residual", res)):
+        for n, p in mod.named_parameters():
+            out[f"grad/{prefix}.{n}"] = p.grad.numpy()
+        for n, bf in mod.named_buffers():
+            out[f"buf/{prefix}.{n}"] = bf.numpy()
+    for key, keep in (("s1", 1 / 0.8), ("s2", 1 / 0.85)):
+        assert np.all(np.isclose(out[key], 0.0) | np.isclose(out[key], keep, rtol=1e-5)), key
+    np.savez_compressed(os.path.join(OUT, "fusion_train.npz"), **out)
+    print("fusion_train ysum", y.sum().item(), "kept", float((out["s1"] > 0).mean()), float((out["s2"] > 0).mean()))
+
+
 def instances_case(ref_metrics):
     """metrics.calculate_instance_metrics (metrics.py:61-194) on seeded synthetic instance sets."""
     from .metrics_oracle import INSTANCE_CASES, make_instance_case
@@ -255,6 +307,8 @@ def main():
         mask_case(ref_te, ref_models)
     if want("fusion"):
         fusion_case(ref_models)
+    if want("fusion_train"):
+        fusion_train_case(ref_models)
     if want("instances"):
         instances_case(ref_metrics)
     if want("tta"):

@@ -255,10 +255,22 @@ def make_fusion_state_dict(seed: int = 0) -> Dict[str, torch.Tensor]:
     return sd
 
 
-def fusion_forward(sd: Dict[str, torch.Tensor], out_main: torch.Tensor, out_aux: torch.Tensor) -> torch.Tensor:
-    """models.py:320-328 in eval mode: cat -> attention gate -> multiply -> fusion head + residual."""
+def fusion_forward(sd: Dict[str, torch.Tensor], out_main: torch.Tensor, out_aux: torch.Tensor, train: bool = False,
+                   dropout_scales=None):
+    """models.py:320-328: cat -> attention gate -> multiply -> fusion head + residual.
+
+    Eval mode (default): BatchNorm on running statistics, Dropout2d is the identity; returns the output tensor.
+    ``train=True``: batch statistics (running statistics / num_batches_tracked updated as nn.BatchNorm2d does) and
+    Dropout2d (models.py:290, 294) applied as a per-(sample, channel) factor ``dropout_scales = (s1 [B,256], s2 [B,128])``
+    with entries ``keep / (1 - p)`` - the draw is the caller's (the reference takes it from torch's global RNG); returns
+    ``(output, new_buffers)``."""
+    nb: Dict[str, torch.Tensor] = {}
+
     def bn(x, p):
-        return F.batch_norm(x, sd[f"{p}.running_mean"], sd[f"{p}.running_var"], sd[f"{p}.weight"], sd[f"{p}.bias"], False, 0.1, 1e-5)
+        if not train:
+            return F.batch_norm(x, sd[f"{p}.running_mean"], sd[f"{p}.running_var"], sd[f"{p}.weight"], sd[f"{p}.bias"], False, 0.1, 1e-5)
+        return _bn(x, sd, p, True, nb)
+
     f = torch.cat([out_main, out_aux], dim=1)
     a = F.conv2d(f, sd["attention_gate.0.weight"], None, padding=1)
     a = F.gelu(bn(a, "attention_gate.1"))
@@ -266,7 +278,12 @@ def fusion_forward(sd: Dict[str, torch.Tensor], out_main: torch.Tensor, out_aux:
     a = torch.sigmoid(bn(a, "attention_gate.4"))
     f = f * a
     h = F.relu(bn(F.conv2d(f, sd["fusion_head.0.weight"], None, padding=1), "fusion_head.1"))
+    if train:
+        h = h * dropout_scales[0][:, :, None, None]
     h = F.relu(bn(F.conv2d(h, sd["fusion_head.4.weight"], None, padding=1), "fusion_head.5"))
+    if train:
+        h = h * dropout_scales[1][:, :, None, None]
     h = F.relu(bn(F.conv2d(h, sd["fusion_head.8.weight"], None, padding=1), "fusion_head.9"))
     h = F.conv2d(h, sd["fusion_head.11.weight"], sd["fusion_head.11.bias"])
-    return h + F.conv2d(f, sd["fusion_residual.weight"], sd["fusion_residual.bias"])
+    y = h + F.conv2d(f, sd["fusion_residual.weight"], sd["fusion_residual.bias"])
+    return (y, nb) if train else y

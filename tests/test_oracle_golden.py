@@ -103,6 +103,27 @@ def test_fusion_blocks_match_reference_fixture(golden_dir):
     np.testing.assert_allclose(y.numpy(), g["out"], rtol=0, atol=2e-5)
 
 
+def test_fusion_blocks_training_match_reference_fixture(golden_dir):
+    """Training mode of the fusion blocks (batch-statistics BN, the reference's own Dropout2d draw read back through hooks):
+    output, input gradients, every parameter gradient and the updated BN buffers."""
+    g = _load(golden_dir, "fusion_train.npz")
+    sd = make_fusion_state_dict(0)
+    params = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
+    a = torch.from_numpy(g["main"]).requires_grad_(True)
+    b = torch.from_numpy(g["aux"]).requires_grad_(True)
+    y, nb = oracle.fusion_forward(params, a, b, train=True, dropout_scales=(torch.from_numpy(g["s1"]), torch.from_numpy(g["s2"])))
+    np.testing.assert_allclose(y.detach().numpy(), g["out"], rtol=0, atol=2e-5)
+    (y * torch.from_numpy(g["dout"])).sum().backward()
+    np.testing.assert_allclose(a.grad.numpy(), g["dmain"], rtol=0, atol=2e-5 * np.abs(g["dmain"]).max())
+    np.testing.assert_allclose(b.grad.numpy(), g["daux"], rtol=0, atol=2e-5 * np.abs(g["daux"]).max())
+    for k in g.files:
+        if k.startswith("grad/"):
+            got = params[k[5:]].grad.numpy()
+            np.testing.assert_allclose(got, g[k], rtol=0, atol=1e-4 * max(1e-12, np.abs(g[k]).max()), err_msg=k)
+        elif k.startswith("buf/"):
+            np.testing.assert_allclose(nb[k[4:]].numpy(), g[k], rtol=0, atol=1e-5 * max(1.0, np.abs(g[k]).max()), err_msg=k)
+
+
 def test_resize_identity_kat3():
     # SURVEY.md KAT-3: bilinear 2x-down with align_corners=False == 2x2 mean
     x = torch.randn(2, 3, 16, 24)
