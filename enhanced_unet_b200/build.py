@@ -18,7 +18,7 @@ BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libeunet_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["core.cu", "metrics.cu", "elementwise.cu", "loss.cu", "tail.cu", "optim.cu", "conv_direct.cu", "conv_tc.cu", "conv_halo.cu", "conv_wgrad_halo.cu", "conv_dgrad_few.cu", "conv_tail_bwd.cu", "tail_out_tma.cu", "bn_apply_tma.cu",
+SOURCES = ["core.cu", "metrics.cu", "elementwise.cu", "loss.cu", "tail.cu", "optim.cu", "conv_direct.cu", "conv_tc.cu", "conv_halo.cu", "conv_halo2.cu", "conv_wgrad_halo.cu", "conv_dgrad_few.cu", "conv_tail_bwd.cu", "tail_out_tma.cu", "bn_apply_tma.cu",
            "mask.cu", "fusion.cu", "probe.cu"]
 
 NVCC_FLAGS = [

@@ -16,6 +16,10 @@ int conv3x3_fwd_halo_bf16(const void* x, int ldx, const void* w, void* y, int ld
                           cudaStream_t st);
 int conv3x3_wgrad_halo_bf16(const void* x, int ldx, const void* dy, int lddy, float* dw, int B, int H, int W, int Cin, int Cout,
                             int f16, cudaStream_t st);
+// CTA-pair (cta_group::2) halo kernel for the N <= 128 layers (conv_halo2.cu): same return convention
+int conv3x3_fwd_halo2(const void* x, int ldx, const void* w, void* y, int ldy, int B, int H, int W, int Cin, int Cout, double* stats,
+                      const float* scale, const float* shift, int relu, int out_raw, int f16, float* amax, cudaStream_t st);
+extern int g_opt_cta_pair;    // 0 (default): never; 1: N = 128 tiles; 2: N = 128 and N = 64 tiles
 extern int g_opt_conv_halo;   // 1 (default): use the halo kernel where it applies
 extern int g_opt_tma_store;   // 1 (default): Cout = 64 halo kernels write their output tile with a TMA tensor store
 

@@ -22,6 +22,7 @@
 namespace eunet {
 
 int g_opt_conv_halo = 1;
+int g_opt_cta_pair = 0;   // measured slower than the single-CTA kernels (see conv_halo2.cu): kept as an option
 int g_opt_tma_store = 1;
 extern int g_opt_tail_out_tma;   // tail.cu: 1 (default) = TMA-pipelined tail_out_fwd
 extern int g_opt_bn_tma;         // elementwise.cu: 1 (default) = TMA-pipelined bn_apply_relu
@@ -404,6 +405,10 @@ static int conv3x3_fwd_bf16(const void* x, int ldx, const void* w, void* y, int 
   EUNET_REQUIRE(Cin % 16 == 0 && Cout % 16 == 0, "conv3x3_fwd(bf16): Cin=%d and Cout=%d must be multiples of 16", Cin, Cout);
   EUNET_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && ldx >= Cin && ldy >= Cout, "conv3x3_fwd(bf16): bad ld (%d, %d)", ldx, ldy);
   EUNET_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0, "conv3x3_fwd(bf16): y not 16-byte aligned");
+  if (g_opt_conv_halo && g_opt_cta_pair && Cout % 256 != 0 && (Cout % 128 == 0 || (g_opt_cta_pair >= 2 && Cout % 64 == 0))) {
+    const int rc = conv3x3_fwd_halo2(x, ldx, w, y, ldy, B, H, W, Cin, Cout, stats, scale, shift, relu, out_raw, f16, amax, st);
+    if (rc <= 0) return rc;
+  }
   if (g_opt_conv_halo) {
     const int rc = conv3x3_fwd_halo_bf16(x, ldx, w, y, ldy, B, H, W, Cin, Cout, stats, scale, shift, relu, out_raw, f16, amax, st);
     if (rc <= 0) return rc;   // launched (0) or failed (< 0); 1 = not covered, fall through to the per-tap kernel
@@ -505,6 +510,10 @@ using namespace eunet;
 extern "C" int eunet_set_option(const char* name, int value) {
   if (strcmp(name, "conv_halo") == 0) {
     g_opt_conv_halo = value;
+    return 0;
+  }
+  if (strcmp(name, "cta_pair") == 0) {
+    g_opt_cta_pair = value;
     return 0;
   }
   if (strcmp(name, "bn_tma") == 0) {

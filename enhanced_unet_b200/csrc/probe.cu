@@ -131,3 +131,33 @@ extern "C" int eunet_probe_umma(const void* a, int a_rows, int a_cols, int a_box
   probe_kernel<<<1, 128, smem_bytes + 1024, (cudaStream_t)stream>>>(ma, mb, mx, p, out_tmem, (uint8_t*)out_smem);
   return check_launch("probe_kernel");
 }
+
+// ---- cluster-launch probe: a CTA pair launched exactly as conv_halo2.cu launches its kernel ----
+namespace eunet {
+__global__ void __launch_bounds__(320, 1) probe_cluster_kernel(int* out) {
+  extern __shared__ uint8_t sm[];
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  if (threadIdx.x == 0) out[blockIdx.y] = (int)r + (sm[0] & 0);
+}
+}  // namespace eunet
+
+extern "C" int eunet_probe_cluster(int* out, int ctas, int smem_bytes, void* stream) {
+  using namespace eunet;
+  EUNET_REQUIRE(ctas >= 2 && ctas % 2 == 0 && ctas <= 256, "probe_cluster: bad CTA count");
+  cudaError_t e = cudaFuncSetAttribute(probe_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  EUNET_REQUIRE(e == cudaSuccess, "probe_cluster: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(1, (unsigned)ctas);
+  cfg.blockDim = dim3(320);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 2; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, probe_cluster_kernel, out);
+  EUNET_REQUIRE(e == cudaSuccess, "probe_cluster: launch: %s", cudaGetErrorString(e));
+  return check_launch("probe_cluster");
+}

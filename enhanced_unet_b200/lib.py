@@ -77,6 +77,7 @@ SIGNATURES = {
     "eunet_adamw_multi": [_p, _p, _p, _p, _p, _i, _p, _f, _f, _f, _f, _f, _f, _i, _f, _p, _p],
     "eunet_adamw_prepare": [_p, _p, _f, _f, _p, _p],
     "eunet_adamw_step": [_p, _p, _p, _p, _ll, _p, _f, _f, _f, _f, _f, _f, _i, _f, _p],
+    "eunet_probe_cluster": [_p, _i, _i, _p],
     "eunet_probe_umma": [_p, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p, _p, _i, _p],
 }
 

@@ -44,6 +44,8 @@ int eunet_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* smem_
 /* tuning / A-B switches for benchmarking and tests (process-global; defaults are the product path):
  *   "conv_halo"    1 (default) = halo-tile persistent conv kernels where they apply; 0 = always the per-tap kernels;
  *                  2 = halo kernels for every shape they cover (tests); 5 = per-tap wgrad without row-halo X boxes
+ *   "cta_pair"     0 (default) = off; 1 = CTA-pair (cta_group::2, M = 256) halo kernel for the N = 128 conv tiles; 2 = also N = 64
+ *                  (correct, but measured 1.6x slower than the single-CTA kernels on B200 - csrc/conv_halo2.cu)
  *   "tma_store"    1 (default) = Cout = 64 halo kernels write their tile with a TMA tensor store; 0 = per-thread stores
  *   "tail_out_tma" 1 (default) = TMA-pipelined tail_out_fwd / tail_bwd_reduce / tail_dec1_*; 0 = the cp.async-ring kernels
  *   "bn_tma"       1 (default) = TMA load -> transform -> TMA store bn_apply_relu; 0 = the cp.async-ring kernel */
@@ -272,6 +274,9 @@ int eunet_probe_umma(const void* a, int a_rows, int a_cols, int a_box_rows, int 
                      int b_rows, int b_cols, int b_box_rows, int b_box_cols, int b_swizzle, const void* x, const int* x_dims,
                      const int* x_box, int x_swizzle, const void* params_blob, int params_bytes, float* out_tmem,
                      void* out_smem, int smem_bytes, void* stream);
+
+/* cluster-launch probe: `ctas` CTAs in pairs (cluster 1 x 2 x 1), out[i] = rank of CTA i inside its pair */
+int eunet_probe_cluster(int* out, int ctas, int smem_bytes, void* stream);
 
 #ifdef __cplusplus
 }

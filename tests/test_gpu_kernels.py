@@ -293,6 +293,43 @@ def test_conv3x3_dgrad_and_wgrad(k, dtn, case):
 
 
 @pytest.mark.parametrize("dtn", ["bf16", "fp16"])
+@pytest.mark.parametrize("case", [(1, 8, 24, 128, 128), (2, 48, 40, 192, 64), (1, 64, 64, 128, 128), (2, 32, 32, 64, 384), (4, 128, 128, 64, 64),
+                                  (1, 40, 24, 64, 64)])
+def test_conv3x3_cta_pair_kernel(k, dtn, case):
+    """The CTA-pair (tcgen05 cta_group::2, M = 256 across two SMs) halo kernel of csrc/conv_halo2.cu - an option, off by
+    default - against F.conv2d on the rounded operands: raw output + batch statistics, and the affine + ReLU epilogue.
+    Odd item counts (the last pair holds one valid item), ragged tiles, several N tiles."""
+    B, H, W, Cin, Cout = case
+    dt = DT[dtn]
+    g = torch.Generator().manual_seed(hash(case) % 1000 + 7)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)
+    want = _conv_ref(rnd(dtn, x), rnd(dtn, w))
+    xd = nhwc(x, dt, ld=Cin + 16, off=16)
+    wp = torch.empty(Cout, 9, Cin, dtype=dt, device="cuda")
+    k.call("eunet_pack_weight3x3", w.cuda().data_ptr(), wp.data_ptr(), k.dtype_code(dt), Cout, Cin, Cout, Cin, 0)
+    M = B * H * W
+    y = torch.empty(M, Cout, dtype=k.raw_dtype(dt), device="cuda")
+    y2 = torch.empty(M, Cout, dtype=dt, device="cuda")
+    stats = torch.zeros(2 * Cout, dtype=torch.float64, device="cuda")
+    sc, sh = (torch.rand(Cout, generator=g) + 0.5).cuda(), torch.randn(Cout, generator=g).cuda()
+    k.set_option("cta_pair", 2)
+    try:
+        k.call("eunet_conv3x3_fwd", xd.data_ptr(), xd.stride(0), wp.data_ptr(), y.data_ptr(), Cout, k.dtype_code(dt), B, H, W, Cin, Cout,
+               stats.data_ptr(), None, None, 0, 1, None)
+        k.call("eunet_conv3x3_fwd", xd.data_ptr(), xd.stride(0), wp.data_ptr(), y2.data_ptr(), Cout, k.dtype_code(dt), B, H, W, Cin, Cout,
+               None, sc.data_ptr(), sh.data_ptr(), 1, 0, None)
+        torch.cuda.synchronize()
+    finally:
+        k.set_option("cta_pair", 0)
+    assert nerr(nchw(y, B, H, W), want) < 1e-3
+    s = stats.cpu()
+    assert nerr(s[:Cout], want.double().sum((0, 2, 3))) < 1e-4 and nerr(s[Cout:], (want.double() ** 2).sum((0, 2, 3))) < 1e-4
+    want2 = F.relu(want * sc.cpu()[None, :, None, None] + sh.cpu()[None, :, None, None])
+    assert nerr(nchw(y2, B, H, W), want2) < TOL[dtn]
+
+
+@pytest.mark.parametrize("dtn", ["bf16", "fp16"])
 @pytest.mark.parametrize("shape", [(2, 16, 24), (1, 40, 20), (3, 8, 8), (2, 128, 136), (1, 250, 64)])
 def test_conv3x3_dgrad_few_channels(k, shape, dtn):
     """Transposed tcgen05 dgrad for a conv with 3 real input channels (enhance.0): fp32 [pixels][4] output against
