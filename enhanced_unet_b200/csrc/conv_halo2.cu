@@ -67,8 +67,8 @@ struct Halo2Cfg {
   static constexpr int B_BYTES = BH * ROWB;
   static constexpr int NACC = (2 * MT * BN <= 512) ? 2 : 1;
   static constexpr int TMEM_COLS = NACC * MT * BN <= 128 ? 128 : NACC * MT * BN <= 256 ? 256 : 512;
-  static constexpr int ASTAGES = MT >= 4 ? 2 : 3;
-  static constexpr int BSTAGES = 8;
+  static constexpr int ASTAGES = 2;
+  static constexpr int BSTAGES = BN == 128 ? 16 : 12;      // deep filter ring: every refill is a cross-SM round trip
   static constexpr int NCHUNK = BN / 32;
   static constexpr int SMEM = 1024 + ASTAGES * A_SLOT + BSTAGES * B_BYTES;
   static_assert(BN == 64 || BN == 128, "CTA-pair kernel: N tiles of 64 or 128");
