@@ -280,6 +280,7 @@ class FusionHead(nn.Module):
         self.fusion_residual = nn.Conv2d(num_classes * 2, num_classes, kernel_size=1)
         self._packs = engine.PackCache()
         self._sat = _SaturationMonitor()
+        self._blob_cache: dict = {}
 
     def _apply(self, fn, *args, **kwargs):
         r = super()._apply(fn, *args, **kwargs)
@@ -309,4 +310,4 @@ class FusionHead(nn.Module):
         with torch.no_grad():
             sd = dict(self.named_parameters())
             sd.update(dict(self.named_buffers()))
-            return engine.fusion_forward(sd, out_main, out_aux, self.act_dtype, self._packs)
+            return engine.fusion_forward(sd, out_main, out_aux, self.act_dtype, self._packs, blob_cache=self._blob_cache)
