@@ -39,7 +39,9 @@ struct TailBwdParams {
   int B, H, W;
   int blocks_x, blocks_y, items;
   uint32_t fmt16;     // operand format (d1p16, flipped filters, the dmid tile formed on chip): 1 = bf16, 0 = fp16
+  int dbg;            // timing experiments only (option "tail_dbg"): 1 skip transform, 2 skip wgrad MMAs, 4 skip U^T MMAs, 8 skip drain
 };
+int g_opt_tail_dbg = 0;
 
 constexpr int kTbStages = 4;
 constexpr int kTbMid = 184 * 128;            // 23552: mid / dmid halo tile slot (180 rows used)
@@ -116,16 +118,12 @@ tail_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmMid, const __grid_co
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
         const uint32_t s = it % kTbStages;
         tc::mbar_wait(tc::smem_u32(&xf_full[s]), (it / kTbStages) & 1u);
-        tc::mbar_wait(tc::smem_u32(&acc_empty), (it & 1u) ^ 1u);
         tc::tc_fence_after();
         const uint32_t t_addr = a_base + s * kTbStage, x_addr = t_addr + kTbMid + kTbDout;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint64_t adesc = tc::make_smem_desc(w_base + j * 32, 16, 1024, tc::kSwizzle128);
-          const uint64_t bdesc = tc::make_smem_desc(t_addr + j * 32, 16, 1024, tc::kSwizzle128);
-          tc::umma_bf16(tmem_base, adesc, bdesc, idesc_u, j != 0 ? 1u : 0u);
-        }
-        tc::umma_commit(tc::smem_u32(&acc_full));
+        // the 24 wgrad MMAs first: they accumulate into their own TMEM columns and do not depend on the drain warps, so they
+        // run while U^T of the previous tile is still being copied out (the single-buffered U^T used to serialise the MMA
+        // and drain stages: ~3000 clk per tile against ~950 clk of MMA work)
+        if (!(p.dbg & 2))
 #pragma unroll
         for (int j = 0; j < 8; ++j) {      // K = 16 pixels = image rows 2j, 2j+1 of the tile = halo rows 2j+1, 2j+2 (columns 1..8)
           const uint64_t adesc = tc::make_smem_desc(t_addr + (uint32_t)(((2 * j + 1) * 10 + 1) * 128), 0, 10 * 128, tc::kSwizzle128);
@@ -135,6 +133,16 @@ tail_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmMid, const __grid_co
             tc::umma_bf16(tmem_base + kTbWgCol + dy * 48, adesc, bdesc, idesc_w, (it | j) != 0 ? 1u : 0u);
           }
         }
+        tc::mbar_wait(tc::smem_u32(&acc_empty), (it & 1u) ^ 1u);
+        tc::tc_fence_after();
+        if (!(p.dbg & 4))
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint64_t adesc = tc::make_smem_desc(w_base + j * 32, 16, 1024, tc::kSwizzle128);
+          const uint64_t bdesc = tc::make_smem_desc(t_addr + j * 32, 16, 1024, tc::kSwizzle128);
+          tc::umma_bf16(tmem_base, adesc, bdesc, idesc_u, j != 0 ? 1u : 0u);
+        }
+        tc::umma_commit(tc::smem_u32(&acc_full));
         tc::umma_commit(tc::smem_u32(&st_empty[s]));
       }
       tc::umma_commit(tc::smem_u32(&fin_bar));
@@ -155,6 +163,12 @@ tail_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmMid, const __grid_co
       float* S = s_gen + (it & 1u) * (kTbSBytes / 4);
       tc::mbar_wait(tc::smem_u32(&acc_full), it & 1u);
       tc::tc_fence_after();
+      if (p.dbg & 8) {
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty));
+        continue;
+      }
 #pragma unroll 1
       for (int c = 0; c < 3; ++c) {
         const int col0 = e * 96 + c * 32;
@@ -212,44 +226,61 @@ tail_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmMid, const __grid_co
         ws[2][e] = w2.v[e] * a.v[e];
       }
     }
+    // this thread's four halo rows (r0 + 48 k; the last one exists only for r0 < 36) and their shared-memory offsets are
+    // fixed for the whole kernel.  The loop body is BRANCH-FREE: rows outside the image were zero-filled by TMA and are
+    // zeroed again by a select, so that the compiler can issue the loads of all rows up front (twelve warps per SM have
+    // to hide the shared-memory latency themselves: with a bounds-check branch per row this stage ran at 2400 clk per tile
+    // against ~900 clk of issue slots and bounded the kernel)
+    int ry[4], rx[4];
+    uint32_t off[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = r0 + 48 * k;
+      ry[k] = r / 10;
+      rx[k] = r - ry[k] * 10;
+      off[k] = (uint32_t)(r * 128) + ((uint32_t)(j ^ (r & 7)) << 4);
+    }
+    const bool last_ok = r0 + 144 < 180;
+    auto row = [&](uint32_t t_addr, uint32_t d_addr, int k, int gy0, int gx0) {
+      const int r = r0 + 48 * k;
+      const int gy = gy0 + ry[k], gx = gx0 + rx[k];
+      const bool inb = (unsigned)gy < (unsigned)p.H && (unsigned)gx < (unsigned)p.W;
+      uint32_t h0, h1, h2, h3;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(h0), "=r"(h1), "=r"(h2), "=r"(h3) : "r"(t_addr + off[k]));
+      float g0, g1, g2, gpad;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(g0), "=f"(g1), "=f"(g2), "=f"(gpad) : "r"(d_addr + (uint32_t)(r * 16)));
+      const uint32_t hw[4] = {h0, h1, h2, h3};
+      float o[8];
+#pragma unroll
+      for (int e2 = 0; e2 < 4; ++e2) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[e2]));
+        const float v[2] = {f.x, f.y};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int e = 2 * e2 + h;
+          float rr = fmaf(Bc[e], v[h], A[e]);
+          if (fmaf(v[h], sc[e], sh[e]) > 0.f) rr = fmaf(g2, ws[2][e], fmaf(g1, ws[1][e], fmaf(g0, ws[0][e], rr)));
+          o[e] = rr;
+        }
+      }
+      uint32_t u0, u1, u2, u3;
+      if (p.fmt16) { u0 = pack_bf16x2(o[0], o[1]); u1 = pack_bf16x2(o[2], o[3]); u2 = pack_bf16x2(o[4], o[5]); u3 = pack_bf16x2(o[6], o[7]); }
+      else { u0 = tc::cvt_f16x2_sat(o[0], o[1]); u1 = tc::cvt_f16x2_sat(o[2], o[3]); u2 = tc::cvt_f16x2_sat(o[4], o[5]); u3 = tc::cvt_f16x2_sat(o[6], o[7]); }
+      if (!inb) u0 = u1 = u2 = u3 = 0u;          // the transposed convolution's boundary condition
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(t_addr + off[k]), "r"(u0), "r"(u1), "r"(u2), "r"(u3) : "memory");
+    };
     uint32_t it = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
       const int bx = item % p.blocks_x, by = (item / p.blocks_x) % p.blocks_y;
       const uint32_t s = it % kTbStages;
       const uint32_t t_addr = a_base + s * kTbStage, d_addr = t_addr + kTbMid;
       tc::mbar_wait(tc::smem_u32(&tma_full[s]), (it / kTbStages) & 1u);
-#pragma unroll 2
-      for (int k = 0; k < 4; ++k) {
-        const int r = r0 + 48 * k;
-        if (r < 180) {
-          const int ry = r / 10, rx = r - ry * 10;
-          const int gy = by * 16 - 1 + ry, gx = bx * 8 - 1 + rx;
-          const uint32_t addr = t_addr + (uint32_t)(r * 128) + ((uint32_t)(j ^ (r & 7)) << 4);
-          uint32_t u0 = 0u, u1 = 0u, u2 = 0u, u3 = 0u;
-          if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
-            uint32_t h0, h1, h2, h3;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(h0), "=r"(h1), "=r"(h2), "=r"(h3) : "r"(addr));
-            float g0, g1, g2, gpad;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(g0), "=f"(g1), "=f"(g2), "=f"(gpad) : "r"(d_addr + (uint32_t)(r * 16)));
-            const uint32_t hw[4] = {h0, h1, h2, h3};
-            float o[8];
-#pragma unroll
-            for (int e2 = 0; e2 < 4; ++e2) {
-              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[e2]));
-              const float v[2] = {f.x, f.y};
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const int e = 2 * e2 + h;
-                float rr = fmaf(Bc[e], v[h], A[e]);
-                if (fmaf(v[h], sc[e], sh[e]) > 0.f) rr = fmaf(g2, ws[2][e], fmaf(g1, ws[1][e], fmaf(g0, ws[0][e], rr)));
-                o[e] = rr;
-              }
-            }
-            if (p.fmt16) { u0 = pack_bf16x2(o[0], o[1]); u1 = pack_bf16x2(o[2], o[3]); u2 = pack_bf16x2(o[4], o[5]); u3 = pack_bf16x2(o[6], o[7]); }
-            else { u0 = tc::cvt_f16x2_sat(o[0], o[1]); u1 = tc::cvt_f16x2_sat(o[2], o[3]); u2 = tc::cvt_f16x2_sat(o[4], o[5]); u3 = tc::cvt_f16x2_sat(o[6], o[7]); }
-          }
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u0), "r"(u1), "r"(u2), "r"(u3) : "memory");
-        }
+      if (!(p.dbg & 1)) {
+        const int gy0 = by * 16 - 1, gx0 = bx * 8 - 1;
+        row(t_addr, d_addr, 0, gy0, gx0);
+        row(t_addr, d_addr, 1, gy0, gx0);
+        row(t_addr, d_addr, 2, gy0, gx0);
+        if (last_ok) row(t_addr, d_addr, 3, gy0, gx0);
       }
       tc::fence_proxy_async_smem();       // generic-proxy writes -> visible to the tensor core's async-proxy reads
       __syncwarp();
@@ -292,6 +323,7 @@ extern "C" int eunet_tail_bwd_fused(const float* dout4, const void* mid_raw, con
   EUNET_REQUIRE(dtype == EUNET_BF16 || dtype == EUNET_F16, "tail_bwd_fused: tensor-core path only (dtype %d)", dtype);
   TailBwdParams p;
   p.fmt16 = dtype == EUNET_F16 ? 0u : 1u;
+  p.dbg = g_opt_tail_dbg;
   p.dx4 = dx4; p.dw = dw_packed; p.scale = scale; p.shift = shift; p.mean = mean; p.invstd = invstd; p.w3 = w3; p.acc = acc;
   p.B = B; p.H = H2; p.W = W2;
   p.blocks_x = (W2 + 7) / 8;

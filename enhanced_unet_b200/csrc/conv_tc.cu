@@ -24,6 +24,7 @@ namespace eunet {
 int g_opt_conv_halo = 1;
 int g_opt_cta_pair = 0;   // measured slower than the single-CTA kernels (see conv_halo2.cu): kept as an option
 int g_opt_tma_store = 1;
+extern int g_opt_tail_dbg;       // conv_tail_bwd.cu: timing experiments only
 extern int g_opt_tail_out_tma;   // tail.cu: 1 (default) = TMA-pipelined tail_out_fwd
 extern int g_opt_bn_tma;         // elementwise.cu: 1 (default) = TMA-pipelined bn_apply_relu
 
@@ -510,6 +511,10 @@ using namespace eunet;
 extern "C" int eunet_set_option(const char* name, int value) {
   if (strcmp(name, "conv_halo") == 0) {
     g_opt_conv_halo = value;
+    return 0;
+  }
+  if (strcmp(name, "tail_dbg") == 0) {
+    g_opt_tail_dbg = value;
     return 0;
   }
   if (strcmp(name, "cta_pair") == 0) {
