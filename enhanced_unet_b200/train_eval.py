@@ -4,9 +4,11 @@ same names, constructor arguments, batch format and hyper-parameters.  Everythin
 the numbers is the C-ABI kernels: model forward/backward, fused loss, clip+AdamW, softmax/resize, the
 probability->mask cascade and the confusion counts.
 
-Out of scope: cv2 CLAHE pre-processing, the 0.75x/1.25x TTA views,
-instance splitting (skimage), COCO evaluation, plotting and the real-data ``CellDataset``; the drivers
-therefore accept any iterable of reference-format batches and ship a synthetic generator.
+Out of scope: instance splitting (skimage), COCO evaluation, plotting and the
+real-data ``CellDataset``; the drivers therefore accept any iterable of reference-format batches and ship a synthetic
+generator.  The reference's per-image cv2 pre-processing in front of ``predict_semantic_mask`` (CLAHE + sharpening,
+train_eval.py:365-395) is host-side image I/O, not arithmetic of the path: ``Evaluator._prepare_image_tensor`` makes the
+same cv2 calls so that the entry point behaves like the reference's; everything after it runs on the GPU kernels.
 """
 from __future__ import annotations
 
@@ -155,6 +157,24 @@ class Evaluator:
     def tta(self, value: bool) -> None:
         self.enable_tta = bool(value)
 
+    def _prepare_image_tensor(self, image: torch.Tensor) -> torch.Tensor:
+        """Reference train_eval.py:365-395 (host-side, cv2): [3,h,w] in [0,1] (or 0..255) -> uint8 RGB -> CLAHE(2.0, 8x8) on
+        the L channel of LAB -> 3x3 sharpening (0.15 * [[-1,-1,-1],[-1,9,-1],[-1,-1,-1]]) -> float [0,1] on the device."""
+        try:
+            import cv2
+        except ImportError as e:      # loud: the reference cannot run without cv2 either
+            raise RuntimeError("Evaluator._prepare_image_tensor needs OpenCV (cv2), as the reference does") from e
+        host = image.detach().float().cpu()
+        rgb = host.permute(1, 2, 0).numpy()
+        rgb = (rgb * 255).astype(np.uint8) if float(host.max()) <= 1.0 else rgb.astype(np.uint8)
+        lab = cv2.cvtColor(rgb, cv2.COLOR_RGB2LAB)
+        lum, a_ch, b_ch = cv2.split(lab)
+        lum = cv2.createCLAHE(clipLimit=2.0, tileGridSize=(8, 8)).apply(lum)
+        rgb = cv2.cvtColor(cv2.merge([lum, a_ch, b_ch]), cv2.COLOR_LAB2RGB)
+        sharpen = np.array([[-1, -1, -1], [-1, 9, -1], [-1, -1, -1]]) * 0.15
+        rgb = np.clip(cv2.filter2D(rgb, -1, sharpen), 0, 255).astype(np.uint8)
+        return torch.from_numpy(rgb.astype(np.float32) / 255.0).permute(2, 0, 1).to(self.device)
+
     @torch.no_grad()
     def _run_model_batch(self, images: torch.Tensor) -> torch.Tensor:
         """[B,3,h,w] -> probabilities [B,3,h,w] (pad to /32, model, bilinear resize == 2x2 mean, softmax; 397-417)."""
@@ -242,10 +262,13 @@ class Evaluator:
             m = m[:h_orig, :w_orig]
         return m.cpu().numpy().astype(np.int64)
 
-    def predict_semantic_mask(self, image: torch.Tensor) -> np.ndarray:
-        """[3,H,W] -> int64 [H,W] (reference 570-652).  CUDA errors propagate: the reference's silent retry on
-        the CPU (576-592) is deliberately not reproduced."""
+    def predict_semantic_mask(self, image: torch.Tensor, preprocess: bool = True) -> np.ndarray:
+        """[3,H,W] -> int64 [H,W] (reference 570-652: cv2 pre-processing -> TTA probabilities -> mask cascade).  CUDA errors
+        propagate: the reference's silent retry on the CPU (576-592) is deliberately not reproduced.  ``preprocess=False``
+        skips the host-side cv2 step (tensors that were pre-processed by the loader already)."""
         self.model.eval()
+        if preprocess:
+            image = self._prepare_image_tensor(image)
         probs = self._probs(image.unsqueeze(0))
         return self._convert_probs_to_mask_device(probs)[0].cpu().numpy().astype(np.int64)
 

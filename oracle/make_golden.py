@@ -285,6 +285,22 @@ def tta_case(ref_te, ref_models):
     np.savez_compressed(os.path.join(OUT, "tta.npz"), **out)
 
 
+def preprocess_case(ref_te, ref_models):
+    """Evaluator._prepare_image_tensor (train_eval.py:365-395): the cv2 CLAHE + sharpening step in front of the model."""
+    model = _ref_model(ref_models, make_state_dict(0)).eval()
+    ev = ref_te.Evaluator(model, torch.device("cpu"), "enhanced_unet")
+    out = {}
+    for name, (h, w, seed) in {"96x80": (96, 80, 31), "64x64": (64, 64, 32)}.items():
+        g = torch.Generator().manual_seed(seed)
+        yy, xx = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+        img = 0.7 + 0.05 * torch.randn(1, h, w, generator=g) - 0.3 * torch.exp(-((yy - h / 2) ** 2 + (xx - w / 3) ** 2) / 60.0)
+        img = img.clamp(0, 1).expand(3, h, w).contiguous()
+        out[f"{name}/image"] = img.numpy()
+        out[f"{name}/prepared"] = ev._prepare_image_tensor(img).numpy()
+        print("preprocess", name, float(out[f"{name}/prepared"].sum()))
+    np.savez_compressed(os.path.join(OUT, "preprocess.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -313,6 +329,8 @@ def main():
         instances_case(ref_metrics)
     if want("tta"):
         tta_case(ref_te, ref_models)
+    if want("preprocess"):
+        preprocess_case(ref_te, ref_models)
 
 
 if __name__ == "__main__":

@@ -85,3 +85,16 @@ def test_no_gpu_means_loud_failure():
         from enhanced_unet_b200 import metrics
         with pytest.raises(RuntimeError):
             metrics.calculate_semantic_metrics(np.zeros((4, 4), np.int64), np.zeros((4, 4), np.int64))
+
+
+def test_prepare_image_tensor_matches_reference_fixture(golden_dir):
+    """Evaluator._prepare_image_tensor (host-side cv2 CLAHE + sharpening, reference train_eval.py:365-395) against the output of
+    the reference's own method (tests/golden/preprocess.npz, oracle/make_golden.py:preprocess_case): bit-identical."""
+    pytest.importorskip("cv2")
+    from enhanced_unet_b200.train_eval import Evaluator
+    g = np.load(os.path.join(golden_dir, "preprocess.npz"))
+    ev = Evaluator(model=None, device="cpu", model_name="enhanced_unet")
+    assert ev.enable_tta                                    # reference train_eval.py:363
+    for name in ("96x80", "64x64"):
+        got = ev._prepare_image_tensor(torch.from_numpy(g[f"{name}/image"])).numpy()
+        assert got.shape == g[f"{name}/prepared"].shape and np.array_equal(got, g[f"{name}/prepared"]), name
