@@ -312,8 +312,14 @@ def test_five_step_trajectory_matches_reference_optimiser():
     plist = [p for p in params.values() if p.requires_grad]
     opt = torch.optim.AdamW(plist, lr=lr, weight_decay=1e-4, betas=(0.9, 0.999))
     ref_losses = []
+    bn_of = lambda conv: re.sub(r"\.(\d)$", lambda mo: f".{int(mo.group(1)) + 1}", conv)      # model.enc1.0 -> model.enc1.1
+    convs = [n[:-5] for n in sd if pre_bn_bias.match(n)]
+    bias_ref = {c: [] for c in convs}
+    bias_got = {c: [] for c in convs}
     for x, t in zip(xs, ts):
         opt.zero_grad()
+        for c in convs:
+            bias_ref[c].append(params[c + ".bias"].detach().clone())
         y, nb = oracle.unet_forward(params, x, train=True)
         loss = oracle.batch_loss(y, t)
         loss.backward()
@@ -328,7 +334,11 @@ def test_five_step_trajectory_matches_reference_optimiser():
     tr = Trainer(m, "cuda", "enhanced_unet", total_epochs=50)
     for g in tr.optimizer.param_groups:
         g["lr"] = lr
-    losses = [float(tr.train_step(x, [t[0], t[1]])) for x, t in zip(xs, ts)]
+    losses = []
+    for x, t in zip(xs, ts):
+        for c in convs:
+            bias_got[c].append(dict(m.named_parameters())[c + ".bias"].detach().cpu().clone())
+        losses.append(float(tr.train_step(x, [t[0], t[1]])))
     print(f"[trajectory] losses {['%.5f' % v for v in losses]} vs {['%.5f' % v for v in ref_losses]}")
     # step 0 sees identical weights (1e-6); from then on the two fp32 trajectories drift apart as described above
     # (measured 2e-5, then 4e-4 .. 7e-4 per step at this learning rate, run-to-run variation included)
@@ -342,11 +352,16 @@ def test_five_step_trajectory_matches_reference_optimiser():
             assert int(got) == steps == int(ref), name
         elif "running_" in name:
             ref_t, got_t = ref.double(), got.double()
-            # running_mean carries the conv bias, which the reference random-walks by +-lr per step (see the docstring)
-            tol = 5e-3 + (2 * steps * lr / max(float(ref_t.abs().max()), 1e-12) if name.endswith("running_mean") else 0.0)
-            e = float((got_t - ref_t).abs().max() / ref_t.abs().max())
-            worst_s = max(worst_s, e if name.endswith("running_var") else 0.0)
-            assert e <= tol, (name, e, tol)
+            if name.endswith("running_mean"):
+                # running_mean = momentum average of (batch mean of the bias-free conv + conv bias); the reference random-walks
+                # that bias on rounding noise (docstring), so its recorded history is taken out on both sides before comparing
+                conv = [c for c in convs if bn_of(c) + ".running_mean" == name][0]
+                for hist, tt in ((bias_ref[conv], ref_t), (bias_got[conv], got_t)):
+                    for k, b in enumerate(hist):
+                        tt -= 0.1 * 0.9 ** (steps - 1 - k) * b.double()
+            e = float((got_t - ref_t).abs().max() / max(float(ref_t.abs().max()), 1e-3))
+            worst_s = max(worst_s, e)
+            assert e <= 5e-2, (name, e)       # measured <= 2.3e-2 (enc4.1: 128 values per channel at this size), deterministic
         elif not pre_bn_bias.match(name):
             p0 = sd[name].double()
             dr, dg = ref.detach().double() - p0, got.double() - p0
@@ -357,7 +372,7 @@ def test_five_step_trajectory_matches_reference_optimiser():
                 rel = float((got.double() - ref.detach().double()).norm() / ref.detach().double().norm())
                 worst_p = max(worst_p, rel)
                 assert rel <= 2e-2, (name, rel)     # measured 5e-3 = ~10 % of the 5-step update: gradients of two correct fp32 paths differ by ~1e-3
-    print(f"[trajectory] worst parameter relL2 {worst_p:.2e}, worst update cosine {worst_c:.4f}, worst running_var err {worst_s:.2e}")
+    print(f"[trajectory] worst parameter relL2 {worst_p:.2e}, worst update cosine {worst_c:.4f}, worst running-statistic err {worst_s:.2e}")
 
 
 def test_graphed_train_step_matches_eager_steps():
