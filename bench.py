@@ -73,11 +73,13 @@ def hbm_bytes_per_step(batch: int, res: int) -> dict:
     bn_layers = [(0, 64)] * 2 + [(1, 128)] * 2 + [(2, 256)] * 2 + [(3, 512)] * 2 + [(2, 256)] * 2 + [(1, 128)] * 2 + [(0, 64)] * 2
     elems = sum(batch * (res >> l) ** 2 * c for l, c in bn_layers)
     pooled = sum(batch * (res >> l) ** 2 * c // 4 for l, c in ((0, 64), (1, 128), (2, 256)))
-    ups = [(3, 512), (2, 256), (1, 128)]          # (input level, channels)
-    up_bytes = sum(batch * (res >> l) ** 2 * c * 2 * 5 for l, c in ups)        # read in (2 B) + write 4x out (8 B)
+    ups = [(3, 512), (2, 256), (1, 128)]          # (input level, channels): enc4.4, dec4.4, dec3.4 feed the upsample only
+    up_elems = sum(batch * (res >> l) ** 2 * c for l, c in ups)
+    up_bytes = up_elems * 2 * 5                   # read in (2 B) + write 4x out (8 B)
     m1, m2 = batch * res * res, 4 * batch * res * res
     return {
-        "eunet_bn_apply_relu": elems * 4 + pooled * 2,
+        "eunet_bn_apply_relu": (elems - up_elems) * 4 + pooled * 2,
+        "eunet_bn_apply_relu_upsample2": up_bytes,         # training: BN apply + ReLU + upsample fused (no stored activation)
         "eunet_bn_bwd_reduce": elems * 4,
         "eunet_bn_bwd_apply": elems * 6,
         "eunet_upsample2_fwd": up_bytes,

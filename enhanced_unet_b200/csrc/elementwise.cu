@@ -225,9 +225,12 @@ __global__ void maxpool2_bwd_kernel(const T* __restrict__ dpool, int ldp, const 
 // ------------------------------------------------------------------------------------------------
 constexpr int kUpSeg = 8;
 
-template <typename T>
+// AFF: the input is a RAW (pre-BatchNorm) conv output and relu(x * scale + shift) is applied on load - BN apply + ReLU +
+// upsample in one pass for the blocks whose activation is consumed by the upsample only (enc4, dec4, dec3).
+template <typename T, typename TI, bool AFF>
 __global__ void __launch_bounds__(256)
-upsample2_fwd_kernel(const T* __restrict__ x, int ldx, T* __restrict__ out, int ldo, int B, int H, int W, int C) {
+upsample2_fwd_kernel(const TI* __restrict__ x, int ldx, T* __restrict__ out, int ldo, int B, int H, int W, int C,
+                     const float* __restrict__ scale, const float* __restrict__ shift) {
   const int G = C >> 3, nseg = (W + kUpSeg - 1) / kUpSeg;
   const long long items = (long long)B * nseg * H * G;
   const int Wo = 2 * W, Ho = 2 * H;
@@ -240,12 +243,22 @@ upsample2_fwd_kernel(const T* __restrict__ x, int ldx, T* __restrict__ out, int 
     const int j0 = seg * kUpSeg, j1 = min(W, j0 + kUpSeg);
     const float wyp = k > 0 ? 0.25f : 0.f, wyc0 = k > 0 ? 0.75f : 1.f;
     const float wyn = k < H - 1 ? 0.25f : 0.f, wyc1 = k < H - 1 ? 0.75f : 1.f;
-    const T* rm = x + (((long long)b * H + (k > 0 ? k - 1 : 0)) * W) * ldx + cg * 8;
-    const T* rc = x + (((long long)b * H + k) * W) * ldx + cg * 8;
-    const T* rp = x + (((long long)b * H + (k < H - 1 ? k + 1 : H - 1)) * W) * ldx + cg * 8;
+    const TI* rm = x + (((long long)b * H + (k > 0 ? k - 1 : 0)) * W) * ldx + cg * 8;
+    const TI* rc = x + (((long long)b * H + k) * W) * ldx + cg * 8;
+    const TI* rp = x + (((long long)b * H + (k < H - 1 ? k + 1 : H - 1)) * W) * ldx + cg * 8;
+    F8 sc, sh;
+    if (AFF) { sc = load8(scale + cg * 8); sh = load8(shift + cg * 8); }
     F8 p0, p1, c0, c1, n0, n1;   // vertically interpolated columns j-1, j, j+1 for output rows 2k (0) and 2k+1 (1)
     auto vcol = [&](int j, F8& v0, F8& v1) {
-      const F8 a = load8(rm + (long long)j * ldx), c = load8(rc + (long long)j * ldx), d = load8(rp + (long long)j * ldx);
+      F8 a = load8(rm + (long long)j * ldx), c = load8(rc + (long long)j * ldx), d = load8(rp + (long long)j * ldx);
+      if (AFF) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          a.v[e] = fmaxf(fmaf(a.v[e], sc.v[e], sh.v[e]), 0.f);
+          c.v[e] = fmaxf(fmaf(c.v[e], sc.v[e], sh.v[e]), 0.f);
+          d.v[e] = fmaxf(fmaf(d.v[e], sc.v[e], sh.v[e]), 0.f);
+        }
+      }
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         v0.v[e] = wyp * a.v[e] + wyc0 * c.v[e];
@@ -729,9 +742,19 @@ int eunet_upsample2_fwd(const void* x, int ldx, void* out, int ldo, int dtype, i
   if (check_vec(x, ldx, C, "upsample2_fwd(x)") || check_vec(out, ldo, C, "upsample2_fwd(out)")) return -1;
   EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "upsample2_fwd: empty tensor");
   const long long items = (long long)B * H * ((W + kUpSeg - 1) / kUpSeg) * (C / 8);
-  DISPATCH_DTYPE(dtype, upsample2_fwd_kernel<T><<<ew_grid(items), 256, 0, (cudaStream_t)stream>>>((const T*)x, ldx, (T*)out,
-                                                                                                   ldo, B, H, W, C));
+  DISPATCH_DTYPE(dtype, upsample2_fwd_kernel<T, T, false><<<ew_grid(items), 256, 0, (cudaStream_t)stream>>>(
+                            (const T*)x, ldx, (T*)out, ldo, B, H, W, C, nullptr, nullptr));
   return check_launch("upsample2_fwd");
+}
+
+int eunet_bn_apply_relu_upsample2(const void* y, int ldy, void* out, int ldo, int dtype, int B, int H, int W, int C,
+                                  const float* scale, const float* shift, void* stream) {
+  if (check_vec(y, ldy, C, "bn_apply_relu_upsample2(y)") || check_vec(out, ldo, C, "bn_apply_relu_upsample2(out)")) return -1;
+  EUNET_REQUIRE(B > 0 && H > 0 && W > 0 && scale && shift, "bn_apply_relu_upsample2: bad arguments");
+  const long long items = (long long)B * H * ((W + kUpSeg - 1) / kUpSeg) * (C / 8);
+  DISPATCH_DTYPE(dtype, upsample2_fwd_kernel<T, TY, true><<<ew_grid(items), 256, 0, (cudaStream_t)stream>>>(
+                            (const TY*)y, ldy, (T*)out, ldo, B, H, W, C, scale, shift));
+  return check_launch("bn_apply_relu_upsample2");
 }
 
 int eunet_upsample2_bwd(const void* dout, int ldo, void* dx, int ldx, int dtype, int B, int H, int W, int C, void* stream) {

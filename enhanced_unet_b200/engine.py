@@ -249,7 +249,11 @@ class _BNSaved:
 
 
 def _conv_bn_train(cx: _Ctx, packs: PackCache, sd: Dict[str, torch.Tensor], conv: str, bn: str, x: torch.Tensor, B, H, W, cin_p,
-                   cout, out: torch.Tensor, pooled: Optional[torch.Tensor], hilo: bool = False, stats=None) -> _BNSaved:
+                   cout, out: Optional[torch.Tensor], pooled: Optional[torch.Tensor], hilo: bool = False, stats=None,
+                   up_into: Optional[torch.Tensor] = None) -> _BNSaved:
+    """conv (+ batch statistics) -> finalize -> BN apply + ReLU into ``out`` (+ 2x2 max-pool into ``pooled``), or - when the
+    activation is consumed by the x2 upsample only (``up_into`` = the concat slice at twice the resolution) - BN apply + ReLU +
+    bilinear upsample in one pass, without ever storing the activation."""
     M = B * H * W
     y = cx.empty(M, cout, dtype=cx.raw)
     if stats is None:
@@ -262,8 +266,11 @@ def _conv_bn_train(cx: _Ctx, packs: PackCache, sd: Dict[str, torch.Tensor], conv
     call("eunet_bn_finalize", ptr(stats), M, ptr(sd[bn + ".weight"]), ptr(sd[bn + ".bias"]), ptr(sd.get(conv + ".bias")),
          ptr(sd[bn + ".running_mean"]), ptr(sd[bn + ".running_var"]), ptr(sd[bn + ".num_batches_tracked"]), BN_MOMENTUM, BN_EPS,
          ptr(scale), ptr(shift), ptr(mean), ptr(invstd), cout)
-    call("eunet_bn_apply_relu", ptr(y), _ld(y), ptr(out), _ld(out), ptr(pooled), _ld(pooled) if pooled is not None else 0,
-         cx.code, B, H, W, cout, ptr(scale), ptr(shift))
+    if up_into is not None:
+        call("eunet_bn_apply_relu_upsample2", ptr(y), _ld(y), ptr(up_into), _ld(up_into), cx.code, B, H, W, cout, ptr(scale), ptr(shift))
+    else:
+        call("eunet_bn_apply_relu", ptr(y), _ld(y), ptr(out), _ld(out), ptr(pooled), _ld(pooled) if pooled is not None else 0,
+             cx.code, B, H, W, cout, ptr(scale), ptr(shift))
     return _BNSaved(y, scale, shift, mean, invstd)
 
 
@@ -324,10 +331,13 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, train: bool, act_dtype
     cat4 = cx.empty(Ms[2], 768)   # [up(e4) | e3]
     e1, e2, e3 = cat2[:, 128:192], cat3[:, 256:384], cat4[:, 512:768]
     p1, p2, p3 = cx.empty(Ms[1], 64), cx.empty(Ms[2], 128), cx.empty(Ms[3], 256)
-    e4 = cx.empty(Ms[3], 512)
-    d4, d3, d2 = cx.empty(Ms[2], 256), cx.empty(Ms[1], 128), cx.empty(Ms[0], 64)
+    # e4 / d4 / d3 feed the upsample only: materialised in eval mode (conv epilogue output), never in training
+    e4, d4, d3 = (None, None, None) if train else (cx.empty(Ms[3], 512), cx.empty(Ms[2], 256), cx.empty(Ms[1], 128))
+    d2 = cx.empty(Ms[0], 64)
 
-    def block(prefix, xin, lvl, cin_p, cout, out, pooled=None):
+    def block(prefix, xin, lvl, cin_p, cout, out, pooled=None, up_into=None):
+        """``up_into``: the block's activation is consumed by the x2 upsample only -> in training it is never stored (fused BN
+        apply + ReLU + upsample); ``out`` is then only used in eval mode (conv epilogue -> ``out`` -> upsample)."""
         h, w = dims[lvl]
         mid = cx.empty(Ms[lvl], cout)
         first = hilo and prefix == "model.enc1"
@@ -335,7 +345,7 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, train: bool, act_dtype
             sv.bn[prefix + ".1"] = _conv_bn_train(cx, packs, sd, prefix + ".0", prefix + ".1", xin, B, h, w, cin_p, cout, mid, None,
                                                   hilo=first, stats=zp64.take(2 * cout))
             sv.bn[prefix + ".4"] = _conv_bn_train(cx, packs, sd, prefix + ".3", prefix + ".4", mid, B, h, w, cout, cout, out, pooled,
-                                                  stats=zp64.take(2 * cout))
+                                                  stats=zp64.take(2 * cout), up_into=up_into)
             sv.act[prefix + ".in"] = xin
             sv.act[prefix + ".mid"] = mid
         else:
@@ -343,20 +353,15 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, train: bool, act_dtype
             _conv_bn_eval(cx, packs, sd, prefix + ".3", prefix + ".4", mid, B, h, w, cout, cout, out)
             if pooled is not None:
                 call("eunet_maxpool2_fwd", ptr(out), _ld(out), ptr(pooled), _ld(pooled), cx.code, B, h, w, cout)
-
-    def up(src, lvl_src, c, dst):
-        h, w = dims[lvl_src]
-        call("eunet_upsample2_fwd", ptr(src), _ld(src), ptr(dst), _ld(dst), cx.code, B, h, w, c)
+            if up_into is not None:
+                call("eunet_upsample2_fwd", ptr(out), _ld(out), ptr(up_into), _ld(up_into), cx.code, B, h, w, cout)
 
     block("model.enc1", x16, 0, 16, 64, e1, p1)
     block("model.enc2", p1, 1, 64, 128, e2, p2)
     block("model.enc3", p2, 2, 128, 256, e3, p3)
-    block("model.enc4", p3, 3, 256, 512, e4)
-    up(e4, 3, 512, cat4[:, 0:512])
-    block("model.dec4", cat4, 2, 768, 256, d4)
-    up(d4, 2, 256, cat3[:, 0:256])
-    block("model.dec3", cat3, 1, 384, 128, d3)
-    up(d3, 1, 128, cat2[:, 0:128])
+    block("model.enc4", p3, 3, 256, 512, e4, up_into=cat4[:, 0:512])
+    block("model.dec4", cat4, 2, 768, 256, d4, up_into=cat3[:, 0:256])
+    block("model.dec3", cat3, 1, 384, 128, d3, up_into=cat2[:, 0:128])
     block("model.dec2", cat2, 0, 192, 64, d2)
 
     # ---- tail: z = dec1(d2) @HxW, d1 = up(z), mid = enhance.0(d1), out = d1 + enhance.3(relu(bn(mid))) ----

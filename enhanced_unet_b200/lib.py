@@ -47,6 +47,7 @@ SIGNATURES = {
     "eunet_maxpool2_bwd": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "eunet_upsample2_fwd": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p],
     "eunet_upsample2_bwd": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p],
+    "eunet_bn_apply_relu_upsample2": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p],
     "eunet_tail_dec1_fwd": [_p, _i, _i, _p, _p, _p, _ll, _p],
     "eunet_tail_up_fwd": [_p, _p, _p, _i, _i, _i, _i, _p],
     "eunet_tail_pack3": [_p, _p, _i, _i, _i, _p, _p],

@@ -147,6 +147,10 @@ int eunet_maxpool2_bwd(const void* dpool, int ldp, const void* x, int ldx, void*
                        int B, int H, int W, int C, void* stream);
 int eunet_upsample2_fwd(const void* x, int ldx, void* out, int ldo, int dtype, int B, int H, int W, int C, void* stream);
 int eunet_upsample2_bwd(const void* dout, int ldo, void* dx, int ldx, int dtype, int B, int H, int W, int C, void* stream);
+/* out = upsample2(relu(y * scale + shift)): BN apply + ReLU (models.py:220-224) + nn.Upsample (models.py:215, 233-235) in one
+ * pass over the RAW conv output y [B,H,W,C] -> out [B,2H,2W,C]; for blocks whose activation feeds the upsample only. */
+int eunet_bn_apply_relu_upsample2(const void* y, int ldy, void* out, int ldo, int dtype, int B, int H, int W, int C,
+                                  const float* scale, const float* shift, void* stream);
 
 /* ---- the 2Hx2W tail (models.py:212, 236, 308-313, 337): dec1 1x1, final upsample, enhance head, residual.
  * z = dec1(d2) is computed at HxW (a 1x1 conv commutes with bilinear interpolation), d1 = up(z). ---- */

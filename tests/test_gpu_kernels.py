@@ -124,6 +124,31 @@ def test_upsample_fwd_bwd(k, dtn, shape):
 
 
 @pytest.mark.parametrize("dtn", MODES)
+@pytest.mark.parametrize("shape", [(2, 64, 5, 7), (1, 16, 1, 1), (2, 128, 8, 8), (1, 512, 6, 9), (2, 256, 12, 20)])
+def test_bn_apply_relu_upsample_fused(k, dtn, shape):
+    """BN apply + ReLU + bilinear x2 upsample in one pass over the RAW conv output (the activation of enc4 / dec4 / dec3 is
+    consumed by the upsample only and never stored in training) against F.interpolate(relu(y * scale + shift)); the output is
+    a channel slice of a wider (concat) buffer."""
+    B, C, H, W = shape
+    dt = DT[dtn]
+    raw_dt = k.raw_dtype(dt)
+    g = torch.Generator().manual_seed(C + H)
+    y = torch.randn(shape, generator=g) * 1.5 + 0.2
+    sc, sh = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.5
+    yr = y.to(raw_dt).float()
+    want = F.interpolate(F.relu(yr * sc[None, :, None, None] + sh[None, :, None, None]), scale_factor=2, mode="bilinear", align_corners=False)
+    yd = nhwc(y, raw_dt)
+    buf = torch.full((B * 4 * H * W, C + 16), 3.0, dtype=dt, device="cuda")
+    out = buf[:, 8:8 + C]
+    scd, shd = sc.cuda(), sh.cuda()
+    k.call("eunet_bn_apply_relu_upsample2", yd.data_ptr(), C, out.data_ptr(), out.stride(0), k.dtype_code(dt), B, H, W, C, scd.data_ptr(),
+           shd.data_ptr())
+    torch.cuda.synchronize()
+    assert nerr(nchw(out, B, 2 * H, 2 * W), want) < TOL[dtn]
+    assert torch.all(buf[:, :8] == 3.0) and torch.all(buf[:, 8 + C:] == 3.0)
+
+
+@pytest.mark.parametrize("dtn", MODES)
 @pytest.mark.parametrize("C", [64, 128, 512])
 def test_bn_train_apply_pool_and_backward(k, dtn, C):
     """conv output y -> batch stats -> finalize (+running stats) -> apply+ReLU(+pool) and the full backward,
