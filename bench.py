@@ -80,8 +80,11 @@ def hbm_bytes_per_step(batch: int, res: int) -> dict:
     return {
         "eunet_bn_apply_relu": (elems - up_elems) * 4 + pooled * 2,
         "eunet_bn_apply_relu_upsample2": up_bytes,         # training: BN apply + ReLU + upsample fused (no stored activation)
-        "eunet_bn_bwd_reduce": elems * 4,
-        "eunet_bn_bwd_apply": elems * 6,
+        "eunet_bn_bwd_reduce": (elems - 4 * pooled) * 4,
+        "eunet_bn_bwd_apply": (elems - 4 * pooled) * 6,
+        # enc1.4 / enc2.4 / enc3.4: BN backward with the max-pool gradient routed on the fly (dskip 2 + y 2 + dpool 0.5 B)
+        "eunet_bn_bwd_reduce_pool": 4 * pooled * 4 + pooled * 2,
+        "eunet_bn_bwd_apply_pool": 4 * pooled * 6 + pooled * 2,
         "eunet_upsample2_fwd": up_bytes,
         "eunet_upsample2_bwd": up_bytes,
         "eunet_maxpool2_bwd": sum(batch * (res >> l) ** 2 * c * (2 + 4) + batch * (res >> l) ** 2 * c // 4 * 2

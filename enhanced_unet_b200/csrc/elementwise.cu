@@ -474,6 +474,196 @@ bn_bwd_apply_kernel(const T* __restrict__ dact, int ldd, const TY* __restrict__ 
   cp_async_wait<0>();
 }
 
+// ---- BN + ReLU backward for an encoder output that ALSO feeds a 2x2 max-pool (enc1.4, enc2.4, enc3.4) ----
+// The gradient of such an activation is  dskip (from the decoder's concat slice) + route(dpool)  where the pooled gradient
+// goes to the first maximum of its window (ATen tie-break).  Instead of a max-pool backward pass that read-modify-writes
+// the skip slice (6.5 B per element) followed by the two BN passes, both BN passes form that sum on the fly: one thread
+// owns one 2x2 window x 8 channels, recomputes the four stored activations round_T(relu(y * scale + shift)) - exactly the
+// values the forward pool compared - and routes dpool itself.
+// One thread = one 2x2 window x eight channels.  The nine 16-byte vectors of a window stay PACKED in registers (36 for 16-bit
+// storage) and are expanded a channel pair at a time: expanding all of them first costs 165 registers and one resident block
+// per SM (measured 0.19-0.26 of the HBM roofline).
+template <typename T> struct Pk8 { uint4 u; };
+template <> struct Pk8<float> { float4 a, b; };
+template <typename T> __device__ __forceinline__ Pk8<T> ldpk(const T* p) { return Pk8<T>{*reinterpret_cast<const uint4*>(p)}; }
+template <> __device__ __forceinline__ Pk8<float> ldpk<float>(const float* p) {
+  return Pk8<float>{*reinterpret_cast<const float4*>(p), *reinterpret_cast<const float4*>(p + 4)};
+}
+__device__ __forceinline__ uint32_t pk_word(const uint4& u, int i) { return i == 0 ? u.x : i == 1 ? u.y : i == 2 ? u.z : u.w; }
+__device__ __forceinline__ float2 pk_pair(const Pk8<__half>& r, int kp) {
+  const uint32_t w = pk_word(r.u, kp);
+  return __half22float2(*reinterpret_cast<const __half2*>(&w));
+}
+__device__ __forceinline__ float2 pk_pair(const Pk8<__nv_bfloat16>& r, int kp) {
+  const uint32_t w = pk_word(r.u, kp);
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ float2 pk_pair(const Pk8<float>& r, int kp) {
+  return kp == 0 ? make_float2(r.a.x, r.a.y) : kp == 1 ? make_float2(r.a.z, r.a.w) : kp == 2 ? make_float2(r.b.x, r.b.y) : make_float2(r.b.z, r.b.w);
+}
+__device__ __forceinline__ void pk_set(Pk8<__half>& r, int kp, float lo, float hi) {
+  const uint32_t w = pack_f16x2(lo, hi);
+  if (kp == 0) r.u.x = w; else if (kp == 1) r.u.y = w; else if (kp == 2) r.u.z = w; else r.u.w = w;
+}
+__device__ __forceinline__ void pk_set(Pk8<__nv_bfloat16>& r, int kp, float lo, float hi) {
+  const uint32_t w = pack_bf16x2(lo, hi);
+  if (kp == 0) r.u.x = w; else if (kp == 1) r.u.y = w; else if (kp == 2) r.u.z = w; else r.u.w = w;
+}
+__device__ __forceinline__ void pk_set(Pk8<float>& r, int kp, float lo, float hi) {
+  if (kp == 0) { r.a.x = lo; r.a.y = hi; } else if (kp == 1) { r.a.z = lo; r.a.w = hi; }
+  else if (kp == 2) { r.b.x = lo; r.b.y = hi; } else { r.b.z = lo; r.b.w = hi; }
+}
+template <typename T> __device__ __forceinline__ void stpk(T* p, const Pk8<T>& r) { *reinterpret_cast<uint4*>(p) = r.u; }
+template <> __device__ __forceinline__ void stpk<float>(float* p, const Pk8<float>& r) {
+  *reinterpret_cast<float4*>(p) = r.a;
+  *reinterpret_cast<float4*>(p + 4) = r.b;
+}
+
+template <typename T, typename TY> struct PoolWindow {
+  Pk8<T> dp, d[4];
+  Pk8<TY> y[4];
+  unsigned pos[4];          // pixel index of each window element (B*H*W < 2^32, checked on the host)
+  __device__ __forceinline__ void load(const T* __restrict__ dskip, int ldd, const T* __restrict__ dpool, int ldp,
+                                       const TY* __restrict__ yp, int ldy, int H, int W, unsigned item, int lgG) {
+    const unsigned Hp = H >> 1, Wp = W >> 1;
+    const unsigned c0 = (item & ((1u << lgG) - 1)) * 8;
+    unsigned q = item >> lgG;                 // pooled pixel index (b, py, px)
+    const unsigned px = q % Wp, r = q / Wp;   // r = b * Hp + py: the input row pair is rows 2r, 2r+1 of the [B*H] stack
+    dp = ldpk(dpool + (size_t)q * ldp + c0);
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      pos[w] = (2 * r + (w >> 1)) * (unsigned)W + 2 * px + (w & 1);
+      y[w] = ldpk(yp + (size_t)pos[w] * ldy + c0);
+      d[w] = ldpk(dskip + (size_t)pos[w] * ldd + c0);
+    }
+    (void)Hp;
+  }
+  // Gradient entering BN for channels 2kp, 2kp+1 of the four window elements: ReLU mask of (skip gradient + routed pool gradient).
+  // The pool gradient goes to the first maximum (row-major window order, ATen's tie-break) of the fp32 pre-activations: that
+  // element is always one of the maxima of the stored (rounded) activations the forward pool compared, and where rounding
+  // made several of those equal it is the one an fp32 forward would have picked.
+  __device__ __forceinline__ void grads(int kp, float sc0, float sh0, float sc1, float sh1, float (&g)[4][2], float (&yy)[4][2]) const {
+    const float2 dpv = pk_pair(dp, kp);
+    float p[4][2];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float2 yv = pk_pair(y[w], kp);
+      yy[w][0] = yv.x;
+      yy[w][1] = yv.y;
+      p[w][0] = fmaf(yv.x, sc0, sh0);
+      p[w][1] = fmaf(yv.y, sc1, sh1);
+    }
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float m = fmaxf(fmaxf(p[0][e], p[1][e]), fmaxf(p[2][e], p[3][e]));
+      const float dpe = e ? dpv.y : dpv.x;
+      const bool e0 = p[0][e] == m, e1 = !e0 && p[1][e] == m, e2 = !e0 && !e1 && p[2][e] == m, e3 = !e0 && !e1 && !e2;
+      const bool hit[4] = {e0, e1, e2, e3};
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const float2 dv = pk_pair(d[w], kp);
+        g[w][e] = p[w][e] > 0.f ? (e ? dv.y : dv.x) + (hit[w] ? dpe : 0.f) : 0.f;
+      }
+    }
+  }
+};
+
+__host__ __device__ inline int ilog2_exact(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+template <typename T, typename TY>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_reduce_pool_kernel(const T* __restrict__ dskip, int ldd, const T* __restrict__ dpool, int ldp, const TY* __restrict__ y,
+                          int ldy, int B, int H, int W, int C, int lgG, const float* __restrict__ scale,
+                          const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
+                          double* __restrict__ sums) {
+  __shared__ float red[2][256 * 8];
+  const int G = 1 << lgG, R = 256 >> lgG;
+  const int cg = threadIdx.x & (G - 1), r = threadIdx.x >> lgG;   // 256 % G == 0: a thread keeps its channel group over the grid stride
+  const F8 sc = load8(scale + cg * 8), sh = load8(shift + cg * 8), mu = load8(mean + cg * 8);
+  float sg[8], sgx[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sg[e] = sgx[e] = 0.f;
+  const unsigned items = (unsigned)B * (H >> 1) * (W >> 1) * G;
+  for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < items; i += gridDim.x * 256u) {
+    PoolWindow<T, TY> win;
+    win.load(dskip, ldd, dpool, ldp, y, ldy, H, W, i, lgG);
+#pragma unroll
+    for (int kp = 0; kp < 4; ++kp) {
+      float g[4][2], yy[4][2];
+      win.grads(kp, sc.v[2 * kp], sh.v[2 * kp], sc.v[2 * kp + 1], sh.v[2 * kp + 1], g, yy);
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          sg[2 * kp + e] += g[w][e];
+          sgx[2 * kp + e] = fmaf(g[w][e], yy[w][e] - mu.v[2 * kp + e], sgx[2 * kp + e]);
+        }
+    }
+  }
+  const F8 is = load8(invstd + cg * 8);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    red[0][r * C + cg * 8 + e] = sg[e];
+    red[1][r * C + cg * 8 + e] = sgx[e] * is.v[e];
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 2 * C; t += 256) {
+    const int which = t / C, c = t % C;
+    float s = 0.f;
+    for (int rr = 0; rr < R; ++rr) s += red[which][rr * C + c];
+    atomicAdd(&sums[which * C + c], (double)s);
+  }
+}
+
+template <typename T, typename TY>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_apply_pool_kernel(const T* __restrict__ dskip, int ldd, const T* __restrict__ dpool, int ldp, const TY* __restrict__ y,
+                         int ldy, T* __restrict__ dy, int lddy, int B, int H, int W, int C, int lgG,
+                         const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                         const float* __restrict__ invstd, const double* __restrict__ sums, float* __restrict__ dgamma,
+                         float* __restrict__ dbeta, const float* __restrict__ gscale) {
+  if (blockIdx.x == 0) {
+    const double inv = (double)gscale_inv(gscale);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      if (dbeta) dbeta[c] = (float)(sums[c] * inv);
+      if (dgamma) dgamma[c] = (float)(sums[C + c] * inv);
+    }
+  }
+  const int cg = threadIdx.x & ((1 << lgG) - 1);
+  const double invM = 1.0 / ((double)B * H * W);
+  const F8 sc = load8(scale + cg * 8), sh = load8(shift + cg * 8);
+  // dy = sc (g - k1 - (y - mean) invstd k2) = sc g + P + Q y
+  float P[8], Q[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float k1 = (float)(sums[cg * 8 + e] * invM), k2 = (float)(sums[C + cg * 8 + e] * invM);
+    const float mu = mean[cg * 8 + e], is = invstd[cg * 8 + e];
+    Q[e] = -sc.v[e] * is * k2;
+    P[e] = -sc.v[e] * k1 - Q[e] * mu;
+  }
+  const unsigned items = (unsigned)B * (H >> 1) * (W >> 1) << lgG;
+  for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < items; i += gridDim.x * 256u) {
+    PoolWindow<T, TY> win;
+    win.load(dskip, ldd, dpool, ldp, y, ldy, H, W, i, lgG);
+    Pk8<T> o[4];
+#pragma unroll
+    for (int kp = 0; kp < 4; ++kp) {
+      float g[4][2], yy[4][2];
+      win.grads(kp, sc.v[2 * kp], sh.v[2 * kp], sc.v[2 * kp + 1], sh.v[2 * kp + 1], g, yy);
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+        pk_set(o[w], kp, fmaf(sc.v[2 * kp], g[w][0], fmaf(Q[2 * kp], yy[w][0], P[2 * kp])),
+               fmaf(sc.v[2 * kp + 1], g[w][1], fmaf(Q[2 * kp + 1], yy[w][1], P[2 * kp + 1])));
+    }
+#pragma unroll
+    for (int w = 0; w < 4; ++w) stpk(dy + (size_t)win.pos[w] * lddy + cg * 8, o[w]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // packing
 // ------------------------------------------------------------------------------------------------
@@ -710,6 +900,42 @@ int eunet_bn_bwd_apply(const void* dact, int ldd, const void* y, int ldy, void* 
                             (const T*)dact, ldd, (const TY*)y, ldy, (T*)dy, lddy, M, C, scale, shift, mean, invstd, sums, dgamma,
                             dbeta, gscale));
   return check_launch("bn_bwd_apply");
+}
+
+int eunet_bn_bwd_reduce_pool(const void* dskip, int ldd, const void* dpool, int ldp, const void* y, int ldy, int dtype, int B, int H,
+                             int W, int C, const float* scale, const float* shift, const float* mean, const float* invstd,
+                             double* sums, void* stream) {
+  if (check_vec(dskip, ldd, C, "bn_bwd_reduce_pool(dskip)") || check_vec(dpool, ldp, C, "bn_bwd_reduce_pool(dpool)") ||
+      check_vec(y, ldy, C, "bn_bwd_reduce_pool(y)"))
+    return -1;
+  EUNET_REQUIRE(B > 0 && H > 0 && W > 0 && (H & 1) == 0 && (W & 1) == 0, "bn_bwd_reduce_pool: H,W must be even (got %dx%d)", H, W);
+  EUNET_REQUIRE(C <= 2048 && 256 % (C / 8) == 0, "bn_bwd_reduce_pool: C/8=%d must divide 256", C / 8);
+  EUNET_REQUIRE((long long)B * H * W < (1ll << 31), "bn_bwd_reduce_pool: %lld pixels exceed the 32-bit index range", (long long)B * H * W);
+  const long long items = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  const int lgG = ilog2_exact(C / 8);
+  DISPATCH_DTYPE(dtype, const int grid = one_wave_grid(bn_bwd_reduce_pool_kernel<T, TY>, 256, 0, (items + 255) / 256);
+                 bn_bwd_reduce_pool_kernel<T, TY><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)dskip, ldd, (const T*)dpool, ldp,
+                                                                                        (const TY*)y, ldy, B, H, W, C, lgG, scale,
+                                                                                        shift, mean, invstd, sums));
+  return check_launch("bn_bwd_reduce_pool");
+}
+
+int eunet_bn_bwd_apply_pool(const void* dskip, int ldd, const void* dpool, int ldp, const void* y, int ldy, void* dy, int lddy,
+                            int dtype, int B, int H, int W, int C, const float* scale, const float* shift, const float* mean,
+                            const float* invstd, const double* sums, float* dgamma, float* dbeta, const float* gscale,
+                            void* stream) {
+  if (check_vec(dskip, ldd, C, "bn_bwd_apply_pool(dskip)") || check_vec(dpool, ldp, C, "bn_bwd_apply_pool(dpool)") ||
+      check_vec(y, ldy, C, "bn_bwd_apply_pool(y)") || check_vec(dy, lddy, C, "bn_bwd_apply_pool(dy)"))
+    return -1;
+  EUNET_REQUIRE(B > 0 && H > 0 && W > 0 && (H & 1) == 0 && (W & 1) == 0, "bn_bwd_apply_pool: H,W must be even (got %dx%d)", H, W);
+  EUNET_REQUIRE(C <= 2048 && 256 % (C / 8) == 0, "bn_bwd_apply_pool: C/8=%d must divide 256", C / 8);
+  EUNET_REQUIRE((long long)B * H * W < (1ll << 31), "bn_bwd_apply_pool: %lld pixels exceed the 32-bit index range", (long long)B * H * W);
+  const long long items = (long long)B * (H / 2) * (W / 2) * (C / 8);
+  const int lgG = ilog2_exact(C / 8);
+  DISPATCH_DTYPE(dtype, bn_bwd_apply_pool_kernel<T, TY><<<ew_grid(items), 256, 0, (cudaStream_t)stream>>>(
+                            (const T*)dskip, ldd, (const T*)dpool, ldp, (const TY*)y, ldy, (T*)dy, lddy, B, H, W, C, lgG, scale, shift,
+                            mean, invstd, sums, dgamma, dbeta, gscale));
+  return check_launch("bn_bwd_apply_pool");
 }
 
 int eunet_maxpool2_fwd(const void* x, int ldx, void* out, int ldo, int dtype, int B, int H, int W, int C, void* stream) {

@@ -507,25 +507,37 @@ def backward(sd: Dict[str, torch.Tensor], sv: Saved, dout: torch.Tensor, act_dty
     cast64("model.dec1.weight", acc2[0:192], (3, 64, 1, 1))
     cast64("model.dec1.bias", acc2[192:195], (3,))
 
-    def bn_bwd(name: str, dact: torch.Tensor, M: int, C: int) -> torch.Tensor:
+    def bn_bwd(name: str, dact: torch.Tensor, M: int, C: int, dpool: Optional[torch.Tensor] = None, hw=None) -> torch.Tensor:
+        """BN + ReLU backward of ``name``.  ``dpool``: the activation also fed a 2x2 max-pool whose gradient this is; the
+        two passes then form dact + route(dpool) on the fly (no max-pool backward pass over the skip slice)."""
         s = sv.bn[name]
         sums = zp64.take(2 * C)
-        call("eunet_bn_bwd_reduce", ptr(dact), _ld(dact), ptr(s.y), _ld(s.y), cx.code, M, C, ptr(s.scale), ptr(s.shift),
-             ptr(s.mean), ptr(s.invstd), ptr(sums))
         dy = cx.empty(M, C)
         dg, db = sink.dst(name + ".weight", (C,)), sink.dst(name + ".bias", (C,))
+        if dpool is not None:
+            h, w = hw
+            call("eunet_bn_bwd_reduce_pool", ptr(dact), _ld(dact), ptr(dpool), _ld(dpool), ptr(s.y), _ld(s.y), cx.code, B, h, w, C,
+                 ptr(s.scale), ptr(s.shift), ptr(s.mean), ptr(s.invstd), ptr(sums))
+            call("eunet_bn_bwd_apply_pool", ptr(dact), _ld(dact), ptr(dpool), _ld(dpool), ptr(s.y), _ld(s.y), ptr(dy), _ld(dy), cx.code,
+                 B, h, w, C, ptr(s.scale), ptr(s.shift), ptr(s.mean), ptr(s.invstd), ptr(sums), ptr(dg), ptr(db), ptr(gs))
+            sink.ready(name + ".weight")
+            sink.ready(name + ".bias")
+            return dy
+        call("eunet_bn_bwd_reduce", ptr(dact), _ld(dact), ptr(s.y), _ld(s.y), cx.code, M, C, ptr(s.scale), ptr(s.shift),
+             ptr(s.mean), ptr(s.invstd), ptr(sums))
         call("eunet_bn_bwd_apply", ptr(dact), _ld(dact), ptr(s.y), _ld(s.y), ptr(dy), _ld(dy), cx.code, M, C, ptr(s.scale),
              ptr(s.shift), ptr(s.mean), ptr(s.invstd), ptr(sums), ptr(dg), ptr(db), ptr(gs))
         sink.ready(name + ".weight")
         sink.ready(name + ".bias")
         return dy
 
-    def block_bwd(prefix: str, dact: torch.Tensor, lvl: int, cin: int, cout: int, need_dx: bool) -> Optional[torch.Tensor]:
+    def block_bwd(prefix: str, dact: torch.Tensor, lvl: int, cin: int, cout: int, need_dx: bool,
+                  dpool: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
         h, w = dims[lvl]
         M = Ms[lvl]
         cin_p = _pad16(cin)
         xin, mid = sv.act[prefix + ".in"], sv.act[prefix + ".mid"]
-        dy_b = bn_bwd(prefix + ".4", dact, M, cout)
+        dy_b = bn_bwd(prefix + ".4", dact, M, cout, dpool=dpool, hw=(h, w))
         wgrad_into(prefix + ".3.weight", conv3x3_wgrad(cx, mid, dy_b, B, h, w, cout, cout, pool), cout, cout)
         zero_bias(prefix + ".3.bias", cout)
         dmid_act = cx.empty(M, cout)
@@ -546,24 +558,18 @@ def backward(sd: Dict[str, torch.Tensor], sv: Saved, dout: torch.Tensor, act_dty
         call("eunet_upsample2_bwd", ptr(dsrc), _ld(dsrc), ptr(dx), _ld(dx), cx.code, B, h, w, c)
         return dx
 
-    def pool_bwd_into(dpool: torch.Tensor, xact: torch.Tensor, dx: torch.Tensor, lvl: int, c: int) -> None:
-        h, w = dims[lvl]
-        call("eunet_maxpool2_bwd", ptr(dpool), _ld(dpool), ptr(xact), _ld(xact), ptr(dx), _ld(dx), 1, cx.code, B, h, w, c)
-
-    cat2, cat3, cat4 = sv.act["cat2"], sv.act["cat3"], sv.act["cat4"]
     dcat2 = block_bwd("model.dec2", dd2, 0, 192, 64, True)
     dd3 = up_bwd(dcat2[:, 0:128], 1, 128)
     dcat3 = block_bwd("model.dec3", dd3, 1, 384, 128, True)
     dd4 = up_bwd(dcat3[:, 0:256], 2, 256)
     dcat4 = block_bwd("model.dec4", dd4, 2, 768, 256, True)
     de4 = up_bwd(dcat4[:, 0:512], 3, 512)
+    # encoder outputs fed the decoder (skip slice of the concat gradient) AND the max-pool (dp*): both gradients are summed
+    # inside the BN backward passes of the block's last layer
     dp3 = block_bwd("model.enc4", de4, 3, 256, 512, True)
-    pool_bwd_into(dp3, cat4[:, 512:768], dcat4[:, 512:768], 2, 256)
-    dp2 = block_bwd("model.enc3", dcat4[:, 512:768], 2, 128, 256, True)
-    pool_bwd_into(dp2, cat3[:, 256:384], dcat3[:, 256:384], 1, 128)
-    dp1 = block_bwd("model.enc2", dcat3[:, 256:384], 1, 64, 128, True)
-    pool_bwd_into(dp1, cat2[:, 128:192], dcat2[:, 128:192], 0, 64)
-    block_bwd("model.enc1", dcat2[:, 128:192], 0, 3, 64, False)
+    dp2 = block_bwd("model.enc3", dcat4[:, 512:768], 2, 128, 256, True, dpool=dp3)
+    dp1 = block_bwd("model.enc2", dcat3[:, 256:384], 1, 64, 128, True, dpool=dp2)
+    block_bwd("model.enc1", dcat2[:, 128:192], 0, 3, 64, False, dpool=dp1)
     return grads
 
 

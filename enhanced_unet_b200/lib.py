@@ -43,6 +43,8 @@ SIGNATURES = {
     "eunet_bn_apply_relu": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p],
     "eunet_bn_bwd_reduce": [_p, _i, _p, _i, _i, _ll, _i, _p, _p, _p, _p, _p, _p],
     "eunet_bn_bwd_apply": [_p, _i, _p, _i, _p, _i, _i, _ll, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "eunet_bn_bwd_reduce_pool": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p],
+    "eunet_bn_bwd_apply_pool": [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "eunet_maxpool2_fwd": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p],
     "eunet_maxpool2_bwd": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "eunet_upsample2_fwd": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p],

@@ -140,6 +140,17 @@ int eunet_bn_bwd_apply(const void* dact, int ldd, const void* y, int ldy, void* 
                        const float* scale, const float* shift, const float* mean, const float* invstd, const double* sums,
                        float* dgamma, float* dbeta, const float* gscale, void* stream);
 
+/* The same two passes for an encoder output that also feeds nn.MaxPool2d(2) (models.py:229-231): the gradient of the
+ * activation is dskip + route(dpool) (first maximum of every 2x2 window of the stored activations, ATen tie-break), formed on
+ * the fly from the RAW conv output y - no separate max-pool backward pass, no read-modify-write of the skip slice.
+ * dskip: [B,H,W,C] gradient from the decoder's concat slice; dpool: [B,H/2,W/2,C] gradient of the pooled tensor. */
+int eunet_bn_bwd_reduce_pool(const void* dskip, int ldd, const void* dpool, int ldp, const void* y, int ldy, int dtype, int B, int H,
+                             int W, int C, const float* scale, const float* shift, const float* mean, const float* invstd,
+                             double* sums, void* stream);
+int eunet_bn_bwd_apply_pool(const void* dskip, int ldd, const void* dpool, int ldp, const void* y, int ldy, void* dy, int lddy,
+                            int dtype, int B, int H, int W, int C, const float* scale, const float* shift, const float* mean,
+                            const float* invstd, const double* sums, float* dgamma, float* dbeta, const float* gscale, void* stream);
+
 /* ---- nn.MaxPool2d(2) (models.py:214) and nn.Upsample(x2, bilinear, align_corners=False) (models.py:215) ---- */
 int eunet_maxpool2_fwd(const void* x, int ldx, void* out, int ldo, int dtype, int B, int H, int W, int C, void* stream);
 /* dx (+)= route(dpool) to the first maximum of each 2x2 window (ATen tie-break) */

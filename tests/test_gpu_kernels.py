@@ -217,6 +217,49 @@ def test_bn_train_apply_pool_and_backward(k, dtn, C):
     assert nerr(got_eval, want_eval) < 1e-5
 
 
+@pytest.mark.parametrize("dtn", MODES)
+@pytest.mark.parametrize("case", [(2, 64, 8, 12), (1, 128, 6, 6), (2, 256, 4, 8), (3, 64, 2, 2)])
+def test_bn_backward_with_fused_maxpool_routing(k, dtn, case):
+    """bn_bwd_reduce_pool / bn_bwd_apply_pool: BN + ReLU backward of an encoder output whose gradient is
+    dskip + maxpool-backward(dpool), with the routing (first maximum of the fp32 activations, ATen tie-break) done inside the
+    two passes - against torch: max_pool2d indices of the activations, max_unpool2d, then autograd through
+    relu(batch_norm(y)).  The skip gradient is a channel slice of a wider buffer."""
+    B, C, H, W = case
+    dt = DT[dtn]
+    raw_dt = k.raw_dtype(dt)
+    g = torch.Generator().manual_seed(C + H)
+    y = torch.randn(B, C, H, W, generator=g) * 1.3 + 0.2
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.3
+    dskip = rnd(dtn, torch.randn(B, C, H, W, generator=g))
+    dpool = rnd(dtn, torch.randn(B, C, H // 2, W // 2, generator=g))
+    yr = y.to(raw_dt).float().requires_grad_(True)
+    gm, bt = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    act = F.relu(F.batch_norm(yr, None, None, gm, bt, True, 0.1, 1e-5))
+    _, idx = F.max_pool2d(act.detach(), 2, return_indices=True)      # first maximum of the fp32 activations (see PoolWindow::grads)
+    routed = F.max_unpool2d(dpool, idx, 2, output_size=(H, W))
+    (act * (dskip + routed)).sum().backward()
+    M = B * H * W
+    yd = nhwc(y, raw_dt)
+    mean = yr.detach().mean((0, 2, 3))
+    invstd = 1.0 / torch.sqrt(yr.detach().var((0, 2, 3), unbiased=False) + 1e-5)
+    scale, shift = (gamma * invstd).cuda(), (beta - mean * gamma * invstd).cuda()
+    mean_d, invstd_d = mean.cuda(), invstd.cuda()
+    dsd = nhwc(dskip, dt, ld=C + 16, off=8)
+    dpd = nhwc(dpool, dt)
+    sums = torch.zeros(2 * C, dtype=torch.float64, device="cuda")
+    code = k.dtype_code(dt)
+    k.call("eunet_bn_bwd_reduce_pool", dsd.data_ptr(), dsd.stride(0), dpd.data_ptr(), C, yd.data_ptr(), C, code, B, H, W, C,
+           scale.data_ptr(), shift.data_ptr(), mean_d.data_ptr(), invstd_d.data_ptr(), sums.data_ptr())
+    dy = torch.empty(M, C, dtype=dt, device="cuda")
+    dg, db = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    k.call("eunet_bn_bwd_apply_pool", dsd.data_ptr(), dsd.stride(0), dpd.data_ptr(), C, yd.data_ptr(), C, dy.data_ptr(), C, code, B, H, W,
+           C, scale.data_ptr(), shift.data_ptr(), mean_d.data_ptr(), invstd_d.data_ptr(), sums.data_ptr(), dg.data_ptr(), db.data_ptr(),
+           None)
+    torch.cuda.synchronize()
+    assert nerr(dg.cpu(), gm.grad) < 1e-4 and nerr(db.cpu(), bt.grad) < 1e-4
+    assert nerr(nchw(dy, B, H, W), yr.grad) < 2 * TOL[dtn]
+
+
 # ---------------------------------------------------------------------------------------------
 CONV_CASES = [
     # B, H, W, Cin, Cout
