@@ -39,24 +39,28 @@ struct TailBwdParams {
   int B, H, W;
   int blocks_x, blocks_y, items;
   uint32_t fmt16;     // operand format (d1p16, flipped filters, the dmid tile formed on chip): 1 = bf16, 0 = fp16
-  int dbg;            // timing experiments only (option "tail_dbg"): 1 skip transform, 2 skip wgrad MMAs, 4 skip U^T MMAs, 8 skip drain
+  int dbg;            // timing experiments only (option "tail_dbg"): 1 skip transform, 2 skip wgrad MMAs, 4 skip U^T MMAs, 8 skip drain,
+                      // 16 fp32 transform arithmetic in fp16 mode
 };
 int g_opt_tail_dbg = 0;
 
-constexpr int kTbStages = 4;
+constexpr int kTbStages = 5;
 constexpr int kTbMid = 184 * 128;            // 23552: mid / dmid halo tile slot (180 rows used)
 constexpr int kTbDout = 3072;                // 180 x 16 B
 constexpr int kTbX = 6144;                   // 180 x 32 B
 constexpr int kTbStage = kTbMid + kTbDout + kTbX;   // 32768
 constexpr int kTbSPitch = 188;
 constexpr int kTbSBytes = 27 * kTbSPitch * 4;
-constexpr int kTbWgCol = 192;                // first TMEM column of the wgrad accumulator (U^T uses [0, 184))
+constexpr int kTbUCols = 184;                // U^T accumulator: N = 184 halo rows; TWO of them at columns [0, 184) and [184, 368)
+constexpr int kTbWgCol = 368;                // first TMEM column of the wgrad accumulator (144 columns: 368 + 144 = 512 exactly)
 
+// HMATH (fp16 operands): the transform runs in packed half2 arithmetic, see the transform branch
+template <bool HMATH>
 __global__ void __launch_bounds__(576, 1)
 tail_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmMid, const __grid_constant__ CUtensorMap tmDout,
                       const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const TailBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t tma_full[kTbStages], xf_full[kTbStages], st_empty[kTbStages], acc_full, acc_empty, w_full, fin_bar;
+  __shared__ __align__(8) uint64_t tma_full[kTbStages], xf_full[kTbStages], st_empty[kTbStages], acc_full[2], acc_empty[2], w_full, fin_bar;
   __shared__ uint32_t tmem_base_s;
 
   const uint32_t sbase = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -72,8 +76,10 @@ tail_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmMid, const __grid_co
       tc::mbar_init(tc::smem_u32(&xf_full[s]), 12);
       tc::mbar_init(tc::smem_u32(&st_empty[s]), 1);
     }
-    tc::mbar_init(tc::smem_u32(&acc_full), 1);
-    tc::mbar_init(tc::smem_u32(&acc_empty), 4);
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(tc::smem_u32(&acc_full[s]), 1);
+      tc::mbar_init(tc::smem_u32(&acc_empty[s]), 4);
+    }
     tc::mbar_init(tc::smem_u32(&w_full), 1);
     tc::mbar_init(tc::smem_u32(&fin_bar), 1);
     tc::mbar_fence_init();
@@ -120,9 +126,8 @@ tail_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmMid, const __grid_co
         tc::mbar_wait(tc::smem_u32(&xf_full[s]), (it / kTbStages) & 1u);
         tc::tc_fence_after();
         const uint32_t t_addr = a_base + s * kTbStage, x_addr = t_addr + kTbMid + kTbDout;
-        // the 24 wgrad MMAs first: they accumulate into their own TMEM columns and do not depend on the drain warps, so they
-        // run while U^T of the previous tile is still being copied out (the single-buffered U^T used to serialise the MMA
-        // and drain stages: ~3000 clk per tile against ~950 clk of MMA work)
+        // the 24 wgrad MMAs accumulate into their own TMEM columns for the CTA's whole lifetime; U^T alternates between two
+        // accumulators so that the drain warps copy tile t out while tile t+1 is being multiplied
         if (!(p.dbg & 2))
 #pragma unroll
         for (int j = 0; j < 8; ++j) {      // K = 16 pixels = image rows 2j, 2j+1 of the tile = halo rows 2j+1, 2j+2 (columns 1..8)
@@ -133,16 +138,17 @@ tail_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmMid, const __grid_co
             tc::umma_bf16(tmem_base + kTbWgCol + dy * 48, adesc, bdesc, idesc_w, (it | j) != 0 ? 1u : 0u);
           }
         }
-        tc::mbar_wait(tc::smem_u32(&acc_empty), (it & 1u) ^ 1u);
+        const uint32_t ab = it & 1u;
+        tc::mbar_wait(tc::smem_u32(&acc_empty[ab]), ((it >> 1) & 1u) ^ 1u);
         tc::tc_fence_after();
         if (!(p.dbg & 4))
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint64_t adesc = tc::make_smem_desc(w_base + j * 32, 16, 1024, tc::kSwizzle128);
           const uint64_t bdesc = tc::make_smem_desc(t_addr + j * 32, 16, 1024, tc::kSwizzle128);
-          tc::umma_bf16(tmem_base, adesc, bdesc, idesc_u, j != 0 ? 1u : 0u);
+          tc::umma_bf16(tmem_base + ab * kTbUCols, adesc, bdesc, idesc_u, j != 0 ? 1u : 0u);
         }
-        tc::umma_commit(tc::smem_u32(&acc_full));
+        tc::umma_commit(tc::smem_u32(&acc_full[ab]));
         tc::umma_commit(tc::smem_u32(&st_empty[s]));
       }
       tc::umma_commit(tc::smem_u32(&fin_bar));
@@ -161,19 +167,20 @@ tail_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmMid, const __grid_co
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
       const int bx = item % p.blocks_x, by = (item / p.blocks_x) % p.blocks_y, b = item / (p.blocks_x * p.blocks_y);
       float* S = s_gen + (it & 1u) * (kTbSBytes / 4);
-      tc::mbar_wait(tc::smem_u32(&acc_full), it & 1u);
+      const uint32_t ab = it & 1u;
+      tc::mbar_wait(tc::smem_u32(&acc_full[ab]), (it >> 1) & 1u);
       tc::tc_fence_after();
       if (p.dbg & 8) {
         tc::tc_fence_before();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty));
+        if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[ab]));
         continue;
       }
 #pragma unroll 1
       for (int c = 0; c < 3; ++c) {
         const int col0 = e * 96 + c * 32;
         uint32_t raw[32];
-        tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, raw);
+        tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ab * kTbUCols + (uint32_t)col0, raw);
         tc::tmem_ld_wait();
         if (lane < 16 && row < 27) {
           float4* dst = reinterpret_cast<float4*>(S + row * kTbSPitch + col0);
@@ -187,7 +194,7 @@ tail_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmMid, const __grid_co
       }
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty));    // TMEM drained: the next U^T MMA set may start
+      if (lane == 0) tc::mbar_arrive(tc::smem_u32(&acc_empty[ab]));    // this accumulator is drained: tile t+2 may use it
       // everyone's part of U^T is in S[it & 1]; the other buffer was gathered by all four warps before they got here
       tc::named_bar_sync(1, 128);
       const int gx = bx * 8 + tx, gy = by * 16 + ty;
@@ -210,8 +217,40 @@ tail_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmMid, const __grid_co
     const int j = xt & 7, r0 = xt >> 3;        // 16-byte chunk (channels 8j..8j+7) and first halo row (0..47) of this thread
     // dmid = A + Bc v + [sc v + sh > 0] sum_k g_k (sc w3_k) with A = -sc (k1 - k2 invstd mean), Bc = -sc k2 invstd:
     // 7 constants per channel (56 registers), 7 instructions per element
-    float sc[8], sh[8], A[8], Bc[8], ws[3][8];
-    {
+    // HMATH: the same expression on channel PAIRS in half2 arithmetic (v is fp16 already, the result is stored as fp16):
+    //     dmid2 = fma(m2, S2, fma(Bc2, v2, A2)),  S2 = g0 ws0 + g1 ws1 + g2 ws2 (3 HFMA2),  m2 = [(v2 ^ sgn) > thr] in {0, 1}
+    // = 3.5 instructions per element.  The ReLU mask stays EXACT: sc v + sh > 0 <=> sigma v > sigma tau, tau = -sh / sc,
+    // sigma = sign(sc), and for an fp16 v that is v' > rd(sigma tau) with rd = the largest fp16 not above (a compare, no
+    // arithmetic); only the addends are rounded to fp16 (2^-11 relative, like the stored result itself).
+    float sc[HMATH ? 1 : 8], sh[HMATH ? 1 : 8], A[HMATH ? 1 : 8], Bc[HMATH ? 1 : 8], ws[3][HMATH ? 1 : 8];
+    __half2 hA[HMATH ? 4 : 1], hBc[HMATH ? 4 : 1], hws[3][HMATH ? 4 : 1], hthr[HMATH ? 4 : 1];
+    uint32_t hsgn[HMATH ? 4 : 1];
+    if constexpr (HMATH) {
+      const F8 a = load8(p.scale + j * 8), b = load8(p.shift + j * 8), m = load8(p.mean + j * 8), is = load8(p.invstd + j * 8);
+      const F8 w0 = load8(p.w3 + j * 8), w1 = load8(p.w3 + 64 + j * 8), w2 = load8(p.w3 + 128 + j * 8);
+      float fA[8], fBc[8], thr[8];
+      uint32_t sg[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float k1 = (float)(p.acc[j * 8 + e] / (double)M), k2 = (float)(p.acc[64 + j * 8 + e] / (double)M);
+        fBc[e] = -a.v[e] * k2 * is.v[e];
+        fA[e] = -a.v[e] * k1 - fBc[e] * m.v[e];
+        const float s_ = a.v[e], h_ = b.v[e];
+        sg[e] = s_ < 0.f ? 0x8000u : 0u;
+        // sigma tau rounded DOWN twice (division, conversion): the largest fp16 not above it; sc = 0: constant mask
+        thr[e] = s_ == 0.f ? (h_ > 0.f ? -INFINITY : INFINITY) : __fdiv_rd(-h_, fabsf(s_));
+      }
+#pragma unroll
+      for (int e2 = 0; e2 < 4; ++e2) {
+        hA[e2] = __floats2half2_rn(fA[2 * e2], fA[2 * e2 + 1]);
+        hBc[e2] = __floats2half2_rn(fBc[2 * e2], fBc[2 * e2 + 1]);
+        hws[0][e2] = __floats2half2_rn(w0.v[2 * e2] * a.v[2 * e2], w0.v[2 * e2 + 1] * a.v[2 * e2 + 1]);
+        hws[1][e2] = __floats2half2_rn(w1.v[2 * e2] * a.v[2 * e2], w1.v[2 * e2 + 1] * a.v[2 * e2 + 1]);
+        hws[2][e2] = __floats2half2_rn(w2.v[2 * e2] * a.v[2 * e2], w2.v[2 * e2 + 1] * a.v[2 * e2 + 1]);
+        hthr[e2] = __halves2half2(__float2half_rd(thr[2 * e2]), __float2half_rd(thr[2 * e2 + 1]));
+        hsgn[e2] = sg[2 * e2] | (sg[2 * e2 + 1] << 16);
+      }
+    } else {
       const F8 a = load8(p.scale + j * 8), b = load8(p.shift + j * 8), m = load8(p.mean + j * 8), is = load8(p.invstd + j * 8);
       const F8 w0 = load8(p.w3 + j * 8), w1 = load8(p.w3 + 64 + j * 8), w2 = load8(p.w3 + 128 + j * 8);
 #pragma unroll
@@ -250,6 +289,23 @@ tail_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmMid, const __grid_co
       float g0, g1, g2, gpad;
       asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(g0), "=f"(g1), "=f"(g2), "=f"(gpad) : "r"(d_addr + (uint32_t)(r * 16)));
       const uint32_t hw[4] = {h0, h1, h2, h3};
+      if constexpr (HMATH) {
+        const __half2 q0 = __float2half2_rn(g0), q1 = __float2half2_rn(g1), q2 = __float2half2_rn(g2);
+        const __half2 one = __float2half2_rn(1.f);
+        uint32_t u[4];
+#pragma unroll
+        for (int e2 = 0; e2 < 4; ++e2) {
+          const __half2 v = *reinterpret_cast<const __half2*>(&hw[e2]);
+          const uint32_t vx = hw[e2] ^ hsgn[e2];
+          const __half2 msk = __hgt2(*reinterpret_cast<const __half2*>(&vx), hthr[e2]);      // 1.0 / 0.0 per channel
+          const __half2 S = __hfma2(q2, hws[2][e2], __hfma2(q1, hws[1][e2], __hmul2(q0, hws[0][e2])));
+          const __half2 o2 = __hfma2(msk, S, __hfma2(hBc[e2], v, hA[e2]));
+          u[e2] = inb ? *reinterpret_cast<const uint32_t*>(&o2) : 0u;      // the transposed convolution's boundary condition
+        }
+        (void)one; (void)gpad;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(t_addr + off[k]), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]) : "memory");
+        return;
+      }
       float o[8];
 #pragma unroll
       for (int e2 = 0; e2 < 4; ++e2) {
@@ -356,11 +412,13 @@ extern "C" int eunet_tail_bwd_fused(const float* dout4, const void* mid_raw, con
     if (tc::encode_tensor_map_bf16(&tmW, w_packed_flip, 2, dims, str, box, 128)) return -1;
   }
   constexpr int SMEM = 1024 + 8192 + kTbStages * kTbStage + 2 * kTbSBytes;
+  const bool hmath = p.fmt16 == 0u && !(g_opt_tail_dbg & 16);     // option tail_dbg bit 16: fp32 transform in fp16 mode (A/B)
+  auto kern = hmath ? tail_bwd_fused_kernel<true> : tail_bwd_fused_kernel<false>;
   {   // set on every launch: the attribute is per device, and a process may drive more than one GPU
-    cudaError_t e = cudaFuncSetAttribute(tail_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     EUNET_REQUIRE(e == cudaSuccess, "tail_bwd_fused: cudaFuncSetAttribute(%d): %s", SMEM, cudaGetErrorString(e));
   }
   const int grid = p.items < kNumSMs ? p.items : kNumSMs;
-  tail_bwd_fused_kernel<<<grid, 576, SMEM, (cudaStream_t)stream>>>(tmMid, tmDout, tmX, tmW, p);
+  kern<<<grid, 576, SMEM, (cudaStream_t)stream>>>(tmMid, tmDout, tmX, tmW, p);
   return check_launch("tail_bwd_fused");
 }

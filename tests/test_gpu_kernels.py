@@ -487,7 +487,7 @@ def test_conv3x3_tail_fwd_fused_epilogue(k, shape, store_mid, dtn):
 def test_tail_bwd_fused_matches_separate_kernels(k, shape, dtn):
     """eunet_tail_bwd_fused (BN/ReLU backward formed on chip + wgrad + 3-channel transposed dgrad of enhance.0 from one staged
     tile) against the three separate kernels it replaces (tail_bwd_dmid -> conv3x3_wgrad / conv3x3_dgrad_few), which are
-    themselves pinned against torch; the bf16 dmid is bit-identical in both, only fp32 summation order differs."""
+    themselves pinned against torch."""
     B, H2, W2 = shape
     M = B * H2 * W2
     dt, code = DT[dtn], k.dtype_code(DT[dtn])
@@ -524,8 +524,23 @@ def test_tail_bwd_fused_matches_separate_kernels(k, shape, dtn):
            shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), w3.data_ptr(), acc.data_ptr(), dx.data_ptr(), dw.data_ptr(), code,
            B, H2, W2)
     torch.cuda.synchronize()
-    assert nerr(dx, dx_ref) < 2e-5, nerr(dx, dx_ref)
-    assert nerr(dw, dw_ref) < 2e-5, nerr(dw, dw_ref)
+    # bf16 operands: the dmid formed on chip is bit-identical to tail_bwd_dmid's, only fp32 summation order differs.
+    # fp16 operands: the fused kernel forms dmid in packed half2 arithmetic (exact ReLU mask, addends rounded to fp16):
+    # measured 5e-4 .. 6e-4 against the fp32-then-round dmid of the separate kernel
+    tol = 2e-5 if dtn == "bf16" else 2e-3
+    assert nerr(dx, dx_ref) < tol, nerr(dx, dx_ref)
+    assert nerr(dw, dw_ref) < tol, nerr(dw, dw_ref)
+    if dtn == "fp16":
+        k.set_option("tail_dbg", 16)          # fp32 transform arithmetic: bit-identical dmid again
+        try:
+            dw.zero_()
+            k.call("eunet_tail_bwd_fused", dout4.data_ptr(), mid.data_ptr(), d1p.data_ptr(), wflip.data_ptr(), scale.data_ptr(),
+                   shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), w3.data_ptr(), acc.data_ptr(), dx.data_ptr(), dw.data_ptr(),
+                   code, B, H2, W2)
+            torch.cuda.synchronize()
+        finally:
+            k.set_option("tail_dbg", 0)
+        assert nerr(dx, dx_ref) < 2e-5 and nerr(dw, dw_ref) < 2e-5, (nerr(dx, dx_ref), nerr(dw, dw_ref))
 
 
 @pytest.mark.parametrize("dtn", ["bf16", "fp16", "fp32"])
