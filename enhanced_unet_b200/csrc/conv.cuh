@@ -21,6 +21,8 @@ int conv3x3_fwd_halo2(const void* x, int ldx, const void* w, void* y, int ldy, i
                       const float* scale, const float* shift, int relu, int out_raw, int f16, float* amax, cudaStream_t st);
 extern int g_opt_cta_pair;    // 0 (default): never; 1: N = 128 tiles; 2: N = 128 and N = 64 tiles
 extern int g_opt_conv_halo;   // 1 (default): use the halo kernel where it applies
+extern int g_opt_bn192;       // 0 (default): never; 1: N = 192 tiles for Cout = 192 (dgrad of dec2.0); 2: also Cout = 384
+extern int g_opt_a_ahead;     // 1 (default): halo kernel requests activation tiles ahead of the filter ring (A/B switch)
 extern int g_opt_tma_store;   // 1 (default): Cout = 64 halo kernels write their output tile with a TMA tensor store
 
 // Power-of-two (bw, bh, bb) with bw*bh*bb == pixels minimising the number of tiles over a [B,H,W] image batch.

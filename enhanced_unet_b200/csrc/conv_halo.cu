@@ -33,6 +33,7 @@ struct ConvHaloParams {
   int relu;
   int out_f16;
   uint32_t fmt16;     // tensor-core operand format of x and w: 1 = bf16, 0 = fp16
+  int a_ahead;        // option a_ahead (default 1): halo tiles are requested as soon as their slot is free (0: after the previous chunk's last tap)
   float* amax;        // fp16 outputs: atomicMax of |y| over the stored values when it exceeds the fp16 range (may be NULL)
   // EPI = 1 (fused 2Hx2W tail, reference models.py:310-313 + 337): out = d14 + b3 + W3 . relu(acc * scale + shift)
   const float* w3;    // [3][64]
@@ -65,8 +66,8 @@ struct HaloCfg {
   static constexpr int NACC = (2 * MT * BN <= 512) ? 2 : 1;
   static constexpr int TMEM_NEED = NACC * MT * BN;
   static constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
-  static constexpr int ASTAGES = (KC == 16 || BN == 128) ? 3 : 2;      // BN = 128: a third 44 KB halo slot (384 -> 128 at H/2: +12 %)
-  static constexpr int BSTAGES = WRES ? 0 : (BN >= 128 ? 4 : 6);
+  static constexpr int ASTAGES = (KC == 16 || BN == 128 || BN == 192) ? 3 : 2;      // BN = 128: a third 44 KB halo slot (384 -> 128 at H/2: +12 %)
+  static constexpr int BSTAGES = WRES ? 0 : (BN == 192 ? 6 : BN >= 128 ? 4 : 6);   // BN = 192: 6 x 24 KB filter taps in flight
   static constexpr int CH = BN >= 32 ? 32 : 16;
   static constexpr int NCHUNK = BN / CH;
   // TST: the epilogue stages an item's output tile in shared memory (128-byte swizzled rows = one pixel's BN = 64
@@ -137,19 +138,33 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           for (int tap = 0; tap < 9; ++tap)
             tc::tma_load_2d(b_base + (cc * 9 + tap) * C::B_BYTES, &tmW, wb, tap * p.Cin + cc * KC, n0);
       }
-      uint32_t a_it = 0, b_it = 0;
+      // The halo tiles run AHEAD of the filter taps: this one thread issues both streams, and a tile issued only after the last
+      // tap of the previous chunk (which itself waits for a ring slot) would be requested just BSTAGES taps before the MMA
+      // warp needs it - less than its load time for the 44 / 85 KB tiles (ncu, 192 -> 64 at H: tensor pipe 46 % busy against the
+      // 67 % the shared-memory port allows).  So before every tap the next tile is issued as soon as its slot is free
+      // (non-blocking probe), i.e. up to a whole chunk early.
+      uint32_t a_it = 0, b_it = 0, a_need = 0;
+      int a_item = blockIdx.y, a_cc = 0;
+      auto issue_a = [&](bool block) {
+        if (a_item >= p.items) return;
+        const uint32_t s = a_it % AS;
+        const uint32_t eb = tc::smem_u32(&a_empty[s]), par = ((a_it / AS) & 1u) ^ 1u;
+        if (block) tc::mbar_wait(eb, par);
+        else if (!tc::mbar_test(eb, par)) return;
+        const int bx = a_item % p.blocks_x, by = (a_item / p.blocks_x) % p.blocks_y, b = a_item / (p.blocks_x * p.blocks_y);
+        const uint32_t fb = tc::smem_u32(&a_full[s]);
+        tc::mbar_expect_tx(fb, C::A_BYTES);
+        tc::tma_load_4d(a_base + s * C::A_SLOT, &tmX, fb, a_cc * KC, bx * 8 - 1, by * (16 * MT) - 1, b);
+        ++a_it;
+        if (++a_cc == cchunks) { a_cc = 0; a_item += gridDim.y; }
+      };
       for (int item = blockIdx.y; item < p.items; item += gridDim.y) {
-        const int bx = item % p.blocks_x, by = (item / p.blocks_x) % p.blocks_y, b = item / (p.blocks_x * p.blocks_y);
-        const int x0 = bx * 8, y0 = by * (16 * MT);
         for (int cc = 0; cc < cchunks; ++cc) {
-          const uint32_t s = a_it % AS;
-          tc::mbar_wait(tc::smem_u32(&a_empty[s]), ((a_it / AS) & 1u) ^ 1u);
-          const uint32_t fb = tc::smem_u32(&a_full[s]);
-          tc::mbar_expect_tx(fb, C::A_BYTES);
-          tc::tma_load_4d(a_base + s * C::A_SLOT, &tmX, fb, cc * KC, x0 - 1, y0 - 1, b);
-          ++a_it;
+          while (a_it <= a_need) issue_a(true);       // this chunk's tile is in flight before its filter taps
+          ++a_need;
           if (!WRES) {
             for (int tap = 0; tap < 9; ++tap) {
+              if (p.a_ahead && a_it < a_need + AS - 1) issue_a(false);
               const uint32_t sb = b_it % BS;
               tc::mbar_wait(tc::smem_u32(&b_empty[sb]), ((b_it / BS) & 1u) ^ 1u);
               const uint32_t bb = tc::smem_u32(&b_full[sb]);
@@ -475,7 +490,7 @@ int conv3x3_fwd_halo_bf16(const void* x, int ldx, const void* w, void* y, int ld
   p.y = y; p.ldy = ldy; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.blocks_x = p.blocks_y = p.items = 0;
   p.stats = stats; p.scale = scale; p.shift = shift; p.relu = relu; p.out_f16 = (out_raw || f16) ? 1 : 0;
-  p.fmt16 = f16 ? 0u : 1u; p.amax = amax;
+  p.fmt16 = f16 ? 0u : 1u; p.amax = amax; p.a_ahead = g_opt_a_ahead;
   p.w3 = p.b3 = p.d14 = nullptr; p.out = nullptr;
   if (H < 8 || W < 8) return 1;
   if (y == nullptr && !(Cin == 16 && Cout == 64)) return 1;   // statistics-only pass: only the 16 -> 64 kernel skips stores           // tiny images: the batch-folding per-tap kernel wastes less
@@ -485,6 +500,12 @@ int conv3x3_fwd_halo_bf16(const void* x, int ldx, const void* w, void* y, int ld
       // epilogue overlaps the next item's MMAs; without statistics (dgrad) the per-tap kernel is already at ~0.85 of peak
       return launch_halo<64, 256, 1, false>(x, ldx, w, p, st);
     }
+    // N = 192 (option bn192, off by default; dgrad of dec2.0: 64 -> 192 channels, = 2 also dgrad of dec3.0, 384 = 2 x 192):
+    // a 128 x 64 x 16 MMA reads 6 KB of operands in 32 tensor clocks - bound by the 128 B/clk shared-memory port at 2/3 of
+    // peak - while 128 x 192 x 16 reads 10 KB in 96.  Measured SLOWER all the same (1.37 vs 1.16 ms): with one 128-pixel
+    // tile per item the 48 KB of output go out as per-thread 16-byte stores (32 lines per warp instruction), where the three
+    // N = 64 CTAs use the TMA-store epilogue; a staged epilogue for N = 192 does not fit beside the filter ring.
+    if (g_opt_bn192 >= 1 && Cout % 192 == 0 && (Cout % 128 != 0 || g_opt_bn192 >= 2)) return launch_halo<64, 192, 1, false>(x, ldx, w, p, st);
     if (Cout % 128 == 0) return launch_halo<64, 128, 2, false>(x, ldx, w, p, st);
     if (Cout % 64 == 0) {
       if (Cin == 64) return g_opt_tma_store ? launch_halo<64, 64, 2, true, true>(x, ldx, w, p, st)
@@ -508,7 +529,7 @@ int conv3x3_tail_fwd_bf16(const void* x16, const void* w, void* mid, const float
   p.y = mid; p.ldy = 64; p.B = B; p.H = H; p.W = W; p.Cin = 16; p.Cout = 64;
   p.blocks_x = p.blocks_y = p.items = 0;
   p.stats = nullptr; p.scale = scale; p.shift = shift; p.relu = 0; p.out_f16 = 1;
-  p.fmt16 = f16 ? 0u : 1u; p.amax = nullptr;
+  p.fmt16 = f16 ? 0u : 1u; p.amax = nullptr; p.a_ahead = g_opt_a_ahead;
   p.w3 = w3; p.b3 = b3; p.d14 = d14; p.out = out;
   if (H < 8 || W < 8) return 1;
   if (mid != nullptr) return launch_halo<16, 64, 4, true, true, 1>(x16, 16, w, p, st);

@@ -24,6 +24,8 @@ namespace eunet {
 int g_opt_conv_halo = 1;
 int g_opt_cta_pair = 0;   // measured slower than the single-CTA kernels (see conv_halo2.cu): kept as an option
 int g_opt_tma_store = 1;
+int g_opt_bn192 = 0;      // measured slower than three N = 64 tiles with the TMA-store epilogue (1.37 vs 1.16 ms, dgrad of dec2.0)
+int g_opt_a_ahead = 1;
 extern int g_opt_tail_dbg;       // conv_tail_bwd.cu: timing experiments only
 extern int g_opt_tail_out_tma;   // tail.cu: 1 (default) = TMA-pipelined tail_out_fwd
 extern int g_opt_bn_tma;         // elementwise.cu: 1 (default) = TMA-pipelined bn_apply_relu
@@ -527,6 +529,14 @@ extern "C" int eunet_set_option(const char* name, int value) {
   }
   if (strcmp(name, "tail_out_tma") == 0) {
     g_opt_tail_out_tma = value;
+    return 0;
+  }
+  if (strcmp(name, "a_ahead") == 0) {
+    g_opt_a_ahead = value;
+    return 0;
+  }
+  if (strcmp(name, "bn192") == 0) {
+    g_opt_bn192 = value;
     return 0;
   }
   if (strcmp(name, "tma_store") == 0) {

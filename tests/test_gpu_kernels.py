@@ -328,6 +328,36 @@ def test_conv3x3_fwd_stats_and_epilogue(k, dtn, case):
     assert nerr(nchw(y2, B, H, W), want2) < TOL[dtn]
 
 
+@pytest.mark.parametrize("opt", [("bn192", 1, (2, 32, 40, 64, 192)), ("bn192", 2, (1, 24, 40, 128, 384)),
+                                 ("a_ahead", 0, (2, 48, 40, 192, 64)), ("a_ahead", 0, (1, 64, 64, 128, 128))])
+def test_conv3x3_alternative_configurations(k, opt):
+    """The A/B switches of the halo kernel compute the same convolution: N = 192 tiles (off by default, measured slower) and
+    the activation-tile prefetch order (a_ahead = 0: tiles requested after the previous chunk's last filter tap)."""
+    name, value, (B, H, W, Cin, Cout) = opt
+    g = torch.Generator().manual_seed(Cin + Cout)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)
+    want = _conv_ref(rnd("fp16", x), rnd("fp16", w))
+    xd = nhwc(x, torch.float16)
+    wp = torch.empty(Cout, 9, Cin, dtype=torch.float16, device="cuda")
+    k.call("eunet_pack_weight3x3", w.cuda().data_ptr(), wp.data_ptr(), k.F16, Cout, Cin, Cout, Cin, 0)
+    ys = []
+    for v in (value, 1 - value if name == "a_ahead" else 0):
+        k.set_option(name, v)
+        try:
+            y = torch.empty(B * H * W, Cout, dtype=torch.float16, device="cuda")
+            stats = torch.zeros(2 * Cout, dtype=torch.float64, device="cuda")
+            k.call("eunet_conv3x3_fwd", xd.data_ptr(), Cin, wp.data_ptr(), y.data_ptr(), Cout, k.F16, B, H, W, Cin, Cout,
+                   stats.data_ptr(), None, None, 0, 0, None)
+            torch.cuda.synchronize()
+        finally:
+            k.set_option(name, {"bn192": 0, "a_ahead": 1}[name])
+        assert nerr(nchw(y, B, H, W), want) < TOL["fp16"]
+        assert nerr(stats[:Cout].cpu(), want.double().sum((0, 2, 3))) < 1e-4
+        ys.append(y)
+    assert nerr(ys[0].float(), ys[1].float()) < 1e-3          # same products, at most a different accumulation order
+
+
 @pytest.mark.parametrize("dtn", ["fp32", "bf16", "bf16-pertap", "fp16", "fp16-pertap"])
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv3x3_dgrad_and_wgrad(k, dtn, case):
