@@ -246,6 +246,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const int ty = r >> 3, tx = r & 7;
       const bool want_stats = p.stats != nullptr, affine = EPI == 0 && p.scale != nullptr, do_store = p.y != nullptr;
       const bool want_amax = p.amax != nullptr && p.out_f16 != 0;
+      // every 32-channel chunk of every pixel row starts on a 32-byte boundary (channel-slice views of a wider buffer qualify
+      // when their offset and leading dimension are multiples of 16 elements)
+      const bool wide = !TST && (reinterpret_cast<uintptr_t>(p.y) & 31) == 0 && (p.ldy & 15) == 0;
       float amax = 0.f;
       double tot1[NCW], tot2[NCW];
 #pragma unroll
@@ -273,97 +276,123 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         tc::tc_fence_after();
         const int gx = bx * 8 + tx;
         float part[EPI ? MT : 1][3];
-#pragma unroll
-        for (int cw = 0; cw < NCW; ++cw) {
+        // The T = NCW x MT accumulator chunks of an item are drained through TWO register buffers: the TMEM load of chunk t+1 is
+        // in flight while chunk t is converted and stored (one buffer: every chunk paid the load latency in full, and the
+        // K = 576 layers - 4608 MMA clocks per item - were bound by this loop: ncu tc pipe 43-65 % busy).
+        auto issue = [&](int cw, int mt, uint32_t (&raw)[32]) {
           const int c0 = ((C::NCHUNK >= 2) ? 2 * cw + half : 0) * CH;
-#pragma unroll 1
-          for (int mt = 0; mt < MT; ++mt) {
-            const int gy = by * (16 * MT) + 16 * mt + ty;
-            const bool valid = gx < p.W && gy < p.H;
-            uint32_t raw[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((ab * MT + mt) * BN + c0);
-            if (CH == 32) tc::tmem_ld32(taddr, raw);
-            else {
-              tc::tmem_ld16(taddr, raw);
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((ab * MT + mt) * BN + c0);
+          if (CH == 32) tc::tmem_ld32(taddr, raw);
+          else {
+            tc::tmem_ld16(taddr, raw);
 #pragma unroll
-              for (int i = 16; i < 32; ++i) raw[i] = 0u;
+            for (int i = 16; i < 32; ++i) raw[i] = 0u;
+          }
+        };
+        auto process = [&](int cw, int mt, uint32_t (&raw)[32]) {
+          const int c0 = ((C::NCHUNK >= 2) ? 2 * cw + half : 0) * CH;
+          const int gy = by * (16 * MT) + 16 * mt + ty;
+          const bool valid = gx < p.W && gy < p.H;
+          if (want_stats && valid) {
+#pragma unroll
+            for (int i = 0; i < CH / 2; ++i) {
+              const uint64_t v = tc::pack_f32x2(raw[2 * i], raw[2 * i + 1]);
+              run1[i] = tc::add_f32x2(run1[i], v);
+              run2[i] = tc::fma_f32x2(v, v, run2[i]);
             }
-            tc::tmem_ld_wait();
-            if (want_stats && valid) {
+          }
+          if (EPI == 1) {
+            // this warp's 32 channels of relu(bn(acc)) . W3 for the pixel of this thread
+            float t0 = 0.f, t1 = 0.f, t2 = 0.f, u0 = 0.f, u1 = 0.f, u2 = 0.f;     // two chains per class (ILP)
 #pragma unroll
-              for (int i = 0; i < CH / 2; ++i) {
-                const uint64_t v = tc::pack_f32x2(raw[2 * i], raw[2 * i + 1]);
-                run1[i] = tc::add_f32x2(run1[i], v);
-                run2[i] = tc::fma_f32x2(v, v, run2[i]);
+            for (int i = 0; i < CH; i += 4) {
+              const float4 sc = *reinterpret_cast<const float4*>(&s_scale[c0 + i]), sh = *reinterpret_cast<const float4*>(&s_shift[c0 + i]);
+              const float4 w0 = *reinterpret_cast<const float4*>(&s_w3[c0 + i]), w1 = *reinterpret_cast<const float4*>(&s_w3[BN + c0 + i]);
+              const float4 w2 = *reinterpret_cast<const float4*>(&s_w3[2 * BN + c0 + i]);
+              const float a0 = fmaxf(fmaf(__uint_as_float(raw[i]), sc.x, sh.x), 0.f), a1 = fmaxf(fmaf(__uint_as_float(raw[i + 1]), sc.y, sh.y), 0.f);
+              const float a2 = fmaxf(fmaf(__uint_as_float(raw[i + 2]), sc.z, sh.z), 0.f), a3 = fmaxf(fmaf(__uint_as_float(raw[i + 3]), sc.w, sh.w), 0.f);
+              t0 = fmaf(a2, w0.z, fmaf(a0, w0.x, t0)); u0 = fmaf(a3, w0.w, fmaf(a1, w0.y, u0));
+              t1 = fmaf(a2, w1.z, fmaf(a0, w1.x, t1)); u1 = fmaf(a3, w1.w, fmaf(a1, w1.y, u1));
+              t2 = fmaf(a2, w2.z, fmaf(a0, w2.x, t2)); u2 = fmaf(a3, w2.w, fmaf(a1, w2.y, u2));
+            }
+            t0 += u0; t1 += u1; t2 += u2;
+            part[EPI ? mt : 0][0] = t0; part[EPI ? mt : 0][1] = t1; part[EPI ? mt : 0][2] = t2;
+          }
+          if (do_store && (TST || valid)) {
+            uint32_t dst_s = 0;
+            uint16_t* dst_g = nullptr;
+            if (TST) {   // every row is staged (rows outside the image are clipped by the tensor store)
+              dst_s = stg_base + (li & 1u) * C::STG_BYTES + (uint32_t)((mt * 128 + r) * 128);
+            } else {
+              const long long pix = ((long long)b * p.H + gy) * p.W + gx;
+              dst_g = reinterpret_cast<uint16_t*>(p.y) + pix * p.ldy + n0 + c0;
+            }
+            uint4 held = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int g8 = 0; g8 < CH / 8; ++g8) {
+              float o[8];
+#pragma unroll
+              for (int ee = 0; ee < 8; ++ee) o[ee] = __uint_as_float(raw[g8 * 8 + ee]);
+              if (affine) {
+#pragma unroll
+                for (int h4 = 0; h4 < 2; ++h4) {
+                  const float4 sc = *reinterpret_cast<const float4*>(&s_scale[c0 + g8 * 8 + h4 * 4]);
+                  const float4 sh = *reinterpret_cast<const float4*>(&s_shift[c0 + g8 * 8 + h4 * 4]);
+                  o[h4 * 4 + 0] = fmaf(o[h4 * 4 + 0], sc.x, sh.x); o[h4 * 4 + 1] = fmaf(o[h4 * 4 + 1], sc.y, sh.y);
+                  o[h4 * 4 + 2] = fmaf(o[h4 * 4 + 2], sc.z, sh.z); o[h4 * 4 + 3] = fmaf(o[h4 * 4 + 3], sc.w, sh.w);
+                }
               }
-            }
-            if (EPI == 1) {
-              // this warp's 32 channels of relu(bn(acc)) . W3 for the pixel of this thread
-              float t0 = 0.f, t1 = 0.f, t2 = 0.f, u0 = 0.f, u1 = 0.f, u2 = 0.f;     // two chains per class (ILP)
+              if (p.relu) {
 #pragma unroll
-              for (int i = 0; i < CH; i += 4) {
-                const float4 sc = *reinterpret_cast<const float4*>(&s_scale[c0 + i]), sh = *reinterpret_cast<const float4*>(&s_shift[c0 + i]);
-                const float4 w0 = *reinterpret_cast<const float4*>(&s_w3[c0 + i]), w1 = *reinterpret_cast<const float4*>(&s_w3[BN + c0 + i]);
-                const float4 w2 = *reinterpret_cast<const float4*>(&s_w3[2 * BN + c0 + i]);
-                const float a0 = fmaxf(fmaf(__uint_as_float(raw[i]), sc.x, sh.x), 0.f), a1 = fmaxf(fmaf(__uint_as_float(raw[i + 1]), sc.y, sh.y), 0.f);
-                const float a2 = fmaxf(fmaf(__uint_as_float(raw[i + 2]), sc.z, sh.z), 0.f), a3 = fmaxf(fmaf(__uint_as_float(raw[i + 3]), sc.w, sh.w), 0.f);
-                t0 = fmaf(a2, w0.z, fmaf(a0, w0.x, t0)); u0 = fmaf(a3, w0.w, fmaf(a1, w0.y, u0));
-                t1 = fmaf(a2, w1.z, fmaf(a0, w1.x, t1)); u1 = fmaf(a3, w1.w, fmaf(a1, w1.y, u1));
-                t2 = fmaf(a2, w2.z, fmaf(a0, w2.x, t2)); u2 = fmaf(a3, w2.w, fmaf(a1, w2.y, u2));
+                for (int ee = 0; ee < 8; ++ee) o[ee] = fmaxf(o[ee], 0.f);
               }
-              t0 += u0; t1 += u1; t2 += u2;
-              part[EPI ? mt : 0][0] = t0; part[EPI ? mt : 0][1] = t1; part[EPI ? mt : 0][2] = t2;
-            }
-            if (do_store && (TST || valid)) {
-              uint32_t dst_s = 0;
-              uint16_t* dst_g = nullptr;
-              if (TST) {   // every row is staged (rows outside the image are clipped by the tensor store)
-                dst_s = stg_base + (li & 1u) * C::STG_BYTES + (uint32_t)((mt * 128 + r) * 128);
+              if (want_amax) {
+#pragma unroll
+                for (int ee = 0; ee < 8; ++ee) amax = fmaxf(amax, fabsf(o[ee]));
+              }
+              uint4 u;
+              if (p.out_f16) {
+                u.x = tc::cvt_f16x2_sat(o[0], o[1]); u.y = tc::cvt_f16x2_sat(o[2], o[3]);
+                u.z = tc::cvt_f16x2_sat(o[4], o[5]); u.w = tc::cvt_f16x2_sat(o[6], o[7]);
               } else {
-                const long long pix = ((long long)b * p.H + gy) * p.W + gx;
-                dst_g = reinterpret_cast<uint16_t*>(p.y) + pix * p.ldy + n0 + c0;
+                u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]); u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
               }
-#pragma unroll
-              for (int g8 = 0; g8 < CH / 8; ++g8) {
-                float o[8];
-#pragma unroll
-                for (int ee = 0; ee < 8; ++ee) o[ee] = __uint_as_float(raw[g8 * 8 + ee]);
-                if (affine) {
-#pragma unroll
-                  for (int h4 = 0; h4 < 2; ++h4) {
-                    const float4 sc = *reinterpret_cast<const float4*>(&s_scale[c0 + g8 * 8 + h4 * 4]);
-                    const float4 sh = *reinterpret_cast<const float4*>(&s_shift[c0 + g8 * 8 + h4 * 4]);
-                    o[h4 * 4 + 0] = fmaf(o[h4 * 4 + 0], sc.x, sh.x); o[h4 * 4 + 1] = fmaf(o[h4 * 4 + 1], sc.y, sh.y);
-                    o[h4 * 4 + 2] = fmaf(o[h4 * 4 + 2], sc.z, sh.z); o[h4 * 4 + 3] = fmaf(o[h4 * 4 + 3], sc.w, sh.w);
-                  }
-                }
-                if (p.relu) {
-#pragma unroll
-                  for (int ee = 0; ee < 8; ++ee) o[ee] = fmaxf(o[ee], 0.f);
-                }
-                if (want_amax) {
-#pragma unroll
-                  for (int ee = 0; ee < 8; ++ee) amax = fmaxf(amax, fabsf(o[ee]));
-                }
-                uint4 u;
-                if (p.out_f16) {
-                  u.x = tc::cvt_f16x2_sat(o[0], o[1]); u.y = tc::cvt_f16x2_sat(o[2], o[3]);
-                  u.z = tc::cvt_f16x2_sat(o[4], o[5]); u.w = tc::cvt_f16x2_sat(o[6], o[7]);
-                } else {
-                  u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]); u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
-                }
-                if (TST) {
-                  const uint32_t chunk = (uint32_t)(c0 / 8 + g8);
-                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst_s + ((chunk ^ (uint32_t)(r & 7)) << 4)),
-                               "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w)
+              if (TST) {
+                const uint32_t chunk = (uint32_t)(c0 / 8 + g8);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst_s + ((chunk ^ (uint32_t)(r & 7)) << 4)),
+                             "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w)
+                             : "memory");
+              } else if (wide && CH == 32) {
+                // 32-byte stores (STG.256): a lane writes whole 32-byte sectors, half as many store instructions
+                if (g8 & 1) {
+                  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst_g + (g8 - 1) * 8), "r"(held.x),
+                               "r"(held.y), "r"(held.z), "r"(held.w), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w)
                                : "memory");
                 } else {
-                  *reinterpret_cast<uint4*>(dst_g + g8 * 8) = u;
+                  held = u;
                 }
+              } else {
+                *reinterpret_cast<uint4*>(dst_g + g8 * 8) = u;
               }
             }
           }
-          if (NCW > 1 && want_stats) flush(cw);
+        };
+        constexpr int T = NCW * MT;
+        uint32_t rawA[32], rawB[32];
+        issue(0, 0, rawA);
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const int cw = t / MT, mt = t % MT;
+          if (t & 1) {
+            tc::tmem_ld_wait_dep(rawB);
+            if (t + 1 < T) issue((t + 1) / MT, (t + 1) % MT, rawA);
+            process(cw, mt, rawB);
+          } else {
+            tc::tmem_ld_wait_dep(rawA);
+            if (t + 1 < T) issue((t + 1) / MT, (t + 1) % MT, rawB);
+            process(cw, mt, rawA);
+          }
+          if (NCW > 1 && want_stats && mt == MT - 1) flush(cw);
         }
         if (NCW == 1 && want_stats && ++pending == kFlush) {
           flush(0);
