@@ -778,6 +778,37 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __rest
   }
 }
 
+// the same unpacking for every filter gradient of a backward pass in ONE launch (15 launches of ~6 us of work each otherwise)
+struct UnpackTable {
+  const float* src[kPackMax];
+  float* dst[kPackMax];
+  int co[kPackMax], ci[kPackMax], cipad[kPackMax], hilo[kPackMax];
+  int cstart[kPackMax + 1];
+  int count;
+};
+__global__ void __launch_bounds__(256) unpack_wgrad_multi_kernel(const __grid_constant__ UnpackTable t, const float* __restrict__ gscale) {
+  const float inv = gscale_inv(gscale);
+  const int total = t.cstart[t.count];
+  for (int c = blockIdx.x; c < total; c += gridDim.x) {
+    int lo = 0, hi = t.count;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (t.cstart[mid] <= c) lo = mid; else hi = mid;
+    }
+    const int Ci = t.ci[lo], CiPad = t.cipad[lo], hilo = t.hilo[lo];
+    const int items = t.co[lo] * Ci * 9;
+    const float* dwp = t.src[lo];
+    float* dw = t.dst[lo];
+    const int i0 = (c - t.cstart[lo]) * kPackChunk;
+#pragma unroll 4
+    for (int i = i0 + threadIdx.x; i < min(items, i0 + kPackChunk); i += 256) {
+      const int tap = i % 9, ci = (i / 9) % Ci, co = i / (9 * Ci);
+      const float* row = dwp + ((long long)co * 9 + tap) * CiPad;
+      dw[i] = (hilo ? row[ci] + row[3 + ci] : row[ci]) * inv;
+    }
+  }
+}
+
 __global__ void cast_f64_f32_kernel(const double* __restrict__ s, float* __restrict__ d, long long n, const float* __restrict__ gscale) {
   const double inv = (double)gscale_inv(gscale);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -1038,6 +1069,25 @@ int eunet_unpack_wgrad3x3(const float* dw_packed, float* dw, int Co, int Ci, int
   EUNET_REQUIRE(Co > 0 && Ci > 0 && CiPad >= Ci && (!hilo || (Ci == 3 && CiPad >= 6)), "unpack_wgrad3x3: bad shape");
   unpack_wgrad_kernel<<<ew_grid((long long)Co * Ci * 9), 256, 0, (cudaStream_t)stream>>>(dw_packed, dw, Co, Ci, CiPad, hilo, gscale);
   return check_launch("unpack_wgrad3x3");
+}
+
+int eunet_unpack_wgrad3x3_multi(const void* const* dw_packed, void* const* dw, const int* co, const int* ci, const int* cipad,
+                                const int* hilo, int count, const float* gscale, void* stream) {
+  EUNET_REQUIRE(count > 0 && count <= kPackMax, "unpack_wgrad3x3_multi: %d tensors (max %d)", count, kPackMax);
+  UnpackTable t;
+  t.count = count;
+  t.cstart[0] = 0;
+  for (int i = 0; i < count; ++i) {
+    EUNET_REQUIRE(dw_packed[i] && dw[i] && co[i] > 0 && ci[i] > 0 && cipad[i] >= ci[i] && (!hilo[i] || (ci[i] == 3 && cipad[i] >= 6)),
+                  "unpack_wgrad3x3_multi: bad entry %d", i);
+    const long long items = (long long)co[i] * 9 * ci[i];
+    EUNET_REQUIRE(items < (1LL << 30), "unpack_wgrad3x3_multi: tensor %d too large", i);
+    t.src[i] = (const float*)dw_packed[i]; t.dst[i] = (float*)dw[i];
+    t.co[i] = co[i]; t.ci[i] = ci[i]; t.cipad[i] = cipad[i]; t.hilo[i] = hilo[i];
+    t.cstart[i + 1] = t.cstart[i] + (int)((items + kPackChunk - 1) / kPackChunk);
+  }
+  unpack_wgrad_multi_kernel<<<clamp_grid(t.cstart[count], 16), 256, 0, (cudaStream_t)stream>>>(t, gscale);
+  return check_launch("unpack_wgrad3x3_multi");
 }
 
 int eunet_cast_f64_f32(const double* src, float* dst, long long n, const float* gscale, void* stream) {

@@ -200,10 +200,30 @@ def unpack_wgrad(dwp: torch.Tensor, co: int, ci: int, hilo: bool = False, out: O
     return dw
 
 
+def unpack_wgrad_multi(items, gscale: Optional[torch.Tensor]) -> None:
+    """``items`` = [(packed gradient, destination, co, ci, hilo)]: every filter gradient of a pass in ONE launch."""
+    import ctypes
+    for i in range(0, len(items), 32):
+        part = items[i:i + 32]
+        n = len(part)
+        VP, IA = ctypes.c_void_p * n, ctypes.c_int * n
+        for dwp, dw, co, ci, _ in part:
+            assert dw.is_contiguous() and dw.numel() == co * ci * 9 and dw.dtype == torch.float32
+        call("eunet_unpack_wgrad3x3_multi", VP(*[t[0].data_ptr() for t in part]), VP(*[t[1].data_ptr() for t in part]),
+             IA(*[t[2] for t in part]), IA(*[t[3] for t in part]), IA(*[t[0].shape[2] for t in part]),
+             IA(*[int(t[4]) for t in part]), n, ptr(gscale))
+
+
 class GradSink:
     """Where ``backward`` puts parameter gradients.  The default allocates one fp32 tensor per parameter; the
     data-parallel path passes a ``parallel.FlatGradBuffer`` so that gradients land in ONE flat buffer laid out in
     production order and finished buckets can be all-reduced while the rest of backward still runs."""
+
+    def closes(self, name: str) -> bool:
+        """True when ``ready(name)`` hands gradients to a consumer that runs before backward returns (a data-parallel
+        bucket leaving).  The filter-gradient unpacks are deferred into ONE multi-tensor launch per such hand-over - a
+        single launch at the end of backward here, instead of fifteen."""
+        return False
 
     def __init__(self, device: torch.device):
         self.dev = device
@@ -445,15 +465,23 @@ def backward(sd: Dict[str, torch.Tensor], sv: Saved, dout: torch.Tensor, act_dty
     def cast64(name: str, src: torch.Tensor, shape) -> None:
         dst = sink.dst(name, shape)
         call("eunet_cast_f64_f32", ptr(src), ptr(dst), dst.numel(), ptr(gs))
-        sink.ready(name)
+        ready(name)
 
     def zero_bias(name: str, c: int) -> None:      # conv bias in front of a train-mode BN: exact zero gradient
         sink.zero_dst(name, (c,), zbias)
+        ready(name)
+
+    deferred = []          # filter gradients waiting for the next multi-tensor unpack launch
+
+    def ready(name: str) -> None:
+        if deferred and sink.closes(name):
+            unpack_wgrad_multi(deferred, gs)
+            deferred.clear()
         sink.ready(name)
 
     def wgrad_into(name: str, dwp: torch.Tensor, co: int, ci: int, hilo: bool = False) -> None:
-        unpack_wgrad(dwp, co, ci, hilo, out=sink.dst(name, (co, ci, 3, 3)), gscale=gs)
-        sink.ready(name)
+        deferred.append((dwp, sink.dst(name, (co, ci, 3, 3)), co, ci, hilo))
+        ready(name)
 
     # ---- tail ----
     M1, M2x = Ms[0], 4 * Ms[0]
@@ -520,15 +548,15 @@ def backward(sd: Dict[str, torch.Tensor], sv: Saved, dout: torch.Tensor, act_dty
                  ptr(s.scale), ptr(s.shift), ptr(s.mean), ptr(s.invstd), ptr(sums))
             call("eunet_bn_bwd_apply_pool", ptr(dact), _ld(dact), ptr(dpool), _ld(dpool), ptr(s.y), _ld(s.y), ptr(dy), _ld(dy), cx.code,
                  B, h, w, C, ptr(s.scale), ptr(s.shift), ptr(s.mean), ptr(s.invstd), ptr(sums), ptr(dg), ptr(db), ptr(gs))
-            sink.ready(name + ".weight")
-            sink.ready(name + ".bias")
+            ready(name + ".weight")
+            ready(name + ".bias")
             return dy
         call("eunet_bn_bwd_reduce", ptr(dact), _ld(dact), ptr(s.y), _ld(s.y), cx.code, M, C, ptr(s.scale), ptr(s.shift),
              ptr(s.mean), ptr(s.invstd), ptr(sums))
         call("eunet_bn_bwd_apply", ptr(dact), _ld(dact), ptr(s.y), _ld(s.y), ptr(dy), _ld(dy), cx.code, M, C, ptr(s.scale),
              ptr(s.shift), ptr(s.mean), ptr(s.invstd), ptr(sums), ptr(dg), ptr(db), ptr(gs))
-        sink.ready(name + ".weight")
-        sink.ready(name + ".bias")
+        ready(name + ".weight")
+        ready(name + ".bias")
         return dy
 
     def block_bwd(prefix: str, dact: torch.Tensor, lvl: int, cin: int, cout: int, need_dx: bool,
@@ -570,6 +598,9 @@ def backward(sd: Dict[str, torch.Tensor], sv: Saved, dout: torch.Tensor, act_dty
     dp2 = block_bwd("model.enc3", dcat4[:, 512:768], 2, 128, 256, True, dpool=dp3)
     dp1 = block_bwd("model.enc2", dcat3[:, 256:384], 1, 64, 128, True, dpool=dp2)
     block_bwd("model.enc1", dcat2[:, 128:192], 0, 3, 64, False, dpool=dp1)
+    if deferred:
+        unpack_wgrad_multi(deferred, gs)
+        deferred.clear()
     return grads
 
 

@@ -33,6 +33,7 @@ SIGNATURES = {
     "eunet_pack_input_nchw": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "eunet_pack_weight3x3": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
     "eunet_pack_weight3x3_multi": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
+    "eunet_unpack_wgrad3x3_multi": [_p, _p, _p, _p, _p, _p, _i, _p, _p],
     "eunet_unpack_wgrad3x3": [_p, _p, _i, _i, _i, _i, _p, _p],
     "eunet_conv3x3_fwd": [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p],
     "eunet_conv3x3_tail_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],

@@ -72,6 +72,7 @@ class FlatGradBuffer:
     # gradients on their way then, so that only enc1's 154 KB (the last bucket) is exchanged after the last kernel.
     LEVEL_ENDS = ("model.enc3.0.bias", "model.enc2.0.bias")
 
+
     @classmethod
     def for_model(cls, model: torch.nn.Module, bucket_bytes: int = 8 << 20, group=None) -> "FlatGradBuffer":
         from . import engine
@@ -92,6 +93,10 @@ class FlatGradBuffer:
     def zero_dst(self, name: str, shape, pool=None) -> torch.Tensor:
         """Slice for a gradient that is exactly zero: ``begin`` zeroed the whole buffer (one fill), nothing to do."""
         return self.dst(name, shape)
+
+    def closes(self, name: str) -> bool:
+        """A bucket leaves for the all-reduce when ``name`` is ready (nothing leaves early on a single rank)."""
+        return name in self._closes and world_size(self.group) > 1
 
     def ready(self, name: str) -> None:
         b = self._closes.get(name)

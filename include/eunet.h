@@ -83,6 +83,9 @@ int eunet_pack_weight3x3_multi(const void* const* w, void* const* out, const int
 /* dw_packed [Co][9][CiPad] fp32 -> dw [Co,Ci,3,3] fp32 (layout of nn.Conv2d.weight.grad); hilo: sum the x_hi / x_lo channels */
 int eunet_unpack_wgrad3x3(const float* dw_packed, float* dw, int Co, int Ci, int CiPad, int hilo, const float* gscale,
                           void* stream);
+/* the same unpacking for up to 32 filter gradients in ONE launch (all arrays have `count` entries) */
+int eunet_unpack_wgrad3x3_multi(const void* const* dw_packed, void* const* dw, const int* co, const int* ci, const int* cipad,
+                                const int* hilo, int count, const float* gscale, void* stream);
 
 /* ---- nn.Conv2d(k=3, padding=1) forward (models.py:219,222,309) and its autograd dgrad/wgrad
  * (loss.backward(), train_eval.py:338).  bf16: tcgen05/TMEM implicit GEMM with TMA-staged tiles;

@@ -328,6 +328,32 @@ def test_conv3x3_fwd_stats_and_epilogue(k, dtn, case):
     assert nerr(nchw(y2, B, H, W), want2) < TOL[dtn]
 
 
+def test_unpack_wgrad_multi_matches_single(k):
+    """eunet_unpack_wgrad3x3_multi (every filter gradient of a pass in one launch) == eunet_unpack_wgrad3x3 per tensor,
+    including the hi/lo input split of the first layer and the gradient scale."""
+    import ctypes
+    g = torch.Generator(device="cuda").manual_seed(3)
+    shapes = [(64, 3, 16, 1), (64, 3, 16, 0), (64, 64, 64, 0), (128, 192, 192, 0), (512, 256, 256, 0), (16, 48, 48, 0)]
+    gs = torch.tensor([8.0, 0.125, 0.0, 0.0], device="cuda")
+    srcs = [torch.randn(co, 9, cip, device="cuda", generator=g) for co, ci, cip, _ in shapes]
+    want = []
+    for (co, ci, cip, hilo), src in zip(shapes, srcs):
+        d = torch.empty(co, ci, 3, 3, device="cuda")
+        k.call("eunet_unpack_wgrad3x3", src.data_ptr(), d.data_ptr(), co, ci, cip, hilo, gs.data_ptr())
+        want.append(d)
+    got = [torch.full((co, ci, 3, 3), 7.0, device="cuda") for co, ci, _, _ in shapes]
+    n = len(shapes)
+    VP, IA = ctypes.c_void_p * n, ctypes.c_int * n
+    k.call("eunet_unpack_wgrad3x3_multi", VP(*[s_.data_ptr() for s_ in srcs]), VP(*[d.data_ptr() for d in got]),
+           IA(*[s_[0] for s_ in shapes]), IA(*[s_[1] for s_ in shapes]), IA(*[s_[2] for s_ in shapes]), IA(*[s_[3] for s_ in shapes]),
+           n, gs.data_ptr())
+    torch.cuda.synchronize()
+    for a_, b_ in zip(got, want):
+        assert torch.equal(a_, b_)
+    ref = srcs[2].reshape(64, 3, 3, 64).permute(0, 3, 1, 2) * 0.125
+    assert torch.equal(want[2], ref.contiguous())
+
+
 @pytest.mark.parametrize("opt", [("bn192", 1, (2, 32, 40, 64, 192)), ("bn192", 2, (1, 24, 40, 128, 384)),
                                  ("a_ahead", 0, (2, 48, 40, 192, 64)), ("a_ahead", 0, (1, 64, 64, 128, 128))])
 def test_conv3x3_alternative_configurations(k, opt):
