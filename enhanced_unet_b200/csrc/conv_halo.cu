@@ -276,6 +276,19 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         tc::tc_fence_after();
         const int gx = bx * 8 + tx;
         float part[EPI ? MT : 1][3];
+        // EPI = 1: the residual d1 of this thread's pixels is requested NOW and consumed after the accumulator chunks have been
+        // reduced (a load issued where it is used put ~1 us of HBM latency on every item of the epilogue chain)
+        float4 dres[EPI ? MT : 1];
+        if (EPI == 1 && half == 0) {
+          const long long HW = (long long)p.H * p.W;
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const int gy = by * (16 * MT) + 16 * mt + ty;
+            dres[EPI ? mt : 0] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gx < p.W && gy < p.H)
+              dres[EPI ? mt : 0] = __ldg(reinterpret_cast<const float4*>(p.d14) + (long long)b * HW + (long long)gy * p.W + gx);
+          }
+        }
         // The T = NCW x MT accumulator chunks of an item are drained through TWO register buffers: the TMEM load of chunk t+1 is
         // in flight while chunk t is converted and stored (one buffer: every chunk paid the load latency in full, and the
         // K = 576 layers - 4608 MMA clocks per item - were bound by this loop: ncu tc pipe 43-65 % busy).
@@ -379,20 +392,54 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         };
         constexpr int T = NCW * MT;
         uint32_t rawA[32], rawB[32];
-        issue(0, 0, rawA);
-#pragma unroll
-        for (int t = 0; t < T; ++t) {
-          const int cw = t / MT, mt = t % MT;
-          if (t & 1) {
-            tc::tmem_ld_wait_dep(rawB);
-            if (t + 1 < T) issue((t + 1) / MT, (t + 1) % MT, rawA);
-            process(cw, mt, rawB);
-          } else {
+        if constexpr (EPI == 1 && !TST && (MT % 2 == 0) && NCW == 1) {
+          // inference tail (nothing stored per channel): TWO tiles per pass share the per-channel constants (5 shared-memory
+          // loads per 4 channels for both) and give the scheduler two independent dot-product chains per class - with two
+          // epilogue warps per scheduler this loop is latency-bound, not issue-bound
+          const int c0 = half * CH;
+#pragma unroll 1
+          for (int mt = 0; mt < MT; mt += 2) {
+            issue(0, mt, rawA);
+            issue(0, mt + 1, rawB);
             tc::tmem_ld_wait_dep(rawA);
-            if (t + 1 < T) issue((t + 1) / MT, (t + 1) % MT, rawB);
-            process(cw, mt, rawA);
+            tc::tmem_ld_wait_dep(rawB);
+            float t[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}}, u[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+#pragma unroll
+            for (int i = 0; i < CH; i += 4) {
+              const float4 sc = *reinterpret_cast<const float4*>(&s_scale[c0 + i]), sh = *reinterpret_cast<const float4*>(&s_shift[c0 + i]);
+              const float4 w0 = *reinterpret_cast<const float4*>(&s_w3[c0 + i]), w1 = *reinterpret_cast<const float4*>(&s_w3[BN + c0 + i]);
+              const float4 w2 = *reinterpret_cast<const float4*>(&s_w3[2 * BN + c0 + i]);
+#pragma unroll
+              for (int h2 = 0; h2 < 2; ++h2) {
+                const uint32_t* raw = h2 ? rawB : rawA;
+                const float a0 = fmaxf(fmaf(__uint_as_float(raw[i]), sc.x, sh.x), 0.f), a1 = fmaxf(fmaf(__uint_as_float(raw[i + 1]), sc.y, sh.y), 0.f);
+                const float a2 = fmaxf(fmaf(__uint_as_float(raw[i + 2]), sc.z, sh.z), 0.f), a3 = fmaxf(fmaf(__uint_as_float(raw[i + 3]), sc.w, sh.w), 0.f);
+                t[h2][0] = fmaf(a2, w0.z, fmaf(a0, w0.x, t[h2][0])); u[h2][0] = fmaf(a3, w0.w, fmaf(a1, w0.y, u[h2][0]));
+                t[h2][1] = fmaf(a2, w1.z, fmaf(a0, w1.x, t[h2][1])); u[h2][1] = fmaf(a3, w1.w, fmaf(a1, w1.y, u[h2][1]));
+                t[h2][2] = fmaf(a2, w2.z, fmaf(a0, w2.x, t[h2][2])); u[h2][2] = fmaf(a3, w2.w, fmaf(a1, w2.y, u[h2][2]));
+              }
+            }
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+              for (int k3 = 0; k3 < 3; ++k3) part[EPI ? mt + h2 : 0][k3] = t[h2][k3] + u[h2][k3];
           }
-          if (NCW > 1 && want_stats && mt == MT - 1) flush(cw);
+        } else {
+          issue(0, 0, rawA);
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            const int cw = t / MT, mt = t % MT;
+            if (t & 1) {
+              tc::tmem_ld_wait_dep(rawB);
+              if (t + 1 < T) issue((t + 1) / MT, (t + 1) % MT, rawA);
+              process(cw, mt, rawB);
+            } else {
+              tc::tmem_ld_wait_dep(rawA);
+              if (t + 1 < T) issue((t + 1) / MT, (t + 1) % MT, rawB);
+              process(cw, mt, rawA);
+            }
+            if (NCW > 1 && want_stats && mt == MT - 1) flush(cw);
+          }
         }
         if (NCW == 1 && want_stats && ++pending == kFlush) {
           flush(0);
@@ -424,7 +471,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
               const int gy = by * (16 * MT) + 16 * mt + ty;
               if (gx < p.W && gy < p.H) {
                 const long long hw = (long long)gy * p.W + gx;
-                const float4 d = __ldg(reinterpret_cast<const float4*>(p.d14) + (long long)b * HW + hw);
+                const float4 d = dres[EPI ? mt : 0];
                 float* o = p.out + (long long)b * 3 * HW + hw;
                 o[0] = d.x + bb0 + (part[EPI ? mt : 0][0] + xq[mt * 96 + lane]);
                 o[HW] = d.y + bb1 + (part[EPI ? mt : 0][1] + xq[mt * 96 + 32 + lane]);
