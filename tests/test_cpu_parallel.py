@@ -40,6 +40,11 @@ def _worker(rank, world, port, tmp):
         assert len(buf.buckets) >= 3 and buf.buckets[0][0] == 0 and buf.buckets[-1][1] == buf.numel
         assert all(a[1] == b[0] for a, b in zip(buf.buckets, buf.buckets[1:]))          # contiguous, in order
         assert buf.names[0].startswith("enhance.") and buf.names[-1] == "model.enc1.0.bias"   # the tail first
+        # hand-over points for the deferred filter-gradient unpack (engine.backward): exactly the names that close a bucket
+        closing = [n for n in buf.names if buf.closes(n)]
+        assert len(closing) == len(buf.buckets) and closing[-1] == buf.names[-1]
+        assert all(n in closing for n in parallel.FlatGradBuffer.LEVEL_ENDS)
+        assert not engine.GradSink(torch.device("cpu")).closes(buf.names[-1])      # single-rank sink: one unpack at the end
         params = dict(m.named_parameters())
         g = torch.Generator().manual_seed(100 + rank)
         other = torch.Generator().manual_seed(100 + (1 - rank))
