@@ -131,31 +131,6 @@ template <bool F16> __device__ __forceinline__ uint32_t pack16x2(float lo, float
 __device__ __forceinline__ float gscale_fwd(const float* gscale) { return gscale ? __ldg(gscale) : 1.f; }
 __device__ __forceinline__ float gscale_inv(const float* gscale) { return gscale ? __ldg(gscale + 1) : 1.f; }
 
-// ---- 4 consecutive channels (8 bytes of 16-bit storage): half the registers of F8 for kernels that keep many vectors live ----
-struct F4 {
-  float v[4];
-};
-__device__ __forceinline__ F4 load4(const float* p) {
-  const float4 a = *reinterpret_cast<const float4*>(p);
-  return F4{{a.x, a.y, a.z, a.w}};
-}
-__device__ __forceinline__ F4 load4(const __half* p) {
-  const uint2 u = *reinterpret_cast<const uint2*>(p);
-  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
-  return F4{{a.x, a.y, b.x, b.y}};
-}
-__device__ __forceinline__ F4 load4(const __nv_bfloat16* p) {
-  const uint2 u = *reinterpret_cast<const uint2*>(p);
-  return F4{{__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u)}};
-}
-__device__ __forceinline__ void store4(float* p, const F4& r) { *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]); }
-__device__ __forceinline__ void store4(__half* p, const F4& r) {
-  *reinterpret_cast<uint2*>(p) = make_uint2(pack_f16x2(r.v[0], r.v[1]), pack_f16x2(r.v[2], r.v[3]));
-}
-__device__ __forceinline__ void store4(__nv_bfloat16* p, const F4& r) {
-  *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(r.v[0], r.v[1]), pack_bf16x2(r.v[2], r.v[3]));
-}
-
 __device__ __forceinline__ float to_f32(float x) { return x; }
 __device__ __forceinline__ float to_f32(__half x) { return __half2float(x); }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 x) { return __bfloat162float(x); }
