@@ -48,7 +48,12 @@ int eunet_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* smem_
  *                  (correct, but measured 1.6x slower than the single-CTA kernels on B200 - csrc/conv_halo2.cu)
  *   "tma_store"    1 (default) = Cout = 64 halo kernels write their tile with a TMA tensor store; 0 = per-thread stores
  *   "tail_out_tma" 1 (default) = TMA-pipelined tail_out_fwd / tail_bwd_reduce / tail_dec1_*; 0 = the cp.async-ring kernels
- *   "bn_tma"       1 (default) = TMA load -> transform -> TMA store bn_apply_relu; 0 = the cp.async-ring kernel */
+ *   "bn_tma"       1 (default) = TMA load -> transform -> TMA store bn_apply_relu; 0 = the cp.async-ring kernel
+ *   "a_ahead"      1 (default) = halo conv requests activation tiles as soon as their slot is free; 0 = after the previous
+ *                  chunk's last filter tap (measured equal)
+ *   "bn192"        0 (default) = off; 1 = N = 192 tiles for Cout = 192 (dgrad of dec2.0); 2 = also Cout = 384 (measured slower)
+ *   "tail_dbg"     0 (default); timing experiments on tail_bwd_fused: bit 1 skip transform, 2 skip wgrad MMAs, 4 skip U^T MMAs,
+ *                  8 skip drain (results invalid), 16 = fp32 transform arithmetic in fp16 mode (valid results) */
 int eunet_set_option(const char* name, int value);
 
 /* ---- metrics.py:12-58 (calculate_iou / calculate_dice / calculate_semantic_metrics) and the confusion
