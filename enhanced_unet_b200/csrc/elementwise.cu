@@ -218,10 +218,10 @@ __global__ void maxpool2_bwd_kernel(const T* __restrict__ dpool, int ldp, const 
 // ------------------------------------------------------------------------------------------------
 // bilinear x2 upsample, align_corners=False.  Output rows 2k / 2k+1 of input row k:
 //   out[2k]   = .25*in[k-1] + .75*in[k]   (k = 0: in[0]);   out[2k+1] = .75*in[k] + .25*in[k+1]  (k = H-1: in[H-1])
-// One thread = 8 channels of one input row k over a run of kUpSeg columns: the vertically interpolated columns
-// (top / bottom output row) slide along the row in registers, so every step costs 3 loads + 4 stores (forward) or
-// 8 loads + 1 store (adjoint) instead of 9 + 4 / 16 + 1.  Item order: channel group fastest, then k, so the threads
-// of a block share their three input rows through L1.
+// One thread = 8 channels of one input row PAIR (forward) / one input row (adjoint) over a run of kUpSeg columns: the
+// vertically interpolated columns (top / bottom output row) slide along the row in registers, so every step costs 2 loads
+// + 4 stores (forward) or 8 loads + 1 store (adjoint) instead of 9 + 4 / 16 + 1.  Item order: channel group fastest, then
+// the row, so the threads of a block share their input rows through L1.
 // ------------------------------------------------------------------------------------------------
 constexpr int kUpSeg = 8;
 
@@ -231,43 +231,47 @@ template <typename T, typename TI, bool AFF>
 __global__ void __launch_bounds__(256)
 upsample2_fwd_kernel(const TI* __restrict__ x, int ldx, T* __restrict__ out, int ldo, int B, int H, int W, int C,
                      const float* __restrict__ scale, const float* __restrict__ shift) {
+  // One item = the PAIR of input rows (kk-1, kk), kk = 0..H, which alone determines the output rows 2kk-1 and 2kk
+  //     out[2kk-1] = .75 in[kk-1] + .25 in[kk]   (kk = H: in[H-1]),      out[2kk] = .25 in[kk-1] + .75 in[kk]   (kk = 0: in[0])
+  // - two row loads (and, AFF, two BatchNorm + ReLU evaluations) per column instead of the three of a mapping by input row.
   const int G = C >> 3, nseg = (W + kUpSeg - 1) / kUpSeg;
-  const long long items = (long long)B * nseg * H * G;
+  const long long items = (long long)B * nseg * (H + 1) * G;
   const int Wo = 2 * W, Ho = 2 * H;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
     const int cg = (int)(i % G);
     long long q = i / G;
-    const int k = (int)(q % H); q /= H;
+    const int kk = (int)(q % (H + 1)); q /= (H + 1);
     const int seg = (int)(q % nseg);
     const int b = (int)(q / nseg);
     const int j0 = seg * kUpSeg, j1 = min(W, j0 + kUpSeg);
-    const float wyp = k > 0 ? 0.25f : 0.f, wyc0 = k > 0 ? 0.75f : 1.f;
-    const float wyn = k < H - 1 ? 0.25f : 0.f, wyc1 = k < H - 1 ? 0.75f : 1.f;
-    const TI* rm = x + (((long long)b * H + (k > 0 ? k - 1 : 0)) * W) * ldx + cg * 8;
-    const TI* rc = x + (((long long)b * H + k) * W) * ldx + cg * 8;
-    const TI* rp = x + (((long long)b * H + (k < H - 1 ? k + 1 : H - 1)) * W) * ldx + cg * 8;
+    const bool has0 = kk > 0, has1 = kk < H;                 // output rows 2kk-1 / 2kk exist
+    // the same products in the same order as the by-row formulas: lower row first
+    const float wl0 = has1 ? 0.75f : 1.f, wu0 = has1 ? 0.25f : 0.f;      // row 2kk-1 (kk = H: the last input row itself)
+    const float wl1 = has0 ? 0.25f : 0.f, wu1 = has0 ? 0.75f : 1.f;      // row 2kk   (kk = 0: the first input row itself)
+    const TI* rl = x + (((long long)b * H + (has0 ? kk - 1 : 0)) * W) * ldx + cg * 8;
+    const TI* ru = x + (((long long)b * H + (has1 ? kk : H - 1)) * W) * ldx + cg * 8;
     F8 sc, sh;
     if (AFF) { sc = load8(scale + cg * 8); sh = load8(shift + cg * 8); }
-    F8 p0, p1, c0, c1, n0, n1;   // vertically interpolated columns j-1, j, j+1 for output rows 2k (0) and 2k+1 (1)
+    F8 p0, p1, c0, c1, n0, n1;   // vertically interpolated columns j-1, j, j+1 for output rows 2kk-1 (0) and 2kk (1)
     auto vcol = [&](int j, F8& v0, F8& v1) {
-      F8 a = load8(rm + (long long)j * ldx), c = load8(rc + (long long)j * ldx), d = load8(rp + (long long)j * ldx);
+      F8 a = load8(rl + (long long)j * ldx), c = load8(ru + (long long)j * ldx);
       if (AFF) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           a.v[e] = fmaxf(fmaf(a.v[e], sc.v[e], sh.v[e]), 0.f);
           c.v[e] = fmaxf(fmaf(c.v[e], sc.v[e], sh.v[e]), 0.f);
-          d.v[e] = fmaxf(fmaf(d.v[e], sc.v[e], sh.v[e]), 0.f);
         }
       }
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        v0.v[e] = wyp * a.v[e] + wyc0 * c.v[e];
-        v1.v[e] = wyc1 * c.v[e] + wyn * d.v[e];
+        v0.v[e] = wl0 * a.v[e] + wu0 * c.v[e];
+        v1.v[e] = wl1 * a.v[e] + wu1 * c.v[e];
       }
     };
     vcol(j0 > 0 ? j0 - 1 : 0, p0, p1);
     vcol(j0, c0, c1);
-    T* o = out + (((long long)b * Ho + 2 * k) * Wo + 2 * j0) * ldo + cg * 8;
+    // rows 2kk-1 and 2kk are adjacent; for kk = 0 the pointer of the (missing) upper row is never dereferenced
+    T* o = out + (((long long)b * Ho + (2 * kk - 1)) * Wo + 2 * j0) * ldo + cg * 8;
 #pragma unroll 2
     for (int j = j0; j < j1; ++j) {
       vcol(j < W - 1 ? j + 1 : W - 1, n0, n1);
@@ -281,19 +285,20 @@ upsample2_fwd_kernel(const TI* __restrict__ x, int ldx, T* __restrict__ out, int
         o10.v[e] = wl * p1.v[e] + wc0 * c1.v[e];
         o11.v[e] = wc1 * c1.v[e] + wr * n1.v[e];
       }
-      store8(o, o00);
-      store8(o + ldo, o01);
-      store8(o + (long long)Wo * ldo, o10);
-      store8(o + (long long)Wo * ldo + ldo, o11);
+      if (has0) {
+        store8(o, o00);
+        store8(o + ldo, o01);
+      }
+      if (has1) {
+        store8(o + (long long)Wo * ldo, o10);
+        store8(o + (long long)Wo * ldo + ldo, o11);
+      }
       o += 2 * (long long)ldo;
       p0 = c0; p1 = c1; c0 = n0; c1 = n1;
     }
   }
 }
 
-// adjoint: input pixel (k,j) gathers output rows 2k-1..2k+2 / columns 2j-1..2j+2 with weights [.25,.75,.75,.25]
-// (at an edge the missing outer sample drops out and the inner weight becomes 1).  The vertically reduced output
-// columns 2j-1, 2j are carried over from the previous step.
 template <typename T>
 __global__ void __launch_bounds__(256)
 upsample2_bwd_kernel(const T* __restrict__ dout, int ldo, T* __restrict__ dx, int ldx, int B, int H, int W, int C) {
@@ -998,7 +1003,7 @@ int eunet_maxpool2_bwd(const void* dpool, int ldp, const void* x, int ldx, void*
 int eunet_upsample2_fwd(const void* x, int ldx, void* out, int ldo, int dtype, int B, int H, int W, int C, void* stream) {
   if (check_vec(x, ldx, C, "upsample2_fwd(x)") || check_vec(out, ldo, C, "upsample2_fwd(out)")) return -1;
   EUNET_REQUIRE(B > 0 && H > 0 && W > 0, "upsample2_fwd: empty tensor");
-  const long long items = (long long)B * H * ((W + kUpSeg - 1) / kUpSeg) * (C / 8);
+  const long long items = (long long)B * (H + 1) * ((W + kUpSeg - 1) / kUpSeg) * (C / 8);
   DISPATCH_DTYPE(dtype, upsample2_fwd_kernel<T, T, false><<<ew_grid(items), 256, 0, (cudaStream_t)stream>>>(
                             (const T*)x, ldx, (T*)out, ldo, B, H, W, C, nullptr, nullptr));
   return check_launch("upsample2_fwd");
@@ -1008,7 +1013,7 @@ int eunet_bn_apply_relu_upsample2(const void* y, int ldy, void* out, int ldo, in
                                   const float* scale, const float* shift, void* stream) {
   if (check_vec(y, ldy, C, "bn_apply_relu_upsample2(y)") || check_vec(out, ldo, C, "bn_apply_relu_upsample2(out)")) return -1;
   EUNET_REQUIRE(B > 0 && H > 0 && W > 0 && scale && shift, "bn_apply_relu_upsample2: bad arguments");
-  const long long items = (long long)B * H * ((W + kUpSeg - 1) / kUpSeg) * (C / 8);
+  const long long items = (long long)B * (H + 1) * ((W + kUpSeg - 1) / kUpSeg) * (C / 8);
   DISPATCH_DTYPE(dtype, upsample2_fwd_kernel<T, TY, true><<<ew_grid(items), 256, 0, (cudaStream_t)stream>>>(
                             (const TY*)y, ldy, (T*)out, ldo, B, H, W, C, scale, shift));
   return check_launch("bn_apply_relu_upsample2");
